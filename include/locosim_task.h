@@ -1,0 +1,45 @@
+/*
+ * TaskSpec wire format: everything of LocoEnv.step()/reset() that is not mj_step, flattened.
+ *
+ * Replaces (reference file:line):
+ *   observation gather   mushroom ObservationHelper._build_obs driven by the env's observation_spec
+ *                        (unitreeA1.py:778-835, base_humanoid.py:292-391, atlas.py:485-562, talos.py:523-598)
+ *                        + LocoEnv._create_observation (base.py:584-604; unitreeA1.py:454-476,722-753)
+ *   termination          LocoEnv.is_absorbing -> _has_fallen (base.py:243-255; unitreeA1.py:503-536;
+ *                        base_humanoid.py:129-180; atlas.py:366-418; talos.py:356-405)
+ *   reward               utils/reward.py:34-117 via LocoEnv.reward (base.py:170-176)
+ *   action scaling       LocoEnv._preprocess_action (base.py:606-621, 121-126)
+ *   reset                LocoEnv.reset/setup/set_sim_state + Trajectory.reset_trajectory
+ *                        (base.py:178-241,478-497; utils/trajectory.py:236-273)
+ *
+ * Two blobs (int32 / float64): header then arrays, tightly packed, in the order below.
+ */
+#ifndef LOCOSIM_TASK_H
+#define LOCOSIM_TASK_H
+
+#define LOCOSIM_TASK_MAGIC 0x5441534B
+#define LOCOSIM_TASK_VERSION 1
+
+enum {
+  TKI_MAGIC = 0, TKI_VERSION, TKI_OBS_DIM, TKI_N_DONE, TKI_REWARD_TYPE, TKI_N_SUBSTEPS, TKI_N_TRAJ, TKI_TRAJ_LEN,
+  TKI_N_GOAL, TKI_RECENTER0, TKI_RECENTER1, TKI_REWARD_I0, TKI_REWARD_I1, TKI_REWARD_I2, TKI_REWARD_I3,
+  TKI_USE_ABSORBING,
+  TKI_HEADER_LEN = 16
+};
+/* int arrays after the header: obs_src_type[obs_dim], obs_src_idx[obs_dim], done_obs_idx[n_done] */
+
+enum { TKR_REWARD_P0 = 0, TKR_REWARD_P1, TKR_HEADER_LEN = 8 };
+/* real arrays after the header: act_mean[nu], act_delta[nu], done_lo[n_done], done_hi[n_done],
+ *                               traj_table[n_traj][traj_len][nq + nv + n_goal]                      */
+
+/* obs_src_type */
+enum { LS_OBS_QPOS = 0, LS_OBS_QVEL = 1, LS_OBS_GOAL = 2 };
+/* reward types (utils/reward.py) */
+enum {
+  LS_REWARD_NONE = 0,            /* NoReward :34 */
+  LS_REWARD_TARGET_VELOCITY = 1, /* TargetVelocityReward :66   exp(-(prev_obs[i0]-p0)^2) */
+  LS_REWARD_VELOCITY_VECTOR = 2, /* VelocityVectorReward :100  exp(-5*|v_xy - goal*[cos,sin]|), i0=x i1=y i2=cos idx i3=goal idx */
+  LS_REWARD_POS = 3              /* PosReward :44  prev_obs[i0] */
+};
+
+#endif
