@@ -1,0 +1,78 @@
+/*
+ * locosim C-ABI: the drop-in boundary of the B200 batched LocoEnv.step() engine.
+ *
+ * The reference has no FFI: its hot path is reached through the Python class hierarchy
+ *   LocoEnv.step/reset                      /root/reference/loco_mujoco/environments/base.py:25,178-203 (step inherited
+ *                                           from mushroom_rl MultiMuJoCo -> mujoco.mj_step, parameters base.py:32-33,109-111)
+ *   GymnasiumWrapper.step/reset             /root/reference/loco_mujoco/environments/gymnasium.py:47-77
+ * Each entry point below names the reference call it replaces. The Python facade
+ * (loco_mujoco_b200/environments/base.py) binds these with ctypes; INTEGRATION.md shows the stub a maintainer of the
+ * reference would add.
+ *
+ * Conventions: plain pointers + sizes, no C++/torch types. All `d_*` pointers are DEVICE pointers owned by the
+ * caller (e.g. torch.cuda tensors), row-major, env-major ([n_envs, dim]). All work is enqueued on `stream`
+ * (a cudaStream_t passed as void*; NULL = default stream); calls are CUDA-graph capturable; no allocation happens
+ * in step/reset. Return value: 0 = OK, non-zero = error, message via locosim_last_error(). Never throws.
+ * One handle per device; calls on one handle must be externally serialised.
+ */
+#ifndef LOCOSIM_H
+#define LOCOSIM_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct locosim_handle locosim_t;
+
+/* Replaces LocoEnv.__init__ -> MultiMuJoCo.__init__ (model compile + MjData) and load_trajectory
+ * (base.py:31-143,145-168).  `model_*`: ModelPack blobs (include/locosim_modelpack.h); `task_*`: TaskSpec blobs
+ * (include/locosim_task.h).  env_id_offset: global index of this shard's first env (multi-GPU sharding keeps the
+ * per-env random streams identical to the single-GPU run). */
+int locosim_create(const int32_t* model_ints, int n_model_ints, const double* model_reals, int n_model_reals,
+                   const int32_t* task_ints, int n_task_ints, const double* task_reals, int n_task_reals,
+                   int n_envs, int device, uint64_t seed, int64_t env_id_offset, locosim_t** out);
+void locosim_destroy(locosim_t* h);
+const char* locosim_last_error(const locosim_t* h);   /* h may be NULL: error of the last failed create */
+
+int locosim_num_envs(const locosim_t* h);
+int locosim_obs_dim(const locosim_t* h);
+int locosim_action_dim(const locosim_t* h);
+int locosim_nq(const locosim_t* h);
+
+/* Newton-solver controls of the fp32 engine (defaults: tolerance 1e-5, ls_tolerance 0.01, max_iter 20, ls_iter 16) */
+int locosim_set_solver(locosim_t* h, float tolerance, float ls_tolerance, int max_iter, int ls_iter);
+
+/* Replaces LocoEnv.reset() (base.py:178-203 -> setup :205-241 -> Trajectory.reset_trajectory trajectory.py:236-273
+ * -> set_sim_state :478-497).  d_mask: uint8 [n_envs] (NULL = all).  Draws (traj, sample) per env from the
+ * counter-based stream unless d_traj_no / d_step_no (int32 [n_envs], may be NULL) pin them.  Writes the reset
+ * observation to d_obs ([n_envs, obs_dim], may be NULL). */
+int locosim_reset(locosim_t* h, const uint8_t* d_mask, const int32_t* d_traj_no, const int32_t* d_step_no, float* d_obs,
+                  void* stream);
+
+/* Replaces LocoEnv.step(action) (mushroom MuJoCo.step: _preprocess_action base.py:606-621, n_substeps x mj_step,
+ * _create_observation :584-604, is_absorbing :243-255, reward :170-176) for every env of the batch, followed by an
+ * in-kernel auto-reset of the envs that terminated.
+ *   d_action   [n_envs, action_dim] in [-1, 1]
+ *   d_obs      [n_envs, obs_dim]   observation after the step (the terminal observation for envs with done=1)
+ *   d_reward   [n_envs]
+ *   d_done     [n_envs] uint8      absorbing flag (has_fallen, or non-finite state)
+ *   d_next_obs [n_envs, obs_dim]   observation to act on next (== d_obs unless done, then the reset observation); may be NULL
+ * auto_reset: 0 leaves terminated envs in their terminal state (caller resets with locosim_reset). */
+int locosim_step(locosim_t* h, const float* d_action, float* d_obs, float* d_reward, uint8_t* d_done, float* d_next_obs,
+                 int auto_reset, void* stream);
+
+/* State access (LocoEnv.set_sim_state base.py:478-497 / data.qpos, data.qvel). fp32 [n_envs, nq]. */
+int locosim_get_state(locosim_t* h, float* d_qpos, float* d_qvel, float* d_qacc_warmstart, void* stream);
+int locosim_set_state(locosim_t* h, const float* d_qpos, const float* d_qvel, const float* d_qacc_warmstart, void* stream);
+
+/* Diagnostics: per-env counters since create: [0]=env steps, [1]=resets, [2]=solver iterations of the last sub-step,
+ * [3]=contacts of the last sub-step.  d_out int32 [n_envs, 4]. */
+int locosim_get_counters(locosim_t* h, int32_t* d_out, void* stream);
+
+/* Launch geometry chosen for this handle: warps(envs) per block, dynamic shared memory bytes per block, blocks. */
+int locosim_launch_info(const locosim_t* h, int* warps_per_block, int* smem_bytes, int* n_blocks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

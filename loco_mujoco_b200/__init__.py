@@ -1,1 +1,15 @@
+"""
+loco_mujoco_b200: B200-native batched `LocoEnv.step()`.
+
+    from loco_mujoco_b200 import LocoEnv
+    env = LocoEnv.make("UnitreeA1.simple", num_envs=4096)      # batched, torch.cuda tensors
+    env = LocoEnv.make("UnitreeA1.simple")                     # drop-in single env, numpy float64
+"""
 __version__ = "0.1.0"
+
+from .environments import LocoEnv
+from .environments.gymnasium import GymnasiumWrapper, make_gym
+
+
+def get_all_task_names():
+    return LocoEnv.get_all_task_names()

@@ -1,0 +1,354 @@
+// locosim.cu -- CUDA engine + C-ABI (include/locosim.h) of the batched LocoEnv.step() hot path, sm_100a.
+//
+// One fused kernel per control step: load state (HBM, env-major, coalesced per warp) -> n_substeps x
+// [kinematics, CRB, collision, constraint assembly, Newton solve, integrate] entirely in shared memory ->
+// observation gather + has_fallen + reward -> in-kernel auto-reset from the trajectory table -> store.
+// See locosim_core.cuh for the per-warp algorithm and DESIGN.md for the layout / roofline accounting.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/locosim.h"
+#include "locosim_config.h"
+#include "locosim_host.h"
+
+// ----------------------------------------------------------------------------------------------------------
+struct EngineState {
+  float *qpos, *qvel, *ws, *goal;   // [N,nv] [N,nv] [N,nv] [N,4]
+  int* episode;                     // [N] reset counter (drives the per-env random stream)
+  int* counters;                    // [N,4]
+};
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+// counter-based draw of (trajectory, sample) for reset number `episode` of global env `genv`
+__device__ __forceinline__ void draw_reset(uint64_t seed, int64_t genv, int episode, int n_traj, int traj_len, int* traj,
+                                           int* step) {
+  uint64_t r = mix64(seed ^ mix64((uint64_t)genv * 0x100000001B3ULL + (uint64_t)(uint32_t)episode));
+  *traj = (int)((r & 0xffffffffULL) % (uint64_t)n_traj);
+  *step = (int)((r >> 32) % (uint64_t)traj_len);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// reset kernel: one warp per env, no shared memory
+// ----------------------------------------------------------------------------------------------------------
+__global__ void reset_kernel(DevModel m, DevTask t, EngineState st, const uint8_t* mask, const int* traj_no,
+                             const int* step_no, float* obs, int n_envs, uint64_t seed, int64_t env_off) {
+  int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (env >= n_envs) return;
+  if (mask && !mask[env]) return;
+  const int nv = m.nv, ncol = 2 * nv + t.n_goal;
+  int tr, sp;
+  int ep = st.episode[env];
+  draw_reset(seed, env_off + env, ep, t.n_traj, t.traj_len, &tr, &sp);
+  if (traj_no) tr = traj_no[env];
+  if (step_no) sp = step_no[env];
+  const float* row = t.table + ((size_t)tr * t.traj_len + sp) * ncol;
+  for (int i = lane; i < nv; i += 32) {
+    float q = row[i];
+    if (i == t.recenter0 || i == t.recenter1) q = 0;
+    st.qpos[(size_t)env * nv + i] = q;
+    st.qvel[(size_t)env * nv + i] = row[nv + i];
+    st.ws[(size_t)env * nv + i] = 0;
+  }
+  for (int k = lane; k < t.n_goal; k += 32) st.goal[(size_t)env * 4 + k] = row[2 * nv + k];
+  if (obs) {
+    for (int k = lane; k < t.obs_dim; k += 32) {
+      int idx = t.obs_src_idx[k], ty = t.obs_src_type[k];
+      float v;
+      if (ty == LS_OBS_QPOS) v = (idx == t.recenter0 || idx == t.recenter1) ? 0.0f : row[idx];
+      else if (ty == LS_OBS_QVEL) v = row[nv + idx];
+      else v = row[2 * nv + idx];
+      obs[(size_t)env * t.obs_dim + k] = v;
+    }
+  }
+  if (lane == 0) { st.episode[env] = ep + 1; st.counters[(size_t)env * 4 + 1] += 1; }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// step kernel: one warp per env, EnvS in dynamic shared memory
+// ----------------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(128) step_kernel(DevModel m, DevTask t, SolverOpts so, EngineState st,
+                                                    const float* __restrict__ action, float* __restrict__ obs,
+                                                    float* __restrict__ reward, uint8_t* __restrict__ done,
+                                                    float* __restrict__ next_obs, int n_envs, int auto_reset,
+                                                    uint64_t seed, int64_t env_off) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (env >= n_envs) return;
+  EnvS<C>& e = reinterpret_cast<EnvS<C>*>(smem_raw)[warp];
+  const int nv = m.nv, nu = m.nu, D = t.obs_dim;
+
+  // ---- load state ----
+  for (int i = lane; i < nv; i += 32) {
+    e.qpos[i] = st.qpos[(size_t)env * nv + i];
+    e.qvel[i] = st.qvel[(size_t)env * nv + i];
+    e.qacc_ws[i] = st.ws[(size_t)env * nv + i];
+    e.qacc[i] = 0;
+  }
+  for (int i = lane; i < nu; i += 32) e.ctrl[i] = action[(size_t)env * nu + i] * t.act_delta[i] + t.act_mean[i];
+  if (lane < 4) e.goal[lane] = st.goal[(size_t)env * 4 + lane];
+  __syncwarp();
+  for (int k = lane; k < D; k += 32) e.obs_prev[k] = obs_value(t, e, k);
+  __syncwarp();
+
+  // ---- physics ----
+  physics_substeps(m, e, so, t.n_substeps);
+
+  // ---- observation, termination, reward ----
+  bool bad = false;
+  for (int i = lane; i < nv; i += 32) bad |= !(isfinite(e.qpos[i]) && isfinite(e.qvel[i]));
+  bool fallen = false;
+  for (int k = lane; k < t.n_done; k += 32) {
+    float v = obs_value(t, e, t.done_obs_idx[k]);
+    fallen |= (v < t.done_lo[k]) || (v > t.done_hi[k]);
+  }
+  bad = __any_sync(0xffffffffu, bad);
+  fallen = __any_sync(0xffffffffu, fallen) && t.use_absorbing;
+  const bool is_done = fallen || bad;
+  for (int k = lane; k < D; k += 32) {
+    float v = obs_value(t, e, k);
+    if (bad) v = 0.0f;
+    obs[(size_t)env * D + k] = v;
+  }
+  if (lane == 0) {
+    float r = 0;
+    const float* p = e.obs_prev;
+    if (t.reward_type == LS_REWARD_TARGET_VELOCITY) { float d = p[t.ri[0]] - t.rp[0]; r = expf(-d * d); }
+    else if (t.reward_type == LS_REWARD_VELOCITY_VECTOR) {
+      float g = p[t.ri[3]];
+      float dx = p[t.ri[0]] - g * p[t.ri[2]], dy = p[t.ri[1]] - g * p[t.ri[2] + 1];
+      r = expf(-5.0f * sqrtf(dx * dx + dy * dy));
+    } else if (t.reward_type == LS_REWARD_POS) r = p[t.ri[0]];
+    reward[env] = r;
+    done[env] = is_done ? 1 : 0;
+    int* cnt = st.counters + (size_t)env * 4;
+    cnt[0] += 1; cnt[2] = e.solver_iter; cnt[3] = e.ncon;
+  }
+
+  // ---- auto-reset ----
+  if (is_done && (auto_reset || bad)) {
+    int ep = st.episode[env];
+    int tr, sp;
+    draw_reset(seed, env_off + env, ep, t.n_traj, t.traj_len, &tr, &sp);
+    __syncwarp();
+    reset_env(m, t, e, tr, sp);
+    if (lane == 0) { st.episode[env] = ep + 1; st.counters[(size_t)env * 4 + 1] += 1; }
+    for (int k = lane; k < t.n_goal; k += 32) st.goal[(size_t)env * 4 + k] = e.goal[k];
+  }
+  if (next_obs) for (int k = lane; k < D; k += 32) next_obs[(size_t)env * D + k] = obs_value(t, e, k);
+
+  // ---- store state ----
+  for (int i = lane; i < nv; i += 32) {
+    st.qpos[(size_t)env * nv + i] = e.qpos[i];
+    st.qvel[(size_t)env * nv + i] = e.qvel[i];
+    st.ws[(size_t)env * nv + i] = e.qacc_ws[i];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// handle
+// ----------------------------------------------------------------------------------------------------------
+struct locosim_handle {
+  int device = 0, n_envs = 0, cfg = -1, wpb = 4, smem = 0;
+  uint64_t seed = 0;
+  int64_t env_off = 0;
+  HostModel hm;
+  HostTask ht;
+  DevModel dm;
+  DevTask dt;
+  SolverOpts so;
+  EngineState st;
+  int* d_mints = nullptr; float* d_mreals = nullptr; int* d_tints = nullptr; float* d_treals = nullptr;
+  std::string err;
+};
+static std::string g_create_error;
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t _e = (call);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                    \
+      return 1;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+template <class C>
+static bool cfg_fits(const HostModel& hm, const HostTask& ht) {
+  return hm.nv <= C::NV && hm.nb <= C::NB && hm.ng <= C::NG && ht.obs_dim <= C::MAXOBS;
+}
+template <class C>
+static int cfg_smem() { return (int)sizeof(EnvS<C>); }
+
+template <class C>
+static int launch_step(locosim_handle* h, const float* a, float* o, float* r, uint8_t* d, float* no, int auto_reset,
+                       cudaStream_t s) {
+  int blocks = (h->n_envs + h->wpb - 1) / h->wpb;
+  step_kernel<C><<<blocks, h->wpb * 32, h->smem, s>>>(h->dm, h->dt, h->so, h->st, a, o, r, d, no, h->n_envs, auto_reset,
+                                                      h->seed, h->env_off);
+  CK(cudaGetLastError());
+  return 0;
+}
+template <class C>
+static int setup_cfg(locosim_handle* h) {
+  int per_env = cfg_smem<C>();
+  int dev_max = 0;
+  CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+  int sm_total = 0;
+  CK(cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
+  // choose warps/block in {1..4} maximising resident envs per SM (1 KB/block reserved by the driver)
+  int best = 1, best_env = 0;
+  for (int w = 1; w <= 4; w++) {
+    int sm = w * per_env;
+    if (sm > dev_max) break;
+    int blocks_per_sm = sm_total / (sm + 1024);
+    if (blocks_per_sm > 32) blocks_per_sm = 32;
+    int envs = blocks_per_sm * w;
+    if (envs >= best_env) { best_env = envs; best = w; }
+  }
+  h->wpb = best;
+  h->smem = best * per_env;
+  CK(cudaFuncSetAttribute(step_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+  return 0;
+}
+
+extern "C" {
+
+const char* locosim_last_error(const locosim_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const int32_t* ti, int nti, const double* tr,
+                   int ntr, int n_envs, int device, uint64_t seed, int64_t env_off, locosim_t** out) {
+  locosim_handle* h = new locosim_handle();
+  *out = nullptr;
+  auto fail = [&](const std::string& msg) { g_create_error = msg; delete h; return 1; };
+  if (n_envs <= 0) return fail("n_envs must be positive");
+  std::string err = parse_model(h->hm, mi, nmi, mr, nmr);
+  if (!err.empty()) return fail(err);
+  err = parse_task(h->ht, h->hm.nu, h->hm.nv, ti, nti, tr, ntr);
+  if (!err.empty()) return fail(err);
+  if (h->hm.nu > h->hm.nv) return fail("nu > nv");
+  h->device = device; h->n_envs = n_envs; h->seed = seed; h->env_off = env_off;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) return fail(std::string("no CUDA device: ") + cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail("bad device index");
+  ce = cudaSetDevice(device);
+  if (ce != cudaSuccess) return fail(cudaGetErrorString(ce));
+  if (cfg_fits<CfgA1>(h->hm, h->ht)) h->cfg = 0;
+  else if (cfg_fits<CfgAtlas>(h->hm, h->ht)) h->cfg = 1;
+  else if (cfg_fits<CfgTalos>(h->hm, h->ht)) h->cfg = 2;
+  else if (cfg_fits<CfgHumanoid>(h->hm, h->ht)) h->cfg = 3;
+  else return fail("model exceeds the compiled capacity configurations (locosim_config.h)");
+  h->so.tolerance = 1e-5f; h->so.ls_tolerance = 0.01f; h->so.ls_iter = 16;
+  h->so.max_iter = h->hm.iterations < 20 ? h->hm.iterations : 20;
+  auto up = [&](void** dst, const void* src, size_t bytes) -> bool {
+    if (cudaMalloc(dst, bytes ? bytes : 4) != cudaSuccess) return false;
+    if (bytes && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    return true;
+  };
+  bool ok = up((void**)&h->d_mints, h->hm.ints.data(), h->hm.ints.size() * 4) &&
+            up((void**)&h->d_mreals, h->hm.reals.data(), h->hm.reals.size() * 4) &&
+            up((void**)&h->d_tints, h->ht.ints.data(), h->ht.ints.size() * 4) &&
+            up((void**)&h->d_treals, h->ht.reals.data(), h->ht.reals.size() * 4);
+  size_t N = (size_t)n_envs, nv = (size_t)h->hm.nv;
+  ok = ok && cudaMalloc((void**)&h->st.qpos, N * nv * 4) == cudaSuccess && cudaMalloc((void**)&h->st.qvel, N * nv * 4) == cudaSuccess &&
+       cudaMalloc((void**)&h->st.ws, N * nv * 4) == cudaSuccess && cudaMalloc((void**)&h->st.goal, N * 4 * 4) == cudaSuccess &&
+       cudaMalloc((void**)&h->st.episode, N * 4) == cudaSuccess && cudaMalloc((void**)&h->st.counters, N * 16) == cudaSuccess;
+  if (!ok) { std::string m = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); locosim_destroy(h); g_create_error = m; return 1; }
+  cudaMemset(h->st.qpos, 0, N * nv * 4); cudaMemset(h->st.qvel, 0, N * nv * 4); cudaMemset(h->st.ws, 0, N * nv * 4);
+  cudaMemset(h->st.goal, 0, N * 16); cudaMemset(h->st.episode, 0, N * 4); cudaMemset(h->st.counters, 0, N * 16);
+  bind_model(h->dm, h->hm, h->d_mints, h->d_mreals);
+  bind_task(h->dt, h->ht, h->hm.nu, h->d_tints, h->d_treals);
+  int rc = 0;
+  switch (h->cfg) {
+    case 0: rc = setup_cfg<CfgA1>(h); break;
+    case 1: rc = setup_cfg<CfgAtlas>(h); break;
+    case 2: rc = setup_cfg<CfgTalos>(h); break;
+    default: rc = setup_cfg<CfgHumanoid>(h); break;
+  }
+  if (rc) { g_create_error = h->err; locosim_destroy(h); return 1; }
+  *out = h;
+  return 0;
+}
+
+void locosim_destroy(locosim_t* h) {
+  if (!h) return;
+  cudaFree(h->d_mints); cudaFree(h->d_mreals); cudaFree(h->d_tints); cudaFree(h->d_treals);
+  cudaFree(h->st.qpos); cudaFree(h->st.qvel); cudaFree(h->st.ws); cudaFree(h->st.goal); cudaFree(h->st.episode);
+  cudaFree(h->st.counters);
+  delete h;
+}
+
+int locosim_num_envs(const locosim_t* h) { return h->n_envs; }
+int locosim_obs_dim(const locosim_t* h) { return h->ht.obs_dim; }
+int locosim_action_dim(const locosim_t* h) { return h->hm.nu; }
+int locosim_nq(const locosim_t* h) { return h->hm.nv; }
+
+int locosim_set_solver(locosim_t* h, float tol, float ls_tol, int max_iter, int ls_iter) {
+  if (tol <= 0 || ls_tol <= 0 || max_iter < 1 || ls_iter < 1) { h->err = "bad solver options"; return 1; }
+  h->so.tolerance = tol; h->so.ls_tolerance = ls_tol; h->so.max_iter = max_iter; h->so.ls_iter = ls_iter;
+  return 0;
+}
+
+int locosim_reset(locosim_t* h, const uint8_t* d_mask, const int32_t* d_traj, const int32_t* d_step, float* d_obs,
+                  void* stream) {
+  CK(cudaSetDevice(h->device));
+  int threads = 128, blocks = (h->n_envs * 32 + threads - 1) / threads;
+  reset_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(h->dm, h->dt, h->st, d_mask, d_traj, d_step, d_obs, h->n_envs,
+                                                             h->seed, h->env_off);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int locosim_step(locosim_t* h, const float* a, float* o, float* r, uint8_t* d, float* no, int auto_reset, void* stream) {
+  if (!a || !o || !r || !d) { h->err = "null buffer"; return 1; }
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (h->cfg) {
+    case 0: return launch_step<CfgA1>(h, a, o, r, d, no, auto_reset, s);
+    case 1: return launch_step<CfgAtlas>(h, a, o, r, d, no, auto_reset, s);
+    case 2: return launch_step<CfgTalos>(h, a, o, r, d, no, auto_reset, s);
+    default: return launch_step<CfgHumanoid>(h, a, o, r, d, no, auto_reset, s);
+  }
+}
+
+int locosim_get_state(locosim_t* h, float* q, float* v, float* w, void* stream) {
+  size_t bytes = (size_t)h->n_envs * h->hm.nv * 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (q) CK(cudaMemcpyAsync(q, h->st.qpos, bytes, cudaMemcpyDeviceToDevice, s));
+  if (v) CK(cudaMemcpyAsync(v, h->st.qvel, bytes, cudaMemcpyDeviceToDevice, s));
+  if (w) CK(cudaMemcpyAsync(w, h->st.ws, bytes, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+int locosim_set_state(locosim_t* h, const float* q, const float* v, const float* w, void* stream) {
+  size_t bytes = (size_t)h->n_envs * h->hm.nv * 4;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (q) CK(cudaMemcpyAsync(h->st.qpos, q, bytes, cudaMemcpyDeviceToDevice, s));
+  if (v) CK(cudaMemcpyAsync(h->st.qvel, v, bytes, cudaMemcpyDeviceToDevice, s));
+  if (w) CK(cudaMemcpyAsync(h->st.ws, w, bytes, cudaMemcpyDeviceToDevice, s));
+  else CK(cudaMemsetAsync(h->st.ws, 0, bytes, s));
+  return 0;
+}
+int locosim_get_counters(locosim_t* h, int32_t* d_out, void* stream) {
+  CK(cudaMemcpyAsync(d_out, h->st.counters, (size_t)h->n_envs * 16, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+int locosim_launch_info(const locosim_t* h, int* wpb, int* smem, int* blocks) {
+  if (wpb) *wpb = h->wpb;
+  if (smem) *smem = h->smem;
+  if (blocks) *blocks = (h->n_envs + h->wpb - 1) / h->wpb;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1400 @@
+// locosim_core.cuh -- warp-per-environment rigid-body + soft-contact step, fp32, sm_100a.
+//
+// One warp owns one environment for the whole control step (n_substeps physics steps + observation /
+// reward / termination / auto-reset); all per-env state lives in shared memory (struct EnvS) and never
+// touches HBM between the initial load and the final store.  Loops whose iterations are independent are
+// strided over the 32 lanes (PAR_FOR) and separated by __syncwarp(); scalar control flow (solver iterations,
+// line-search bracketing) is warp-uniform because every reduction is an all-lanes butterfly.
+//
+// What is computed is the reference's LocoEnv.step() hot path: mushroom_rl MuJoCo.step ->
+// mujoco.mj_step(model, data, n_substeps) (/root/reference/loco_mujoco/environments/base.py:25,32-33,109-111)
+// plus the hooks listed in include/locosim_task.h.  The algorithmic spec is MuJoCo 2.3.7's mj_step pipeline;
+// the fp64 restatement that pins it against the reference's golden rollouts is oracle/locosim_ref.c (test only).
+//
+// The same source compiles as a *serial emulation* with -DLS_EMULATE (lanes executed one after another):
+// a development aid to debug numerics on a CPU-only box; it is never part of the product path.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/locosim_modelpack.h"
+#include "../../include/locosim_task.h"
+
+#ifdef LS_EMULATE
+#define LS_DEV static inline
+#define PAR_FOR(i, n) for (int i = 0; i < (n); i++)
+#define SYNC() ((void)0)
+#define WARP_SUM(x) (x)
+#define WARP_MIN(x) (x)
+#define LANE0
+#define LS_LANE 0
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+#else
+#define LS_DEV __device__ __forceinline__
+#define PAR_FOR(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
+#define SYNC() __syncwarp()
+#define WARP_SUM(x) warp_sum(x)
+#define LANE0 if ((threadIdx.x & 31) == 0)
+#define LS_LANE ((int)(threadIdx.x & 31))
+LS_DEV float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+#endif
+
+#define LS_MINVAL 1e-15f
+#define LS_MINIMP 0.0001f
+#define LS_MAXIMP 0.9999f
+
+enum { ROW_FRICTION = 1, ROW_LIMIT = 3, ROW_CON_FRICTIONLESS = 5, ROW_CON_PYRAMIDAL = 6, ROW_CON_ELLIPTIC = 7 };
+enum { ST_SATISFIED = 0, ST_QUADRATIC = 1, ST_LINEARNEG = 2, ST_LINEARPOS = 3, ST_CONE = 4 };
+
+// ----------------------------------------------------------------------------------------------------------
+// device-side model view: pointers into the fp32 / int32 device copies of the ModelPack blobs
+// ----------------------------------------------------------------------------------------------------------
+struct DevModel {
+  int nb, nv, ng, nu, np, nm, integrator, cone, iterations, nlevel, nfric;
+  float timestep, gravity[3], impratio, tolerance, meaninertia;
+  int has_damping;
+#define X(name, cnt) const int* name;
+  LOCOSIM_MP_INT_FIELDS(X)
+#undef X
+#define X(name, cnt) const float* name;
+  LOCOSIM_MP_REAL_FIELDS(X)
+#undef X
+  // engine-only derived tables (built in locosim.cu from the ModelPack)
+  const int* body_level;     // [nb] depth in the tree (world = 0)
+  const int* body_dofmask;   // [nb] bit d set if dof d is on the path root..body
+  const int* dof_frow;       // [nv] index of the frictionloss row of dof d, or -1
+};
+
+struct DevTask {
+  int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter0, recenter1, ri[4], use_absorbing;
+  float rp[2];
+  const int *obs_src_type, *obs_src_idx, *done_obs_idx;
+  const float *act_mean, *act_delta, *done_lo, *done_hi, *table;
+};
+
+struct SolverOpts {
+  float tolerance;     // Newton termination (scaled improvement / gradient), fp32-appropriate
+  float ls_tolerance;  // relative line-search gradient tolerance
+  int max_iter;        // Newton iterations cap
+  int ls_iter;         // line-search evaluations cap
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// per-environment working set (shared memory, one per warp)
+// ----------------------------------------------------------------------------------------------------------
+template <class C>
+struct EnvS {
+  enum { NV = C::NV, NB = C::NB, NG = C::NG, NVP = C::NV + 1, MAXCON = C::MAXCON, MAXROW = C::MAXROW,
+         MAXUNIT = 2 * C::NV, MAXEFC = 2 * C::NV + C::MAXROW };
+  // state
+  float qpos[NV], qvel[NV], qacc[NV], qacc_ws[NV], ctrl[NV];
+  float qfrc_smooth[NV], qacc_smooth[NV], qfrc_constraint[NV];
+  // RK4 scratch
+  float x0q[NV], x0v[NV], accq[NV], accv[NV];
+  // kinematics
+  float xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[NB][3], ximat[NB][9];
+  float xanchor[NV][3], xaxis[NV][3];
+  float gxpos[NG][3];
+  float com[4];
+  float cinert[NB][10], crb[NB][10], cdof[NV][6], cdof_dot[NV][6], cvel[NB][6], cacc[NB][6];
+  float M[NV][NVP], L[NV][NVP], H[NV][NVP];
+  // contacts
+  int ncon, nunit, nrow, nefc, nlim, solver_iter, pad0, pad1;
+  float con_dist[MAXCON], con_pos[MAXCON][3], con_frame[MAXCON][9], con_fri[MAXCON][5], con_solref[MAXCON][2],
+      con_solimp[MAXCON][5], con_incl[MAXCON], con_mu[MAXCON];
+  int con_dim[MAXCON], con_g1[MAXCON], con_g2[MAXCON], con_row[MAXCON];
+  // constraint rows: [0,nunit) unit rows (friction then limits), [nunit, nunit+nrow) contact rows
+  int r_type[MAXEFC], r_id[MAXEFC], r_state[MAXEFC];
+  float r_sign[MAXEFC];   // unit rows: J entry (+1 friction, -side for limits)
+  float r_pos[MAXEFC], r_margin[MAXEFC], r_fl[MAXEFC], r_diag[MAXEFC];
+  float r_R[MAXEFC], r_D[MAXEFC], r_aref[MAXEFC], r_jar[MAXEFC], r_Jv[MAXEFC], r_force[MAXEFC];
+  int d_lrow[NV][2];      // limit row of dof d (side 0/1) or -1
+  float J[MAXROW][NV];
+  // solver vectors
+  float Ma[NV], grad[NV], Mgrad[NV], search[NV], Mv[NV];
+  float Y[6][NV];
+  // task
+  float goal[4];
+  float obs_prev[C::MAXOBS];
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// small math
+// ----------------------------------------------------------------------------------------------------------
+LS_DEV float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+LS_DEV void cross3(float* r, const float* a, const float* b) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+LS_DEV float normalize3(float* a) {
+  float n = sqrtf(dot3(a, a));
+  if (n < LS_MINVAL) { a[0] = 1; a[1] = 0; a[2] = 0; }
+  else { float inv = 1.0f / n; a[0] *= inv; a[1] *= inv; a[2] *= inv; }
+  return n;
+}
+LS_DEV void mulmatvec3(float* r, const float* m, const float* v) {
+  float x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2],
+        z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+LS_DEV void mulmatTvec3(float* r, const float* m, const float* v) {
+  float x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2],
+        z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+LS_DEV void quat2mat(float* m, const float* q) {
+  float q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3], q11 = q[1] * q[1], q12 = q[1] * q[2],
+        q13 = q[1] * q[3], q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  m[0] = q00 + q11 - q22 - q33; m[4] = q00 - q11 + q22 - q33; m[8] = q00 - q11 - q22 + q33;
+  m[1] = 2 * (q12 - q03); m[2] = 2 * (q13 + q02); m[3] = 2 * (q12 + q03);
+  m[5] = 2 * (q23 - q01); m[6] = 2 * (q13 - q02); m[7] = 2 * (q23 + q01);
+}
+LS_DEV void mulquat(float* r, const float* a, const float* b) {
+  float t0 = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], t1 = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+        t2 = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], t3 = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+LS_DEV void mulInertVec(float* res, const float* i, const float* v) {
+  res[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  res[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  res[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  res[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  res[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  res[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+LS_DEV void crossMotion(float* res, const float* vel, const float* v) {
+  float a[3], b[3];
+  cross3(res, vel, v);
+  cross3(a, vel, v + 3);
+  cross3(b, vel + 3, v);
+  res[3] = a[0] + b[0]; res[4] = a[1] + b[1]; res[5] = a[2] + b[2];
+}
+LS_DEV void crossForce(float* res, const float* vel, const float* f) {
+  float a[3], b[3];
+  cross3(a, vel, f);
+  cross3(b, vel + 3, f + 3);
+  res[0] = a[0] + b[0]; res[1] = a[1] + b[1]; res[2] = a[2] + b[2];
+  cross3(res + 3, vel, f + 3);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// kinematics (mj_kinematics): level-synchronous over the tree, then geom centres
+// ----------------------------------------------------------------------------------------------------------
+template <class C>
+LS_DEV void kinematics(const DevModel& m, EnvS<C>& e) {
+  LANE0 {
+    e.xpos[0][0] = e.xpos[0][1] = e.xpos[0][2] = 0;
+    e.xquat[0][0] = 1; e.xquat[0][1] = e.xquat[0][2] = e.xquat[0][3] = 0;
+    for (int k = 0; k < 9; k++) e.xmat[0][k] = (k % 4 == 0) ? 1.0f : 0.0f;
+    e.xipos[0][0] = e.xipos[0][1] = e.xipos[0][2] = 0;
+  }
+  SYNC();
+  for (int lev = 1; lev < m.nlevel; lev++) {
+    PAR_FOR(b, m.nb) {
+      if (m.body_level[b] != lev) continue;
+      int p = m.body_parentid[b];
+      float pos[3], quat[4], tmp[3], mat[9];
+      mulmatvec3(tmp, e.xmat[p], m.body_pos + 3 * b);
+      for (int k = 0; k < 3; k++) pos[k] = e.xpos[p][k] + tmp[k];
+      mulquat(quat, e.xquat[p], m.body_quat + 4 * b);
+      int jn = m.body_jntnum[b], ja = m.body_jntadr[b];
+      quat2mat(mat, quat);
+      for (int k = 0; k < jn; k++) {
+        int j = ja + k;
+        mulmatvec3(tmp, mat, m.jnt_pos + 3 * j);
+        float anchor[3] = {pos[0] + tmp[0], pos[1] + tmp[1], pos[2] + tmp[2]};
+        float axis[3];
+        mulmatvec3(axis, mat, m.jnt_axis + 3 * j);
+        for (int c = 0; c < 3; c++) { e.xanchor[j][c] = anchor[c]; e.xaxis[j][c] = axis[c]; }
+        float q = e.qpos[j] - m.qpos0[j];
+        if (m.jnt_type[j] == LS_JNT_SLIDE) {
+          for (int c = 0; c < 3; c++) pos[c] += axis[c] * q;
+        } else {
+          float sn, cs;
+          sincosf(0.5f * q, &sn, &cs);
+          float ql[4] = {cs, m.jnt_axis[3 * j] * sn, m.jnt_axis[3 * j + 1] * sn, m.jnt_axis[3 * j + 2] * sn};
+          mulquat(quat, quat, ql);
+          quat2mat(mat, quat);
+          mulmatvec3(tmp, mat, m.jnt_pos + 3 * j);
+          for (int c = 0; c < 3; c++) pos[c] = anchor[c] - tmp[c];
+        }
+      }
+      float n = sqrtf(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
+      float inv = 1.0f / n;
+      for (int c = 0; c < 4; c++) quat[c] *= inv;
+      quat2mat(mat, quat);
+      for (int c = 0; c < 3; c++) e.xpos[b][c] = pos[c];
+      for (int c = 0; c < 4; c++) e.xquat[b][c] = quat[c];
+      for (int c = 0; c < 9; c++) e.xmat[b][c] = mat[c];
+      mulmatvec3(tmp, mat, m.body_ipos + 3 * b);
+      for (int c = 0; c < 3; c++) e.xipos[b][c] = pos[c] + tmp[c];
+      float iq[4], im[9];
+      mulquat(iq, quat, m.body_iquat + 4 * b);
+      quat2mat(im, iq);
+      for (int c = 0; c < 9; c++) e.ximat[b][c] = im[c];
+    }
+    SYNC();
+  }
+  PAR_FOR(g, m.ng) {
+    int b = m.geom_bodyid[g];
+    float tmp[3];
+    mulmatvec3(tmp, e.xmat[b], m.geom_pos + 3 * g);
+    for (int c = 0; c < 3; c++) e.gxpos[g][c] = e.xpos[b][c] + tmp[c];
+  }
+  SYNC();
+}
+
+template <class C>
+LS_DEV void geom_mat(const DevModel& m, const EnvS<C>& e, int g, float* mat) {
+  float gq[4];
+  mulquat(gq, e.xquat[m.geom_bodyid[g]], m.geom_quat + 4 * g);
+  quat2mat(mat, gq);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// mj_comPos (single kinematic tree: every body's root is body 1, its subtree CoM is the whole-robot CoM)
+// ----------------------------------------------------------------------------------------------------------
+template <class C>
+LS_DEV void com_pos(const DevModel& m, EnvS<C>& e) {
+  float sx = 0, sy = 0, sz = 0, sm = 0;
+  PAR_FOR(b, m.nb) {
+    float ms = m.body_mass[b];
+    sx += ms * e.xipos[b][0]; sy += ms * e.xipos[b][1]; sz += ms * e.xipos[b][2]; sm += ms;
+  }
+  sx = WARP_SUM(sx); sy = WARP_SUM(sy); sz = WARP_SUM(sz); sm = WARP_SUM(sm);
+  float inv = 1.0f / sm;
+  float com[3] = {sx * inv, sy * inv, sz * inv};
+  LANE0 { e.com[0] = com[0]; e.com[1] = com[1]; e.com[2] = com[2]; }
+  PAR_FOR(b, m.nb) {
+    float* ci = e.cinert[b];
+    if (b == 0) { for (int k = 0; k < 10; k++) ci[k] = 0; continue; }
+    float dif[3] = {e.xipos[b][0] - com[0], e.xipos[b][1] - com[1], e.xipos[b][2] - com[2]};
+    const float* R = e.ximat[b];
+    const float* I = m.body_inertia + 3 * b;
+    float mass = m.body_mass[b];
+    float t[9];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) t[3 * r + c] = R[3 * r + c] * I[c];
+    float r00 = t[0] * R[0] + t[1] * R[1] + t[2] * R[2], r11 = t[3] * R[3] + t[4] * R[4] + t[5] * R[5],
+          r22 = t[6] * R[6] + t[7] * R[7] + t[8] * R[8], r01 = t[0] * R[3] + t[1] * R[4] + t[2] * R[5],
+          r02 = t[0] * R[6] + t[1] * R[7] + t[2] * R[8], r12 = t[3] * R[6] + t[4] * R[7] + t[5] * R[8];
+    ci[0] = r00 + mass * (dif[1] * dif[1] + dif[2] * dif[2]);
+    ci[1] = r11 + mass * (dif[0] * dif[0] + dif[2] * dif[2]);
+    ci[2] = r22 + mass * (dif[0] * dif[0] + dif[1] * dif[1]);
+    ci[3] = r01 - mass * dif[0] * dif[1];
+    ci[4] = r02 - mass * dif[0] * dif[2];
+    ci[5] = r12 - mass * dif[1] * dif[2];
+    ci[6] = mass * dif[0]; ci[7] = mass * dif[1]; ci[8] = mass * dif[2]; ci[9] = mass;
+  }
+  PAR_FOR(j, m.nv) {
+    float* cd = e.cdof[j];
+    if (m.jnt_type[j] == LS_JNT_SLIDE) {
+      cd[0] = cd[1] = cd[2] = 0;
+      cd[3] = e.xaxis[j][0]; cd[4] = e.xaxis[j][1]; cd[5] = e.xaxis[j][2];
+    } else {
+      float off[3] = {com[0] - e.xanchor[j][0], com[1] - e.xanchor[j][1], com[2] - e.xanchor[j][2]};
+      cd[0] = e.xaxis[j][0]; cd[1] = e.xaxis[j][1]; cd[2] = e.xaxis[j][2];
+      cross3(cd + 3, e.xaxis[j], off);
+    }
+  }
+  SYNC();
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// dense Cholesky in shared memory (lower triangle, row stride NVP), wavefront over columns
+// ----------------------------------------------------------------------------------------------------------
+template <int NVP>
+LS_DEV void chol_factor(float (*A)[NVP], int n) {
+  for (int j = 0; j < n; j++) {
+    // column j: all rows i >= j in parallel; L[i][j] = (A[i][j] - sum_k<j L[i][k] L[j][k]) / L[j][j]
+    PAR_FOR(ii, n - j) {
+      int i = j + ii;
+      float v = A[i][j];
+      for (int k = 0; k < j; k++) v -= A[i][k] * A[j][k];
+      A[i][j] = v;   // unscaled for now
+    }
+    SYNC();
+    float d = A[j][j];
+    if (d < 1e-12f) d = 1e-12f;
+    float inv = rsqrtf(d);
+    PAR_FOR(ii, n - j) {
+      int i = j + ii;
+      A[i][j] = (ii == 0) ? d * inv : A[i][j] * inv;
+    }
+    SYNC();
+  }
+}
+// solve L L^T x = b in place; x in shared memory
+template <int NVP>
+LS_DEV void chol_solve(float (*L)[NVP], int n, float* x) {
+  // forward: column oriented
+  for (int k = 0; k < n; k++) {
+    float xk = x[k] / L[k][k];
+    SYNC();
+    PAR_FOR(ii, n - k) {
+      int i = k + ii;
+      if (ii == 0) x[k] = xk; else x[i] -= L[i][k] * xk;
+    }
+    SYNC();
+  }
+  // backward: x_i = (y_i - sum_{k>i} L[k][i] x_k) / L[i][i]  -> column oriented on L^T
+  for (int k = n - 1; k >= 0; k--) {
+    float xk = x[k] / L[k][k];
+    SYNC();
+    PAR_FOR(i, k + 1) {
+      if (i == k) x[k] = xk; else x[i] -= L[k][i] * xk;
+    }
+    SYNC();
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// mj_crb + factor: composite inertias up the tree, joint-space inertia M, L = chol(M)
+// ----------------------------------------------------------------------------------------------------------
+template <class C>
+LS_DEV void crb_factor(const DevModel& m, EnvS<C>& e) {
+  PAR_FOR(b, m.nb) for (int k = 0; k < 10; k++) e.crb[b][k] = e.cinert[b][k];
+  SYNC();
+  for (int lev = m.nlevel - 2; lev >= 1; lev--) {
+    // bodies at level `lev` gather their children (level lev+1)
+    PAR_FOR(b, m.nb) {
+      if (m.body_level[b] != lev) continue;
+      float acc[10];
+      for (int k = 0; k < 10; k++) acc[k] = e.crb[b][k];
+      for (int c = b + 1; c < m.nb; c++)
+        if (m.body_parentid[c] == b) for (int k = 0; k < 10; k++) acc[k] += e.crb[c][k];
+      for (int k = 0; k < 10; k++) e.crb[b][k] = acc[k];
+    }
+    SYNC();
+  }
+  PAR_FOR(idx, m.nv * EnvS<C>::NVP) (&e.M[0][0])[idx] = 0;
+  SYNC();
+  PAR_FOR(i, m.nv) {
+    float buf[6];
+    mulInertVec(buf, e.crb[m.jnt_bodyid[i]], e.cdof[i]);
+    for (int j = i; j >= 0; j = m.dof_parentid[j]) {
+      float v = 0;
+      for (int k = 0; k < 6; k++) v += e.cdof[j][k] * buf[k];
+      if (j == i) v += m.dof_armature[i];
+      e.M[i][j] = v;
+      e.M[j][i] = v;
+    }
+  }
+  SYNC();
+  PAR_FOR(idx, m.nv * EnvS<C>::NVP) (&e.L[0][0])[idx] = (&e.M[0][0])[idx];
+  SYNC();
+  chol_factor<EnvS<C>::NVP>(e.L, m.nv);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// narrow phase (one lane per candidate pair). Raw contacts: dist, pos, frame(normal [+tangent hint])
+// ----------------------------------------------------------------------------------------------------------
+struct RawCon { float dist, pos[3], frame[6]; };
+
+LS_DEV int plane_sphere(RawCon* c, float margin, const float* pos1, const float* n, const float* pos2, float r) {
+  float tmp[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  float cdist = dot3(tmp, n);
+  if (cdist > margin + r) return 0;
+  c->dist = cdist - r;
+  for (int k = 0; k < 3; k++) { c->frame[k] = n[k]; c->frame[3 + k] = 0; c->pos[k] = pos2[k] + n[k] * (-c->dist * 0.5f - r); }
+  return 1;
+}
+LS_DEV int plane_capsule(RawCon* c, float margin, const float* pos1, const float* n, const float* pos2, const float* mat2,
+                         const float* size2) {
+  float axis[3] = {mat2[2], mat2[5], mat2[8]};
+  float seg[3] = {axis[0] * size2[1], axis[1] * size2[1], axis[2] * size2[1]};
+  float p[3] = {pos2[0] + seg[0], pos2[1] + seg[1], pos2[2] + seg[2]};
+  int n1 = plane_sphere(c, margin, pos1, n, p, size2[0]);
+  if (n1) for (int k = 0; k < 3; k++) c->frame[3 + k] = axis[k];
+  p[0] = pos2[0] - seg[0]; p[1] = pos2[1] - seg[1]; p[2] = pos2[2] - seg[2];
+  int n2 = plane_sphere(c + n1, margin, pos1, n, p, size2[0]);
+  if (n2) for (int k = 0; k < 3; k++) c[n1].frame[3 + k] = axis[k];
+  return n1 + n2;
+}
+LS_DEV int plane_cylinder(RawCon* c, float margin, const float* pos1, const float* normal, const float* pos2,
+                          const float* mat2, const float* size2) {
+  float axis[3] = {mat2[2], mat2[5], mat2[8]};
+  float d[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  float dist0 = dot3(d, normal);
+  float prjaxis = dot3(normal, axis);
+  if (prjaxis > 0) { axis[0] = -axis[0]; axis[1] = -axis[1]; axis[2] = -axis[2]; prjaxis = -prjaxis; }
+  float vec[3] = {axis[0] * prjaxis - normal[0], axis[1] * prjaxis - normal[1], axis[2] * prjaxis - normal[2]};
+  float len_sqr = dot3(vec, vec);
+  if (len_sqr >= 1e-12f) {
+    float scl = size2[0] * rsqrtf(len_sqr);
+    vec[0] *= scl; vec[1] *= scl; vec[2] *= scl;
+  } else {
+    vec[0] = mat2[0] * size2[0]; vec[1] = mat2[3] * size2[0]; vec[2] = mat2[6] * size2[0];
+  }
+  float prjvec = dot3(vec, normal);
+  axis[0] *= size2[1]; axis[1] *= size2[1]; axis[2] *= size2[1];
+  prjaxis *= size2[1];
+  int cnt = 0;
+  if (dist0 + prjaxis + prjvec <= margin) {
+    c[cnt].dist = dist0 + prjaxis + prjvec;
+    for (int k = 0; k < 3; k++) {
+      c[cnt].pos[k] = pos2[k] + vec[k] + axis[k] - normal[k] * c[cnt].dist * 0.5f;
+      c[cnt].frame[k] = normal[k]; c[cnt].frame[3 + k] = 0;
+    }
+    cnt++;
+  } else return 0;
+  if (dist0 - prjaxis + prjvec <= margin) {
+    c[cnt].dist = dist0 - prjaxis + prjvec;
+    for (int k = 0; k < 3; k++) {
+      c[cnt].pos[k] = pos2[k] + vec[k] - axis[k] - normal[k] * c[cnt].dist * 0.5f;
+      c[cnt].frame[k] = normal[k]; c[cnt].frame[3 + k] = 0;
+    }
+    cnt++;
+  }
+  float prjvec1 = -prjvec * 0.5f;
+  if (dist0 + prjaxis + prjvec1 <= margin) {
+    float vec1[3];
+    cross3(vec1, vec, axis);
+    normalize3(vec1);
+    float sc = size2[0] * 0.8660254037844386f;
+    vec1[0] *= sc; vec1[1] *= sc; vec1[2] *= sc;
+    for (int sgn = 1; sgn >= -1; sgn -= 2) {
+      c[cnt].dist = dist0 + prjaxis + prjvec1;
+      for (int k = 0; k < 3; k++) {
+        c[cnt].pos[k] = pos2[k] + sgn * vec1[k] + axis[k] - vec[k] * 0.5f - normal[k] * c[cnt].dist * 0.5f;
+        c[cnt].frame[k] = normal[k]; c[cnt].frame[3 + k] = 0;
+      }
+      cnt++;
+    }
+  }
+  return cnt;
+}
+LS_DEV int plane_box(RawCon* c, float margin, const float* pos1, const float* norm, const float* pos2, const float* mat2,
+                     const float* size2) {
+  float d[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  float dist = dot3(d, norm);
+  int cnt = 0;
+  for (int i = 0; i < 8; i++) {
+    float vec[3] = {(i & 1 ? size2[0] : -size2[0]), (i & 2 ? size2[1] : -size2[1]), (i & 4 ? size2[2] : -size2[2])};
+    float corner[3];
+    mulmatvec3(corner, mat2, vec);
+    float ldist = dot3(norm, corner);
+    if (dist + ldist > margin || ldist > 0) continue;
+    c[cnt].dist = dist + ldist;
+    for (int k = 0; k < 3; k++) {
+      c[cnt].pos[k] = pos2[k] + corner[k] - norm[k] * c[cnt].dist * 0.5f;
+      c[cnt].frame[k] = norm[k]; c[cnt].frame[3 + k] = 0;
+    }
+    if (++cnt >= 4) break;
+  }
+  return cnt;
+}
+LS_DEV int plane_mesh(RawCon* c, float margin, const float* pos1, const float* norm, const float* pos2, const float* mat2,
+                      const float* verts, int nvert, float rbound) {
+  float nl[3];
+  mulmatTvec3(nl, mat2, norm);
+  float d[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  float dist0 = dot3(d, norm);
+  int cnt = 0;
+  int taken[4];
+  float mind2 = (0.3f * rbound) * (0.3f * rbound);
+  for (int pass = 0; pass < 4; pass++) {
+    int best = -1; float bd = 1e30f;
+    for (int i = 0; i < nvert; i++) {
+      const float* v = verts + 3 * i;
+      float dd = dist0 + dot3(nl, v);
+      if (dd > margin || dd >= bd) continue;
+      bool ok = true;
+      for (int t = 0; t < cnt; t++) {
+        const float* w = verts + 3 * taken[t];
+        float ex = v[0] - w[0], ey = v[1] - w[1], ez = v[2] - w[2];
+        if (ex * ex + ey * ey + ez * ez < mind2) { ok = false; break; }
+      }
+      if (ok) { best = i; bd = dd; }
+    }
+    if (best < 0) break;
+    float vg[3];
+    mulmatvec3(vg, mat2, verts + 3 * best);
+    c[cnt].dist = bd;
+    for (int k = 0; k < 3; k++) {
+      c[cnt].pos[k] = pos2[k] + vg[k] - norm[k] * bd * 0.5f;
+      c[cnt].frame[k] = norm[k]; c[cnt].frame[3 + k] = 0;
+    }
+    taken[cnt++] = best;
+  }
+  return cnt;
+}
+LS_DEV int sphere_sphere_raw(RawCon* c, float margin, const float* pos1, float r1, const float* pos2, float r2) {
+  float dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  float cdist = sqrtf(dot3(dif, dif));
+  if (cdist > margin + r1 + r2) return 0;
+  c->dist = cdist - r1 - r2;
+  if (cdist < 1e-12f) { c->frame[0] = 1; c->frame[1] = 0; c->frame[2] = 0; }
+  else { float inv = 1.0f / cdist; c->frame[0] = dif[0] * inv; c->frame[1] = dif[1] * inv; c->frame[2] = dif[2] * inv; }
+  for (int k = 0; k < 3; k++) { c->frame[3 + k] = 0; c->pos[k] = pos1[k] + c->frame[k] * (r1 + 0.5f * c->dist); }
+  return 1;
+}
+LS_DEV int sphere_capsule(RawCon* c, float margin, const float* pos1, float r1, const float* pos2, const float* mat2,
+                          const float* size2) {
+  float axis[3] = {mat2[2], mat2[5], mat2[8]};
+  float vec[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  float x = fminf(size2[1], fmaxf(-size2[1], dot3(axis, vec)));
+  float p[3] = {pos2[0] + axis[0] * x, pos2[1] + axis[1] * x, pos2[2] + axis[2] * x};
+  return sphere_sphere_raw(c, margin, pos1, r1, p, size2[0]);
+}
+LS_DEV int capsule_capsule(RawCon* c, float margin, const float* pos1, const float* mat1, const float* size1,
+                           const float* pos2, const float* mat2, const float* size2) {
+  float a1[3] = {mat1[2], mat1[5], mat1[8]}, a2[3] = {mat2[2], mat2[5], mat2[8]};
+  float dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  float ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif);
+  float det = ma * mc - mb * mb;
+  float len1 = size1[1], len2 = size2[1];
+  if (fabsf(det) >= 1e-10f) {
+    float x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > len1) { x1 = len1; x2 = (v - mb * len1) / mc; }
+    else if (x1 < -len1) { x1 = -len1; x2 = (v + mb * len1) / mc; }
+    if (x2 > len2) { x2 = len2; x1 = fminf(len1, fmaxf(-len1, (u - mb * len2) / ma)); }
+    else if (x2 < -len2) { x2 = -len2; x1 = fminf(len1, fmaxf(-len1, (u + mb * len2) / ma)); }
+    float p1[3] = {pos1[0] + a1[0] * x1, pos1[1] + a1[1] * x1, pos1[2] + a1[2] * x1};
+    float p2[3] = {pos2[0] + a2[0] * x2, pos2[1] + a2[1] * x2, pos2[2] + a2[2] * x2};
+    return sphere_sphere_raw(c, margin, p1, size1[0], p2, size2[0]);
+  }
+  int n = 0;
+  for (int s = -1; s <= 1 && n < 2; s += 2) {
+    float p1[3] = {pos1[0] + a1[0] * len1 * s, pos1[1] + a1[1] * len1 * s, pos1[2] + a1[2] * len1 * s};
+    float vec[3] = {p1[0] - pos2[0], p1[1] - pos2[1], p1[2] - pos2[2]};
+    float x2 = dot3(a2, vec);
+    if (x2 > len2 || x2 < -len2) continue;
+    float p2[3] = {pos2[0] + a2[0] * x2, pos2[1] + a2[1] * x2, pos2[2] + a2[2] * x2};
+    n += sphere_sphere_raw(c + n, margin, p1, size1[0], p2, size2[0]);
+  }
+  for (int s = -1; s <= 1 && n < 2; s += 2) {
+    float p2[3] = {pos2[0] + a2[0] * len2 * s, pos2[1] + a2[1] * len2 * s, pos2[2] + a2[2] * len2 * s};
+    float vec[3] = {p2[0] - pos1[0], p2[1] - pos1[1], p2[2] - pos1[2]};
+    float x1 = dot3(a1, vec);
+    if (x1 >= len1 || x1 <= -len1) continue;
+    float p1[3] = {pos1[0] + a1[0] * x1, pos1[1] + a1[1] * x1, pos1[2] + a1[2] * x1};
+    n += sphere_sphere_raw(c + n, margin, p1, size1[0], p2, size2[0]);
+  }
+  return n;
+}
+
+// mid-phase test for one candidate pair (see oracle/locosim_ref.c collision(): no margin in the filter)
+template <class C>
+LS_DEV bool pair_filter(const DevModel& m, const EnvS<C>& e, int p) {
+  int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+  float d[3] = {e.gxpos[g2][0] - e.gxpos[g1][0], e.gxpos[g2][1] - e.gxpos[g1][1], e.gxpos[g2][2] - e.gxpos[g1][2]};
+  if (m.geom_type[g1] == LS_GEOM_PLANE) {
+    float mat1[9];
+    geom_mat(m, e, g1, mat1);
+    float n[3] = {mat1[2], mat1[5], mat1[8]};
+    return dot3(d, n) <= m.geom_rbound[g2];
+  }
+  float bound = m.geom_rbound[g1] + m.geom_rbound[g2];
+  return dot3(d, d) <= bound * bound;
+}
+
+// narrow phase of pair p, appending to the env's contact list (executed by a single lane)
+template <class C>
+LS_DEV void pair_narrow(const DevModel& m, EnvS<C>& e, int p) {
+  int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+  int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+  float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
+  const float *pos1 = e.gxpos[g1], *pos2 = e.gxpos[g2];
+  const float *size1 = m.geom_size + 3 * g1, *size2 = m.geom_size + 3 * g2;
+  float mat1[9], mat2[9];
+  geom_mat(m, e, g1, mat1);
+  geom_mat(m, e, g2, mat2);
+  RawCon raw[4];
+  int n = 0;
+  if (t1 == LS_GEOM_PLANE) {
+    float nrm[3] = {mat1[2], mat1[5], mat1[8]};
+    if (t2 == LS_GEOM_SPHERE) n = plane_sphere(raw, margin, pos1, nrm, pos2, size2[0]);
+    else if (t2 == LS_GEOM_CAPSULE) n = plane_capsule(raw, margin, pos1, nrm, pos2, mat2, size2);
+    else if (t2 == LS_GEOM_CYLINDER) n = plane_cylinder(raw, margin, pos1, nrm, pos2, mat2, size2);
+    else if (t2 == LS_GEOM_BOX) n = plane_box(raw, margin, pos1, nrm, pos2, mat2, size2);
+    else if (t2 == LS_GEOM_MESH)
+      n = plane_mesh(raw, margin, pos1, nrm, pos2, mat2, m.mesh_vert + 3 * m.geom_meshadr[g2], m.geom_meshnum[g2],
+                     m.geom_rbound[g2]);
+  } else if (t1 == LS_GEOM_SPHERE && t2 == LS_GEOM_SPHERE) {
+    n = sphere_sphere_raw(raw, margin, pos1, size1[0], pos2, size2[0]);
+  } else if (t1 == LS_GEOM_SPHERE && t2 == LS_GEOM_CAPSULE) {
+    n = sphere_capsule(raw, margin, pos1, size1[0], pos2, mat2, size2);
+  } else if (t1 == LS_GEOM_CAPSULE && t2 == LS_GEOM_CAPSULE) {
+    n = capsule_capsule(raw, margin, pos1, mat1, size1, pos2, mat2, size2);
+  }
+  int base = e.ncon;
+  for (int k = 0; k < n && base < EnvS<C>::MAXCON; k++) {
+    // contact parameters (mj_contactParam)
+    int p1 = m.geom_priority[g1], p2 = m.geom_priority[g2];
+    float gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
+    float incl = margin - gap;
+    if (raw[k].dist >= incl) continue;   // not active: never enters the constraint set
+    int ci = base++;
+    float fri[3];
+    if (p1 != p2) {
+      int g = p1 > p2 ? g1 : g2;
+      e.con_dim[ci] = m.geom_condim[g];
+      for (int c = 0; c < 2; c++) e.con_solref[ci][c] = m.geom_solref[2 * g + c];
+      for (int c = 0; c < 5; c++) e.con_solimp[ci][c] = m.geom_solimp[5 * g + c];
+      for (int c = 0; c < 3; c++) fri[c] = m.geom_friction[3 * g + c];
+    } else {
+      e.con_dim[ci] = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
+      float s1 = m.geom_solmix[g1], s2 = m.geom_solmix[g2], mix;
+      if (s1 >= LS_MINVAL && s2 >= LS_MINVAL) mix = s1 / (s1 + s2);
+      else if (s1 < LS_MINVAL && s2 < LS_MINVAL) mix = 0.5f;
+      else if (s1 < LS_MINVAL) mix = 0.0f;
+      else mix = 1.0f;
+      const float *r1 = m.geom_solref + 2 * g1, *r2 = m.geom_solref + 2 * g2;
+      if (r1[0] > 0 && r2[0] > 0) for (int c = 0; c < 2; c++) e.con_solref[ci][c] = mix * r1[c] + (1 - mix) * r2[c];
+      else for (int c = 0; c < 2; c++) e.con_solref[ci][c] = fminf(r1[c], r2[c]);
+      for (int c = 0; c < 5; c++) e.con_solimp[ci][c] = mix * m.geom_solimp[5 * g1 + c] + (1 - mix) * m.geom_solimp[5 * g2 + c];
+      for (int c = 0; c < 3; c++) fri[c] = fmaxf(m.geom_friction[3 * g1 + c], m.geom_friction[3 * g2 + c]);
+    }
+    e.con_fri[ci][0] = fri[0]; e.con_fri[ci][1] = fri[0]; e.con_fri[ci][2] = fri[1]; e.con_fri[ci][3] = fri[2];
+    e.con_fri[ci][4] = fri[2];
+    e.con_incl[ci] = incl;
+    e.con_dist[ci] = raw[k].dist;
+    e.con_g1[ci] = g1; e.con_g2[ci] = g2;
+    for (int c = 0; c < 3; c++) e.con_pos[ci][c] = raw[k].pos[c];
+    // mju_makeFrame
+    float f[9];
+    for (int c = 0; c < 6; c++) f[c] = raw[k].frame[c];
+    normalize3(f);
+    if (dot3(f + 3, f + 3) < 0.25f) {
+      f[3] = f[4] = f[5] = 0;
+      if (f[1] < 0.5f && f[1] > -0.5f) f[4] = 1; else f[5] = 1;
+    }
+    float t = dot3(f, f + 3);
+    for (int c = 0; c < 3; c++) f[3 + c] -= t * f[c];
+    normalize3(f + 3);
+    cross3(f + 6, f, f + 3);
+    for (int c = 0; c < 9; c++) e.con_frame[ci][c] = f[c];
+  }
+  e.ncon = base;
+}
+
+template <class C>
+LS_DEV void collision(const DevModel& m, EnvS<C>& e) {
+  LANE0 { e.ncon = 0; }
+  SYNC();
+#ifdef LS_EMULATE
+  for (int p = 0; p < m.np; p++) if (pair_filter(m, e, p)) pair_narrow(m, e, p);
+#else
+  const int lane = LS_LANE;
+  for (int base = 0; base < m.np; base += 32) {
+    int p = base + lane;
+    bool hit = (p < m.np) && pair_filter(m, e, p);
+    unsigned mask = __ballot_sync(0xffffffffu, hit);
+    while (mask) {
+      int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (lane == src) pair_narrow(m, e, p);
+      __syncwarp();
+    }
+  }
+#endif
+  SYNC();
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// constraint assembly (mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint)
+// ----------------------------------------------------------------------------------------------------------
+LS_DEV void get_impedance(const float* solimp_in, float pos, float margin, float* imp) {
+  float s0 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[0])), s1 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[1]));
+  float s2 = fmaxf(0.0f, solimp_in[2]), s3 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[3])), s4 = fmaxf(1.0f, solimp_in[4]);
+  if (s0 == s1 || s2 <= LS_MINVAL) { *imp = 0.5f * (s0 + s1); return; }
+  float x = fabsf((pos - margin) / s2);
+  if (x >= 1 || x <= 0) { *imp = (x >= 1 ? s1 : s0); return; }
+  float y;
+  if (s4 == 1) y = x;
+  else if (x <= s3) y = powf(x, s4) / powf(s3, s4 - 1);
+  else y = 1 - powf(1 - x, s4) / powf(1 - s3, s4 - 1);
+  *imp = s0 + y * (s1 - s0);
+}
+
+template <class C>
+LS_DEV void make_constraint(const DevModel& m, EnvS<C>& e) {
+  typedef EnvS<C> E;
+  const int nv = m.nv;
+  // ---- unit rows: frictionloss (static row slots) ----
+  PAR_FOR(d, nv) {
+    int r = m.dof_frow[d];
+    if (r >= 0) {
+      e.r_type[r] = ROW_FRICTION; e.r_id[r] = d; e.r_sign[r] = 1.0f;
+      e.r_pos[r] = 0; e.r_margin[r] = 0; e.r_fl[r] = m.dof_frictionloss[d]; e.r_diag[r] = m.dof_invweight0[d];
+    }
+    e.d_lrow[d][0] = -1; e.d_lrow[d][1] = -1;
+  }
+  SYNC();
+  // ---- unit rows: joint limits (dynamic; deterministic order dof-major, lower side first) ----
+  int nunit = m.nfric;
+#ifdef LS_EMULATE
+  for (int d = 0; d < nv; d++) {
+    if (!m.jnt_limited[d]) continue;
+    for (int side = 0; side < 2; side++) {
+      float dist = side == 0 ? e.qpos[d] - m.jnt_range[2 * d] : m.jnt_range[2 * d + 1] - e.qpos[d];
+      if (dist < m.jnt_margin[d]) {
+        int r = nunit++;
+        e.r_type[r] = ROW_LIMIT; e.r_id[r] = d; e.r_sign[r] = side == 0 ? 1.0f : -1.0f;
+        e.r_pos[r] = dist; e.r_margin[r] = m.jnt_margin[d]; e.r_fl[r] = 0; e.r_diag[r] = m.dof_invweight0[d];
+        e.d_lrow[d][side] = r;
+      }
+    }
+  }
+#else
+  {
+    const int lane = LS_LANE;
+    for (int base = 0; base < 2 * nv; base += 32) {
+      int idx = base + lane;
+      int d = idx >> 1, side = idx & 1;
+      bool act = false;
+      float dist = 0;
+      if (idx < 2 * nv && m.jnt_limited[d]) {
+        dist = side == 0 ? e.qpos[d] - m.jnt_range[2 * d] : m.jnt_range[2 * d + 1] - e.qpos[d];
+        act = dist < m.jnt_margin[d];
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        int r = nunit + __popc(mask & ((1u << lane) - 1));
+        e.r_type[r] = ROW_LIMIT; e.r_id[r] = d; e.r_sign[r] = side == 0 ? 1.0f : -1.0f;
+        e.r_pos[r] = dist; e.r_margin[r] = m.jnt_margin[d]; e.r_fl[r] = 0; e.r_diag[r] = m.dof_invweight0[d];
+        e.d_lrow[d][side] = r;
+      }
+      nunit += __popc(mask);
+    }
+  }
+#endif
+  // ---- contact rows: row offsets (serial, tiny) ----
+  LANE0 {
+    int nrow = 0, ncon = e.ncon;
+    for (int ci = 0; ci < ncon; ci++) {
+      int dim = e.con_dim[ci];
+      int nr = (dim == 1) ? 1 : (m.cone == 1 ? dim : 2 * (dim - 1));
+      if (nrow + nr > E::MAXROW) { ncon = ci; break; }
+      e.con_row[ci] = nrow;
+      nrow += nr;
+    }
+    e.ncon = ncon; e.nrow = nrow; e.nunit = nunit; e.nefc = nunit + nrow;
+  }
+  SYNC();
+  const int ncon = e.ncon;
+  // ---- contact Jacobian rows: one work item per (contact, dof) ----
+  PAR_FOR(item, ncon * nv) {
+    int ci = item / nv, d = item - ci * nv;
+    int b1 = m.geom_bodyid[e.con_g1[ci]], b2 = m.geom_bodyid[e.con_g2[ci]];
+    float s = 0;
+    if ((m.body_dofmask[b2] >> d) & 1) s += 1.0f;
+    if ((m.body_dofmask[b1] >> d) & 1) s -= 1.0f;
+    int dim = e.con_dim[ci], row0 = e.con_row[ci];
+    int nr = (dim == 1) ? 1 : (m.cone == 1 ? dim : 2 * (dim - 1));
+    if (s == 0) { for (int r = 0; r < nr; r++) e.J[row0 + r][d] = 0; continue; }
+    float off[3] = {e.con_pos[ci][0] - e.com[0], e.con_pos[ci][1] - e.com[1], e.con_pos[ci][2] - e.com[2]};
+    const float* cd = e.cdof[d];
+    float jp[3], t[3];
+    cross3(t, cd, off);
+    for (int k = 0; k < 3; k++) jp[k] = s * (cd[3 + k] + t[k]);
+    float jr[3] = {s * cd[0], s * cd[1], s * cd[2]};
+    const float* f = e.con_frame[ci];
+    float jd[6];
+    for (int r = 0; r < 3; r++) { jd[r] = dot3(f + 3 * r, jp); jd[3 + r] = dot3(f + 3 * r, jr); }
+    if (dim == 1) e.J[row0][d] = jd[0];
+    else if (m.cone == 1) { for (int r = 0; r < dim; r++) e.J[row0 + r][d] = jd[r]; }
+    else {
+      for (int r = 1; r < dim; r++) {
+        float fr = e.con_fri[ci][r - 1];
+        e.J[row0 + 2 * (r - 1)][d] = jd[0] + fr * jd[r];
+        e.J[row0 + 2 * (r - 1) + 1][d] = jd[0] - fr * jd[r];
+      }
+    }
+  }
+  // ---- contact row metadata ----
+  PAR_FOR(ci, ncon) {
+    int b1 = m.geom_bodyid[e.con_g1[ci]], b2 = m.geom_bodyid[e.con_g2[ci]];
+    float tran = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
+    float rot = m.body_invweight0[2 * b1 + 1] + m.body_invweight0[2 * b2 + 1];
+    int dim = e.con_dim[ci], row0 = nunit + e.con_row[ci];
+    int nr = (dim == 1) ? 1 : (m.cone == 1 ? dim : 2 * (dim - 1));
+    int tp = (dim == 1) ? ROW_CON_FRICTIONLESS : (m.cone == 1 ? ROW_CON_ELLIPTIC : ROW_CON_PYRAMIDAL);
+    for (int r = 0; r < nr; r++) {
+      int rr = row0 + r;
+      e.r_type[rr] = tp; e.r_id[rr] = ci; e.r_sign[rr] = (float)r;   // r_sign = row-within-contact for contact rows
+      e.r_pos[rr] = e.con_dist[ci]; e.r_margin[rr] = e.con_incl[ci]; e.r_fl[rr] = 0;
+      if (tp == ROW_CON_PYRAMIDAL) e.r_diag[rr] = tran + e.con_fri[ci][0] * e.con_fri[ci][0] * tran;
+      else e.r_diag[rr] = r < 3 ? tran : rot;
+    }
+  }
+  SYNC();
+  // ---- impedance, R, reference acceleration ----
+  const int nefc = e.nefc;
+  PAR_FOR(r, nefc) {
+    int tp = e.r_type[r], id = e.r_id[r];
+    const float *solref, *solimp;
+    if (tp == ROW_FRICTION) { solref = m.dof_solref + 2 * id; solimp = m.dof_solimp + 5 * id; }
+    else if (tp == ROW_LIMIT) { solref = m.jnt_solref + 2 * id; solimp = m.jnt_solimp + 5 * id; }
+    else { solref = e.con_solref[id]; solimp = e.con_solimp[id]; }
+    float sr0 = solref[0], sr1 = solref[1];
+    if (sr0 > 0) sr0 = fmaxf(sr0, 2 * m.timestep);
+    float imp;
+    get_impedance(solimp, e.r_pos[r], e.r_margin[r], &imp);
+    e.r_R[r] = fmaxf(LS_MINVAL, (1 - imp) * e.r_diag[r] / imp);
+    float dmax = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp[1]));
+    float K, B;
+    if (sr0 > 0) { K = 1 / fmaxf(LS_MINVAL, dmax * dmax * sr0 * sr0 * sr1 * sr1); B = 2 / fmaxf(LS_MINVAL, dmax * sr0); }
+    else { K = -sr0 / fmaxf(LS_MINVAL, dmax * dmax); B = -sr1 / fmaxf(LS_MINVAL, dmax); }
+    bool friction_row = (tp == ROW_FRICTION) || (tp == ROW_CON_ELLIPTIC && e.r_sign[r] > 0.5f);
+    if (friction_row) K = 0;
+    float vel;
+    if (r < nunit) vel = e.r_sign[r] * e.qvel[id];
+    else {
+      const float* Jr = e.J[r - nunit];
+      vel = 0;
+      for (int d = 0; d < nv; d++) vel += Jr[d] * e.qvel[d];
+    }
+    e.r_aref[r] = -B * vel - K * imp * (e.r_pos[r] - e.r_margin[r]);
+  }
+  SYNC();
+  PAR_FOR(ci, ncon) {
+    int dim = e.con_dim[ci];
+    if (dim == 1) continue;
+    int i = nunit + e.con_row[ci];
+    if (m.cone == 0) {
+      float mu = e.con_fri[ci][0] * rsqrtf(fmaxf(LS_MINVAL, m.impratio));
+      e.con_mu[ci] = mu;
+      float Rpy = 2 * mu * mu * e.r_R[i];
+      for (int j = 0; j < 2 * (dim - 1); j++) e.r_R[i + j] = Rpy;
+    } else {
+      float R0 = e.r_R[i];
+      float R1 = R0 / fmaxf(LS_MINVAL, m.impratio);
+      e.r_R[i + 1] = R1;
+      e.con_mu[ci] = e.con_fri[ci][0] * sqrtf(R1 / R0);
+      for (int j = 1; j < dim - 1; j++)
+        e.r_R[i + j + 1] = R1 * e.con_fri[ci][0] * e.con_fri[ci][0] / (e.con_fri[ci][j] * e.con_fri[ci][j]);
+    }
+  }
+  SYNC();
+  PAR_FOR(r, nefc) e.r_D[r] = 1.0f / e.r_R[r];
+  SYNC();
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// velocity-dependent smooth terms: comVel, RNE bias, passive, actuation -> qfrc_smooth, qacc_smooth
+// ----------------------------------------------------------------------------------------------------------
+template <class C>
+LS_DEV void smooth_forces(const DevModel& m, EnvS<C>& e) {
+  const int nv = m.nv;
+  // comVel + cacc + per-body force, level by level (cvel/cacc of parent needed)
+  LANE0 {
+    for (int k = 0; k < 6; k++) { e.cvel[0][k] = 0; e.cacc[0][k] = 0; }
+    e.cacc[0][3] = -m.gravity[0]; e.cacc[0][4] = -m.gravity[1]; e.cacc[0][5] = -m.gravity[2];
+  }
+  SYNC();
+  for (int lev = 1; lev < m.nlevel; lev++) {
+    PAR_FOR(b, m.nb) {
+      if (m.body_level[b] != lev) continue;
+      int p = m.body_parentid[b];
+      float cvel[6], cacc[6];
+      for (int k = 0; k < 6; k++) { cvel[k] = e.cvel[p][k]; cacc[k] = e.cacc[p][k]; }
+      int jn = m.body_jntnum[b], ja = m.body_jntadr[b];
+      for (int k = 0; k < jn; k++) {
+        int j = ja + k;
+        float cdd[6];
+        crossMotion(cdd, cvel, e.cdof[j]);
+        float qv = e.qvel[j];
+        for (int c = 0; c < 6; c++) { e.cdof_dot[j][c] = cdd[c]; cvel[c] += e.cdof[j][c] * qv; cacc[c] += cdd[c] * qv; }
+      }
+      for (int k = 0; k < 6; k++) { e.cvel[b][k] = cvel[k]; e.cacc[b][k] = cacc[k]; }
+    }
+    SYNC();
+  }
+  // body forces -> reuse crb[b][0..5] as cfrc storage (crb no longer needed after M)
+  PAR_FOR(b, m.nb) {
+    float* f = e.crb[b];
+    if (b == 0) { for (int k = 0; k < 6; k++) f[k] = 0; continue; }
+    float t1[6], t2[6], t3[6];
+    mulInertVec(t1, e.cinert[b], e.cacc[b]);
+    mulInertVec(t2, e.cinert[b], e.cvel[b]);
+    crossForce(t3, e.cvel[b], t2);
+    for (int k = 0; k < 6; k++) f[k] = t1[k] + t3[k];
+  }
+  SYNC();
+  for (int lev = m.nlevel - 2; lev >= 1; lev--) {
+    PAR_FOR(b, m.nb) {
+      if (m.body_level[b] != lev) continue;
+      float acc[6];
+      for (int k = 0; k < 6; k++) acc[k] = e.crb[b][k];
+      for (int c = b + 1; c < m.nb; c++)
+        if (m.body_parentid[c] == b) for (int k = 0; k < 6; k++) acc[k] += e.crb[c][k];
+      for (int k = 0; k < 6; k++) e.crb[b][k] = acc[k];
+    }
+    SYNC();
+  }
+  // qfrc_smooth = passive - bias + actuator
+  PAR_FOR(j, nv) {
+    const float* f = e.crb[m.jnt_bodyid[j]];
+    float bias = 0;
+    for (int c = 0; c < 6; c++) bias += e.cdof[j][c] * f[c];
+    float passive = -m.jnt_stiffness[j] * (e.qpos[j] - m.qpos_spring[j]) - m.dof_damping[j] * e.qvel[j];
+    e.qfrc_smooth[j] = passive - bias;
+  }
+  SYNC();
+  PAR_FOR(i, m.nu) {
+    float c = e.ctrl[i];
+    if (m.actuator_ctrllimited[i]) c = fminf(m.actuator_ctrlrange[2 * i + 1], fmaxf(m.actuator_ctrlrange[2 * i], c));
+    int d = m.actuator_dof[i];
+    float f = m.actuator_gain[i] * c + m.actuator_bias[3 * i] + m.actuator_bias[3 * i + 1] * e.qpos[d] +
+              m.actuator_bias[3 * i + 2] * e.qvel[d];
+    if (m.actuator_forcelimited[i]) f = fminf(m.actuator_forcerange[2 * i + 1], fmaxf(m.actuator_forcerange[2 * i], f));
+    // one actuator per dof in all in-scope models -> no write conflict
+    e.qfrc_smooth[d] += m.actuator_gear[i] * f;
+  }
+  SYNC();
+  PAR_FOR(j, nv) e.qacc_smooth[j] = e.qfrc_smooth[j];
+  SYNC();
+  chol_solve<EnvS<C>::NVP>(e.L, nv, e.qacc_smooth);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// Newton solver (mj_solNewton), warp-parallel over rows / matrix entries
+// ----------------------------------------------------------------------------------------------------------
+template <class C>
+LS_DEV void mulM(const DevModel& m, const EnvS<C>& e, float* res, const float* v) {
+  PAR_FOR(i, m.nv) {
+    float a = 0;
+    for (int j = 0; j < m.nv; j++) a += e.M[i][j] * v[j];
+    res[i] = a;
+  }
+}
+// res[r] = (J v)[r] for all rows
+template <class C>
+LS_DEV void mulJ(const DevModel& m, const EnvS<C>& e, float* res, const float* v) {
+  const int nunit = e.nunit, nefc = e.nefc, nv = m.nv;
+  PAR_FOR(r, nefc) {
+    if (r < nunit) res[r] = e.r_sign[r] * v[e.r_id[r]];
+    else {
+      const float* Jr = e.J[r - nunit];
+      float a = 0;
+      for (int d = 0; d < nv; d++) a += Jr[d] * v[d];
+      res[r] = a;
+    }
+  }
+}
+
+// states, forces, cost from jar (= e.r_jar). Returns the constraint cost (all lanes).
+template <class C>
+LS_DEV float constraint_update(const DevModel& m, EnvS<C>& e) {
+  const int nefc = e.nefc, nunit = e.nunit;
+  float cost = 0;
+  PAR_FOR(r, nefc) {
+    int tp = e.r_type[r];
+    float jar = e.r_jar[r], D = e.r_D[r];
+    if (tp == ROW_FRICTION) {
+      float f = e.r_fl[r], Rf = e.r_R[r] * f;
+      if (jar <= -Rf) { e.r_state[r] = ST_LINEARNEG; e.r_force[r] = f; cost += -0.5f * Rf * f - f * jar; }
+      else if (jar >= Rf) { e.r_state[r] = ST_LINEARPOS; e.r_force[r] = -f; cost += -0.5f * Rf * f + f * jar; }
+      else { e.r_state[r] = ST_QUADRATIC; e.r_force[r] = -D * jar; cost += 0.5f * D * jar * jar; }
+    } else if (tp == ROW_CON_ELLIPTIC) {
+      if (e.r_sign[r] > 0.5f) continue;   // handled by the contact's first row
+      int ci = e.r_id[r], dim = e.con_dim[ci];
+      float mu = e.con_mu[ci];
+      float U[6];
+      U[0] = jar * mu;
+      float TT = 0;
+      for (int j = 1; j < dim; j++) { U[j] = e.r_jar[r + j] * e.con_fri[ci][j - 1]; TT += U[j] * U[j]; }
+      float N = U[0], T = sqrtf(TT);
+      if (N >= mu * T || (T <= 0 && N >= 0)) {
+        for (int j = 0; j < dim; j++) { e.r_force[r + j] = 0; e.r_state[r + j] = ST_SATISFIED; }
+      } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+        for (int j = 0; j < dim; j++) {
+          float jj = e.r_jar[r + j], Dj = e.r_D[r + j];
+          e.r_force[r + j] = -Dj * jj; e.r_state[r + j] = ST_QUADRATIC; cost += 0.5f * Dj * jj * jj;
+        }
+      } else {
+        float Dm = D / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
+        float NmT = N - mu * T;
+        cost += 0.5f * Dm * NmT * NmT;
+        float f0 = -Dm * NmT * mu;
+        e.r_force[r] = f0; e.r_state[r] = ST_CONE;
+        for (int j = 1; j < dim; j++) { e.r_force[r + j] = -f0 / T * U[j] * e.con_fri[ci][j - 1]; e.r_state[r + j] = ST_CONE; }
+      }
+    } else {
+      if (jar < 0) { e.r_state[r] = ST_QUADRATIC; e.r_force[r] = -D * jar; cost += 0.5f * D * jar * jar; }
+      else { e.r_state[r] = ST_SATISFIED; e.r_force[r] = 0; }
+    }
+  }
+  (void)nunit;
+  cost = WARP_SUM(cost);
+  SYNC();
+  return cost;
+}
+
+// qfrc_constraint = J^T force ; returns total cost incl. Gauss term
+template <class C>
+LS_DEV float update_constraint(const DevModel& m, EnvS<C>& e, float* gauss_out) {
+  const int nv = m.nv, nrow = e.nrow, nunit = e.nunit;
+  float cost = constraint_update(m, e);
+  float g = 0;
+  PAR_FOR(d, nv) {
+    float a = 0;
+    int fr = m.dof_frow[d];
+    if (fr >= 0) a += e.r_force[fr];
+    int l0 = e.d_lrow[d][0], l1 = e.d_lrow[d][1];
+    if (l0 >= 0) a += e.r_force[l0];
+    if (l1 >= 0) a -= e.r_force[l1];
+    for (int r = 0; r < nrow; r++) a += e.J[r][d] * e.r_force[nunit + r];
+    e.qfrc_constraint[d] = a;
+    g += 0.5f * (e.Ma[d] - e.qfrc_smooth[d]) * (e.qacc[d] - e.qacc_smooth[d]);
+  }
+  g = WARP_SUM(g);
+  SYNC();
+  *gauss_out = g;
+  return cost + g;
+}
+
+template <class C>
+LS_DEV void make_hessian(const DevModel& m, EnvS<C>& e) {
+  typedef EnvS<C> E;
+  const int nv = m.nv, nrow = e.nrow, nunit = e.nunit;
+  const int ntri = nv * (nv + 1) / 2;
+  // H = M + J^T diag(D active) J  over the lower triangle
+  PAR_FOR(idx, ntri) {
+    // idx -> (i, j), j <= i
+    int i = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+    while ((i + 1) * (i + 2) / 2 <= idx) i++;
+    while (i * (i + 1) / 2 > idx) i--;
+    int j = idx - i * (i + 1) / 2;
+    float h = e.M[i][j];
+    for (int r = 0; r < nrow; r++) {
+      if (e.r_state[nunit + r] == ST_QUADRATIC) h += e.r_D[nunit + r] * e.J[r][i] * e.J[r][j];
+    }
+    if (i == j) {
+      int fr = m.dof_frow[i];
+      if (fr >= 0 && e.r_state[fr] == ST_QUADRATIC) h += e.r_D[fr];
+      int l0 = e.d_lrow[i][0], l1 = e.d_lrow[i][1];
+      if (l0 >= 0 && e.r_state[l0] == ST_QUADRATIC) h += e.r_D[l0];
+      if (l1 >= 0 && e.r_state[l1] == ST_QUADRATIC) h += e.r_D[l1];
+    }
+    e.H[i][j] = h;
+  }
+  SYNC();
+  // cone contacts (elliptic, middle zone): H += Jc^T Hc Jc, one contact at a time
+  for (int ci = 0; ci < e.ncon; ci++) {
+    int r0 = nunit + e.con_row[ci];
+    if (e.r_state[r0] != ST_CONE) continue;
+    int dim = e.con_dim[ci];
+    float mu = e.con_mu[ci];
+    float U[6], scl[6];
+    U[0] = e.r_jar[r0] * mu; scl[0] = mu;
+    float TT = 0;
+    for (int j = 1; j < dim; j++) { scl[j] = e.con_fri[ci][j - 1]; U[j] = e.r_jar[r0 + j] * scl[j]; TT += U[j] * U[j]; }
+    float N = U[0], T = sqrtf(TT);
+    float Dm = e.r_D[r0] / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
+    float invT = 1.0f / T;
+    float c1 = mu * N * invT * invT * invT, c2 = mu * mu - mu * N * invT;
+    // Y[a][d] = sum_b Hc[a][b] J[b][d]
+    PAR_FOR(item, dim * nv) {
+      int a = item / nv, d = item - a * nv;
+      float y = 0;
+      for (int b = 0; b < dim; b++) {
+        float h;
+        if (a == 0 && b == 0) h = 1;
+        else if (a == 0) h = -mu * U[b] * invT;
+        else if (b == 0) h = -mu * U[a] * invT;
+        else h = c1 * U[a] * U[b] + (a == b ? c2 : 0.0f);
+        y += Dm * h * scl[a] * scl[b] * e.J[r0 - nunit + b][d];
+      }
+      e.Y[a][d] = y;
+    }
+    SYNC();
+    PAR_FOR(idx, ntri) {
+      int i = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+      while ((i + 1) * (i + 2) / 2 <= idx) i++;
+      while (i * (i + 1) / 2 > idx) i--;
+      int j = idx - i * (i + 1) / 2;
+      float h = 0;
+      for (int a = 0; a < dim; a++) h += e.J[r0 - nunit + a][i] * e.Y[a][j];
+      e.H[i][j] += h;
+    }
+    SYNC();
+  }
+  chol_factor<E::NVP>(e.H, nv);
+}
+
+struct LSPoint { float alpha, cost, d1, d2; };
+
+template <class C>
+LS_DEV LSPoint ls_eval(const DevModel& m, const EnvS<C>& e, const float* qg, float alpha) {
+  const int nefc = e.nefc;
+  float c = 0, d1 = 0, d2 = 0;
+  PAR_FOR(r, nefc) {
+    int tp = e.r_type[r];
+    float ja = e.r_jar[r], jv = e.r_Jv[r], D = e.r_D[r];
+    float x = ja + alpha * jv;
+    if (tp == ROW_FRICTION) {
+      float f = e.r_fl[r], Rf = e.r_R[r] * f;
+      if (x <= -Rf) { c += f * (-0.5f * Rf - x); d1 += -f * jv; }
+      else if (x >= Rf) { c += f * (-0.5f * Rf + x); d1 += f * jv; }
+      else { c += 0.5f * D * x * x; d1 += D * x * jv; d2 += D * jv * jv; }
+    } else if (tp == ROW_CON_ELLIPTIC) {
+      if (e.r_sign[r] > 0.5f) continue;
+      int ci = e.r_id[r], dim = e.con_dim[ci];
+      float mu = e.con_mu[ci];
+      float U0 = ja * mu, V0 = jv * mu, UU = 0, UV = 0, VV = 0;
+      float qc = 0.5f * D * x * x, q1 = D * x * jv, q2 = D * jv * jv;   // quadratic (bottom zone) pieces
+      for (int j = 1; j < dim; j++) {
+        float fr = e.con_fri[ci][j - 1];
+        float aj = e.r_jar[r + j], vj = e.r_Jv[r + j], Dj = e.r_D[r + j];
+        float u = aj * fr, v = vj * fr;
+        UU += u * u; UV += u * v; VV += v * v;
+        float xj = aj + alpha * vj;
+        qc += 0.5f * Dj * xj * xj; q1 += Dj * xj * vj; q2 += Dj * vj * vj;
+      }
+      float N = U0 + alpha * V0;
+      float Tsqr = UU + alpha * (2 * UV + alpha * VV);
+      if (Tsqr <= 0) {
+        if (N < 0) { c += qc; d1 += q1; d2 += q2; }
+      } else {
+        float T = sqrtf(Tsqr);
+        if (N >= mu * T) {
+        } else if (mu * N + T <= 0) { c += qc; d1 += q1; d2 += q2; }
+        else {
+          float Dm = D / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
+          float N1 = V0, T1 = (UV + alpha * VV) / T, T2 = VV / T - (UV + alpha * VV) * T1 / (T * T);
+          float NmT = N - mu * T, s = N1 - mu * T1;
+          c += 0.5f * Dm * NmT * NmT;
+          d1 += Dm * NmT * s;
+          d2 += Dm * (s * s + NmT * (-mu * T2));
+        }
+      }
+    } else {
+      if (x < 0) { c += 0.5f * D * x * x; d1 += D * x * jv; d2 += D * jv * jv; }
+    }
+  }
+  c = WARP_SUM(c); d1 = WARP_SUM(d1); d2 = WARP_SUM(d2);
+  c += alpha * alpha * qg[2] + alpha * qg[1] + qg[0];
+  d1 += 2 * alpha * qg[2] + qg[1];
+  d2 += 2 * qg[2];
+  if (d2 <= 0) d2 = LS_MINVAL;
+  LSPoint p = {alpha, c, d1, d2};
+  return p;
+}
+
+template <class C>
+LS_DEV float line_search(const DevModel& m, EnvS<C>& e, const SolverOpts& so, float gauss, float scale) {
+  const int nv = m.nv;
+  float sn = 0, q1 = 0, q2 = 0;
+  mulM(m, e, e.Mv, e.search);
+  mulJ(m, e, e.r_Jv, e.search);
+  SYNC();
+  PAR_FOR(i, nv) {
+    float s = e.search[i];
+    sn += s * s;
+    q1 += s * (e.Ma[i] - e.qfrc_smooth[i]);
+    q2 += 0.5f * s * e.Mv[i];
+  }
+  sn = WARP_SUM(sn); q1 = WARP_SUM(q1); q2 = WARP_SUM(q2);
+  float snorm = sqrtf(sn);
+  if (snorm < LS_MINVAL) return 0;
+  float gtol = so.tolerance * so.ls_tolerance * snorm / scale;
+  float qg[3] = {gauss, q1, q2};
+  LSPoint p0 = ls_eval(m, e, qg, 0.0f);
+  LSPoint p1 = ls_eval(m, e, qg, p0.alpha - p0.d1 / p0.d2);
+  if (p0.cost < p1.cost) p1 = p0;
+  if (fabsf(p1.d1) < gtol) return p1.alpha;
+  int iter = 0;
+  float dir = p1.d1 < 0 ? 1.0f : -1.0f;
+  LSPoint p2 = p1;
+  while (p1.d1 * dir <= -gtol && iter < so.ls_iter) {
+    p2 = p1;
+    p1 = ls_eval(m, e, qg, p1.alpha - p1.d1 / p1.d2);
+    iter++;
+    if (fabsf(p1.d1) < gtol) return p1.alpha;
+  }
+  if (iter >= so.ls_iter) return p1.alpha;
+  LSPoint lo = p2, hi = p1;
+  LSPoint best = (p1.cost < p2.cost) ? p1 : p2;
+  while (iter < so.ls_iter) {
+    float amin = fminf(lo.alpha, hi.alpha), amax = fmaxf(lo.alpha, hi.alpha);
+    // Newton from the better end if it stays inside the bracket, else bisect
+    float a = best.alpha - best.d1 / best.d2;
+    if (!(a > amin && a < amax)) a = 0.5f * (lo.alpha + hi.alpha);
+    if (!(a > amin && a < amax)) break;
+    LSPoint pm = ls_eval(m, e, qg, a);
+    iter++;
+    if (pm.cost < best.cost) best = pm;
+    if (fabsf(pm.d1) < gtol) return pm.alpha;
+    if (pm.d1 * dir < 0) lo = pm; else hi = pm;
+    best = (lo.cost < hi.cost) ? lo : hi;
+  }
+  return best.alpha;
+}
+
+template <class C>
+LS_DEV void update_gradient(const DevModel& m, EnvS<C>& e) {
+  PAR_FOR(i, m.nv) {
+    float g = e.Ma[i] - e.qfrc_smooth[i] - e.qfrc_constraint[i];
+    e.grad[i] = g; e.Mgrad[i] = g;
+  }
+  SYNC();
+  chol_solve<EnvS<C>::NVP>(e.H, m.nv, e.Mgrad);
+}
+
+template <class C>
+LS_DEV void fwd_constraint(const DevModel& m, EnvS<C>& e, const SolverOpts& so) {
+  const int nv = m.nv, nefc = e.nefc;
+  if (nefc == 0) {
+    PAR_FOR(i, nv) { e.qacc[i] = e.qacc_smooth[i]; e.qacc_ws[i] = e.qacc_smooth[i]; e.qfrc_constraint[i] = 0; }
+    SYNC();
+    return;
+  }
+  // ---- warmstart choice ----
+  PAR_FOR(i, nv) e.qacc[i] = e.qacc_ws[i];
+  SYNC();
+  mulM(m, e, e.Ma, e.qacc);
+  mulJ(m, e, e.r_jar, e.qacc);
+  SYNC();
+  PAR_FOR(r, nefc) e.r_jar[r] -= e.r_aref[r];
+  SYNC();
+  float cw = constraint_update(m, e);
+  float g = 0;
+  PAR_FOR(i, nv) g += 0.5f * (e.Ma[i] - e.qfrc_smooth[i]) * (e.qacc[i] - e.qacc_smooth[i]);
+  cw += WARP_SUM(g);
+  SYNC();
+  mulJ(m, e, e.r_Jv, e.qacc_smooth);   // r_Jv used as scratch for J*qacc_smooth
+  SYNC();
+  // cost at qacc_smooth: swap in jar = J qacc_smooth - aref
+  PAR_FOR(r, nefc) { float t = e.r_jar[r]; e.r_jar[r] = e.r_Jv[r] - e.r_aref[r]; e.r_Jv[r] = t; }
+  SYNC();
+  float cs = constraint_update(m, e);
+  if (cw > cs) {
+    PAR_FOR(i, nv) e.qacc[i] = e.qacc_smooth[i];
+    SYNC();
+    mulM(m, e, e.Ma, e.qacc);
+  } else {
+    PAR_FOR(r, nefc) e.r_jar[r] = e.r_Jv[r];
+  }
+  SYNC();
+  // ---- Newton iterations ----
+  float scale = 1.0f / (m.meaninertia * (nv > 1 ? nv : 1));
+  float gauss;
+  float cost = update_constraint(m, e, &gauss);
+  make_hessian(m, e);
+  update_gradient(m, e);
+  PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
+  SYNC();
+  int iter = 0;
+  while (iter < so.max_iter) {
+    float alpha = line_search(m, e, so, gauss, scale);
+    if (alpha == 0) break;
+    PAR_FOR(i, nv) { e.qacc[i] += alpha * e.search[i]; e.Ma[i] += alpha * e.Mv[i]; }
+    PAR_FOR(r, nefc) e.r_jar[r] += alpha * e.r_Jv[r];
+    SYNC();
+    float oldcost = cost;
+    cost = update_constraint(m, e, &gauss);
+    make_hessian(m, e);
+    update_gradient(m, e);
+    float gn = 0;
+    PAR_FOR(i, nv) gn += e.grad[i] * e.grad[i];
+    gn = WARP_SUM(gn);
+    float improvement = scale * (oldcost - cost);
+    float gradient = scale * sqrtf(gn);
+    iter++;
+    (void)improvement;
+    if (gradient < so.tolerance) break;
+    PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
+    SYNC();
+  }
+  LANE0 { e.solver_iter = iter; }
+  PAR_FOR(i, nv) e.qacc_ws[i] = e.qacc[i];
+  SYNC();
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// forward dynamics + integrators
+// ----------------------------------------------------------------------------------------------------------
+template <class C>
+LS_DEV void forward(const DevModel& m, EnvS<C>& e, const SolverOpts& so) {
+  kinematics(m, e);
+  com_pos(m, e);
+  crb_factor(m, e);
+  collision(m, e);
+  make_constraint(m, e);
+  smooth_forces(m, e);
+  fwd_constraint(m, e, so);
+}
+
+template <class C>
+LS_DEV void euler_step(const DevModel& m, EnvS<C>& e) {
+  typedef EnvS<C> E;
+  const int nv = m.nv;
+  const float h = m.timestep;
+  if (m.has_damping) {
+    // (M + h*diag(damping)) qacc = qfrc_smooth + qfrc_constraint   (mj_Euler, implicit in joint damping)
+    PAR_FOR(idx, nv * E::NVP) (&e.H[0][0])[idx] = (&e.M[0][0])[idx];
+    SYNC();
+    PAR_FOR(i, nv) { e.H[i][i] += h * m.dof_damping[i]; e.Mgrad[i] = e.qfrc_smooth[i] + e.qfrc_constraint[i]; }
+    SYNC();
+    chol_factor<E::NVP>(e.H, nv);
+    chol_solve<E::NVP>(e.H, nv, e.Mgrad);
+    PAR_FOR(i, nv) { float v = e.qvel[i] + h * e.Mgrad[i]; e.qvel[i] = v; e.qpos[i] += h * v; }
+  } else {
+    PAR_FOR(i, nv) { float v = e.qvel[i] + h * e.qacc[i]; e.qvel[i] = v; e.qpos[i] += h * v; }
+  }
+  SYNC();
+}
+
+template <class C>
+LS_DEV void rk4_step(const DevModel& m, EnvS<C>& e, const SolverOpts& so) {
+  // classic RK4 (mj_RungeKutta N=4); forward() for stage 0 has already been evaluated by the caller
+  const int nv = m.nv;
+  const float h = m.timestep;
+  PAR_FOR(i, nv) {
+    e.x0q[i] = e.qpos[i]; e.x0v[i] = e.qvel[i];
+    e.accq[i] = e.qvel[i] * (1.0f / 6); e.accv[i] = e.qacc[i] * (1.0f / 6);
+  }
+  SYNC();
+  const float A[3] = {0.5f, 0.5f, 1.0f};
+  const float B[3] = {1.0f / 3, 1.0f / 3, 1.0f / 6};
+  for (int s = 0; s < 3; s++) {
+    PAR_FOR(i, nv) {
+      float fv = e.qvel[i], fa = e.qacc[i];   // F[s] = (qvel, qacc) of the previous stage
+      e.qpos[i] = e.x0q[i] + h * A[s] * fv;
+      e.qvel[i] = e.x0v[i] + h * A[s] * fa;
+    }
+    SYNC();
+    forward(m, e, so);
+    PAR_FOR(i, nv) { e.accq[i] += B[s] * e.qvel[i]; e.accv[i] += B[s] * e.qacc[i]; }
+    SYNC();
+  }
+  PAR_FOR(i, nv) { e.qvel[i] = e.x0v[i] + h * e.accv[i]; e.qpos[i] = e.x0q[i] + h * e.accq[i]; }
+  SYNC();
+}
+
+template <class C>
+LS_DEV void physics_substeps(const DevModel& m, EnvS<C>& e, const SolverOpts& so, int nsub) {
+  for (int k = 0; k < nsub; k++) {
+    forward(m, e, so);
+    if (m.integrator == 1) rk4_step(m, e, so); else euler_step(m, e);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// task layer: observation gather, termination, reward, reset from the trajectory table
+// ----------------------------------------------------------------------------------------------------------
+template <class C>
+LS_DEV float obs_value(const DevTask& t, const EnvS<C>& e, int k) {
+  int idx = t.obs_src_idx[k];
+  int ty = t.obs_src_type[k];
+  return ty == LS_OBS_QPOS ? e.qpos[idx] : (ty == LS_OBS_QVEL ? e.qvel[idx] : e.goal[idx]);
+}
+
+template <class C>
+LS_DEV void reset_env(const DevModel& m, const DevTask& t, EnvS<C>& e, int traj_no, int step_no) {
+  const int nv = m.nv, ncol = 2 * nv + t.n_goal;
+  const float* row = t.table + ((size_t)traj_no * t.traj_len + step_no) * ncol;
+  PAR_FOR(i, nv) {
+    float q = row[i];
+    if (i == t.recenter0 || i == t.recenter1) q = 0;
+    e.qpos[i] = q; e.qvel[i] = row[nv + i]; e.qacc_ws[i] = 0; e.qacc[i] = 0;
+  }
+  PAR_FOR(k, t.n_goal) e.goal[k] = row[2 * nv + k];
+  SYNC();
+}

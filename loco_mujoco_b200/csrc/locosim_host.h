@@ -1,0 +1,139 @@
+// Host-side helpers shared by the CUDA engine (locosim.cu) and the serial emulation build (locosim_emu.cpp):
+// parse the ModelPack / TaskSpec wire blobs (include/*.h), convert reals to fp32, derive the engine-only tables,
+// and bind DevModel / DevTask pointer views onto a (host or device) base address.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "locosim_core.cuh"
+
+struct HostModel {
+  std::vector<int> ints;      // all int fields in wire order, then body_level, body_dofmask, dof_frow
+  std::vector<float> reals;   // all real fields in wire order (fp32)
+  int nb, nv, ng, nu, np, nm, integrator, cone, iterations, nlevel, nfric, has_damping;
+  float timestep, gravity[3], impratio, tolerance, meaninertia;
+  int max_condim;
+};
+
+static inline std::string parse_model(HostModel& h, const int* ints, int n_ints, const double* reals, int n_reals) {
+  if (n_ints < MPI_HEADER_LEN || ints[MPI_MAGIC] != LOCOSIM_MP_MAGIC) return "bad ModelPack magic";
+  if (ints[MPI_VERSION] != LOCOSIM_MP_VERSION) return "ModelPack version mismatch";
+  int nb = h.nb = ints[MPI_NBODY], nv = h.nv = ints[MPI_NV], ng = h.ng = ints[MPI_NGEOM], nu = h.nu = ints[MPI_NU],
+      np = h.np = ints[MPI_NPAIR], nm = h.nm = ints[MPI_NMESHVERT];
+  h.integrator = ints[MPI_INTEGRATOR]; h.cone = ints[MPI_CONE]; h.iterations = ints[MPI_ITERATIONS];
+  h.timestep = (float)reals[MPR_TIMESTEP];
+  for (int k = 0; k < 3; k++) h.gravity[k] = (float)reals[MPR_GRAV_X + k];
+  h.impratio = (float)reals[MPR_IMPRATIO]; h.tolerance = (float)reals[MPR_TOLERANCE];
+  h.meaninertia = (float)reals[MPR_MEANINERTIA];
+  if (nv > 31) return "nv > 31 not supported by the dof bitmask";
+  size_t ni = 0, nr = 0;
+#define X(name, cnt) ni += (size_t)(cnt);
+  LOCOSIM_MP_INT_FIELDS(X)
+#undef X
+#define X(name, cnt) nr += (size_t)(cnt);
+  LOCOSIM_MP_REAL_FIELDS(X)
+#undef X
+  if ((size_t)n_ints != MPI_HEADER_LEN + ni || (size_t)n_reals != MPR_HEADER_LEN + nr) return "ModelPack size mismatch";
+  h.ints.assign(ints + MPI_HEADER_LEN, ints + n_ints);
+  h.reals.resize(nr);
+  for (size_t i = 0; i < nr; i++) h.reals[i] = (float)reals[MPR_HEADER_LEN + i];
+  // locate the arrays we need for the derived tables
+  const int* ip = h.ints.data();
+  const int *body_parentid = 0, *body_lastdof = 0, *dof_parentid = 0, *geom_condim = 0;
+#define X(name, cnt) if (std::string(#name) == "body_parentid") body_parentid = ip; \
+                     if (std::string(#name) == "body_lastdof") body_lastdof = ip;   \
+                     if (std::string(#name) == "dof_parentid") dof_parentid = ip;   \
+                     if (std::string(#name) == "geom_condim") geom_condim = ip;     \
+                     ip += (cnt);
+  LOCOSIM_MP_INT_FIELDS(X)
+#undef X
+  const float* rp = h.reals.data();
+  const float *dof_frictionloss = 0, *dof_damping = 0;
+#define X(name, cnt) if (std::string(#name) == "dof_frictionloss") dof_frictionloss = rp; \
+                     if (std::string(#name) == "dof_damping") dof_damping = rp;           \
+                     rp += (cnt);
+  LOCOSIM_MP_REAL_FIELDS(X)
+#undef X
+  std::vector<int> level(nb, 0), mask(nb, 0), frow(nv, -1);
+  int nlevel = 1;
+  for (int b = 1; b < nb; b++) {
+    level[b] = level[body_parentid[b]] + 1;
+    if (level[b] + 1 > nlevel) nlevel = level[b] + 1;
+    int msk = 0;
+    for (int d = body_lastdof[b]; d >= 0; d = dof_parentid[d]) msk |= (1 << d);
+    mask[b] = msk;
+    if (b > 1 && body_parentid[b] == 0) return "more than one kinematic tree (root body) is not supported";
+  }
+  int nfric = 0;
+  h.has_damping = 0;
+  for (int d = 0; d < nv; d++) {
+    if (dof_frictionloss[d] > 0) frow[d] = nfric++;
+    if (dof_damping[d] > 0) h.has_damping = 1;
+  }
+  h.max_condim = 1;
+  for (int g = 0; g < ng; g++) if (geom_condim[g] > h.max_condim) h.max_condim = geom_condim[g];
+  h.nlevel = nlevel; h.nfric = nfric;
+  h.ints.insert(h.ints.end(), level.begin(), level.end());
+  h.ints.insert(h.ints.end(), mask.begin(), mask.end());
+  h.ints.insert(h.ints.end(), frow.begin(), frow.end());
+  (void)nu; (void)np; (void)nm;
+  return "";
+}
+
+static inline void bind_model(DevModel& m, const HostModel& h, const int* ibase, const float* rbase) {
+  m.nb = h.nb; m.nv = h.nv; m.ng = h.ng; m.nu = h.nu; m.np = h.np; m.nm = h.nm;
+  m.integrator = h.integrator; m.cone = h.cone; m.iterations = h.iterations; m.nlevel = h.nlevel; m.nfric = h.nfric;
+  m.timestep = h.timestep; m.gravity[0] = h.gravity[0]; m.gravity[1] = h.gravity[1]; m.gravity[2] = h.gravity[2];
+  m.impratio = h.impratio; m.tolerance = h.tolerance; m.meaninertia = h.meaninertia; m.has_damping = h.has_damping;
+  const int nb = h.nb, nv = h.nv, ng = h.ng, nu = h.nu, np = h.np, nm = h.nm;
+  const int* ip = ibase;
+  const float* rp = rbase;
+#define X(name, cnt) m.name = ip; ip += (cnt);
+  LOCOSIM_MP_INT_FIELDS(X)
+#undef X
+#define X(name, cnt) m.name = rp; rp += (cnt);
+  LOCOSIM_MP_REAL_FIELDS(X)
+#undef X
+  m.body_level = ip; ip += nb;
+  m.body_dofmask = ip; ip += nb;
+  m.dof_frow = ip; ip += nv;
+  (void)nu; (void)np; (void)nm; (void)ng;
+}
+
+struct HostTask {
+  std::vector<int> ints;
+  std::vector<float> reals;
+  int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter0, recenter1, ri[4], use_absorbing;
+  float rp[2];
+};
+
+static inline std::string parse_task(HostTask& t, int nu, int nv, const int* ti, int nti, const double* tr, int ntr) {
+  if (nti < TKI_HEADER_LEN || ti[TKI_MAGIC] != LOCOSIM_TASK_MAGIC) return "bad TaskSpec magic";
+  if (ti[TKI_VERSION] != LOCOSIM_TASK_VERSION) return "TaskSpec version mismatch";
+  t.obs_dim = ti[TKI_OBS_DIM]; t.n_done = ti[TKI_N_DONE]; t.reward_type = ti[TKI_REWARD_TYPE];
+  t.n_substeps = ti[TKI_N_SUBSTEPS]; t.n_traj = ti[TKI_N_TRAJ]; t.traj_len = ti[TKI_TRAJ_LEN]; t.n_goal = ti[TKI_N_GOAL];
+  t.recenter0 = ti[TKI_RECENTER0]; t.recenter1 = ti[TKI_RECENTER1];
+  for (int k = 0; k < 4; k++) t.ri[k] = ti[TKI_REWARD_I0 + k];
+  t.use_absorbing = ti[TKI_USE_ABSORBING];
+  t.rp[0] = (float)tr[TKR_REWARD_P0]; t.rp[1] = (float)tr[TKR_REWARD_P1];
+  size_t ni = 2 * (size_t)t.obs_dim + t.n_done;
+  size_t nr = 2 * (size_t)nu + 2 * (size_t)t.n_done + (size_t)t.n_traj * t.traj_len * (2 * nv + t.n_goal);
+  if ((size_t)nti != TKI_HEADER_LEN + ni || (size_t)ntr != TKR_HEADER_LEN + nr) return "TaskSpec size mismatch";
+  if (t.n_goal > 4) return "n_goal > 4";
+  t.ints.assign(ti + TKI_HEADER_LEN, ti + nti);
+  t.reals.resize(nr);
+  for (size_t i = 0; i < nr; i++) t.reals[i] = (float)tr[TKR_HEADER_LEN + i];
+  return "";
+}
+
+static inline void bind_task(DevTask& d, const HostTask& t, int nu, const int* ibase, const float* rbase) {
+  d.obs_dim = t.obs_dim; d.n_done = t.n_done; d.reward_type = t.reward_type; d.n_substeps = t.n_substeps;
+  d.n_traj = t.n_traj; d.traj_len = t.traj_len; d.n_goal = t.n_goal; d.recenter0 = t.recenter0; d.recenter1 = t.recenter1;
+  for (int k = 0; k < 4; k++) d.ri[k] = t.ri[k];
+  d.use_absorbing = t.use_absorbing; d.rp[0] = t.rp[0]; d.rp[1] = t.rp[1];
+  const int* ip = ibase;
+  d.obs_src_type = ip; ip += t.obs_dim; d.obs_src_idx = ip; ip += t.obs_dim; d.done_obs_idx = ip;
+  const float* rp = rbase;
+  d.act_mean = rp; rp += nu; d.act_delta = rp; rp += nu; d.done_lo = rp; rp += t.n_done; d.done_hi = rp; rp += t.n_done;
+  d.table = rp;
+}

@@ -1,0 +1,161 @@
+"""
+ctypes binding of the CUDA engine's C-ABI (include/locosim.h -> loco_mujoco_b200/liblocosim_cuda.so).
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device is visible, constructing an engine
+raises. (The fp64 CPU oracle under oracle/ is test infrastructure and is never imported from here.)
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblocosim_cuda.so")
+
+
+class EngineUnavailable(RuntimeError):
+    pass
+
+
+def load_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_LIB_PATH):
+        raise EngineUnavailable("CUDA engine library not built: %s (run `python -c 'import __graft_entry__ as g; "
+                                "g.build()'`)" % _LIB_PATH)
+    lib = ctypes.CDLL(_LIB_PATH)
+    vp, ip = ctypes.c_void_p, ctypes.c_int
+    lib.locosim_create.restype = ip
+    lib.locosim_create.argtypes = [vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ctypes.c_uint64, ctypes.c_int64,
+                                   ctypes.POINTER(vp)]
+    lib.locosim_destroy.restype = None
+    lib.locosim_destroy.argtypes = [vp]
+    lib.locosim_last_error.restype = ctypes.c_char_p
+    lib.locosim_last_error.argtypes = [vp]
+    for name in ("locosim_num_envs", "locosim_obs_dim", "locosim_action_dim", "locosim_nq"):
+        getattr(lib, name).restype = ip
+        getattr(lib, name).argtypes = [vp]
+    lib.locosim_set_solver.restype = ip
+    lib.locosim_set_solver.argtypes = [vp, ctypes.c_float, ctypes.c_float, ip, ip]
+    lib.locosim_reset.restype = ip
+    lib.locosim_reset.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.locosim_step.restype = ip
+    lib.locosim_step.argtypes = [vp, vp, vp, vp, vp, vp, ip, vp]
+    lib.locosim_get_state.restype = ip
+    lib.locosim_get_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.locosim_set_state.restype = ip
+    lib.locosim_set_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.locosim_get_counters.restype = ip
+    lib.locosim_get_counters.argtypes = [vp, vp, vp]
+    lib.locosim_launch_info.restype = ip
+    lib.locosim_launch_info.argtypes = [vp, ctypes.POINTER(ip), ctypes.POINTER(ip), ctypes.POINTER(ip)]
+    _LIB = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ["locosim_create", "locosim_destroy", "locosim_last_error", "locosim_num_envs", "locosim_obs_dim",
+                    "locosim_action_dim", "locosim_nq", "locosim_set_solver", "locosim_reset", "locosim_step",
+                    "locosim_get_state", "locosim_set_state", "locosim_get_counters", "locosim_launch_info"]
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class CudaEngine:
+    """n_envs independent worlds of one compiled model on one GPU; all I/O are torch.cuda tensors."""
+
+    def __init__(self, model_blobs, task_blobs, n_envs, device=0, seed=0, env_id_offset=0):
+        import torch
+        if not torch.cuda.is_available():
+            raise EngineUnavailable("no CUDA device visible: the locosim engine has no CPU path")
+        self.torch = torch
+        self.lib = load_library()
+        mi, mr = model_blobs
+        ti, tr = task_blobs
+        mi = np.ascontiguousarray(mi, dtype=np.int32)
+        mr = np.ascontiguousarray(mr, dtype=np.float64)
+        ti = np.ascontiguousarray(ti, dtype=np.int32)
+        tr = np.ascontiguousarray(tr, dtype=np.float64)
+        h = ctypes.c_void_p()
+        rc = self.lib.locosim_create(mi.ctypes.data, len(mi), mr.ctypes.data, len(mr), ti.ctypes.data, len(ti),
+                                     tr.ctypes.data, len(tr), int(n_envs), int(device), int(seed), int(env_id_offset),
+                                     ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError("locosim_create failed: %s" % self.lib.locosim_last_error(None).decode())
+        self.h = h
+        self.device = torch.device("cuda", device)
+        self.n_envs = int(n_envs)
+        self.obs_dim = self.lib.locosim_obs_dim(h)
+        self.action_dim = self.lib.locosim_action_dim(h)
+        self.nq = self.lib.locosim_nq(h)
+        self.obs = torch.zeros((n_envs, self.obs_dim), dtype=torch.float32, device=self.device)
+        self.next_obs = torch.zeros((n_envs, self.obs_dim), dtype=torch.float32, device=self.device)
+        self.reward = torch.zeros((n_envs,), dtype=torch.float32, device=self.device)
+        self.done = torch.zeros((n_envs,), dtype=torch.uint8, device=self.device)
+        self.launches = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("locosim: %s" % self.lib.locosim_last_error(self.h).decode())
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.locosim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_solver(self, tolerance=1e-5, ls_tolerance=0.01, max_iter=20, ls_iter=16):
+        self._check(self.lib.locosim_set_solver(self.h, tolerance, ls_tolerance, max_iter, ls_iter))
+
+    def reset(self, mask=None, traj_no=None, step_no=None, out=None):
+        out = self.next_obs if out is None else out
+        self._check(self.lib.locosim_reset(self.h, _ptr(mask), _ptr(traj_no), _ptr(step_no), _ptr(out), self._stream()))
+        self.launches += 1
+        return out
+
+    def step(self, action, auto_reset=True, want_next_obs=True):
+        """action: float32 cuda [n_envs, action_dim] (contiguous). Returns (obs, reward, done, next_obs) views."""
+        if action.dtype != self.torch.float32 or not action.is_contiguous() or action.device != self.device:
+            raise ValueError("action must be a contiguous float32 tensor on %s" % self.device)
+        if tuple(action.shape) != (self.n_envs, self.action_dim):
+            raise ValueError("action shape %s != %s" % (tuple(action.shape), (self.n_envs, self.action_dim)))
+        self._check(self.lib.locosim_step(self.h, _ptr(action), _ptr(self.obs), _ptr(self.reward), _ptr(self.done),
+                                          _ptr(self.next_obs) if want_next_obs else None, int(bool(auto_reset)),
+                                          self._stream()))
+        self.launches += 1
+        return self.obs, self.reward, self.done, self.next_obs
+
+    def get_state(self):
+        t = self.torch
+        q = t.empty((self.n_envs, self.nq), dtype=t.float32, device=self.device)
+        v = t.empty_like(q)
+        w = t.empty_like(q)
+        self._check(self.lib.locosim_get_state(self.h, _ptr(q), _ptr(v), _ptr(w), self._stream()))
+        return q, v, w
+
+    def set_state(self, qpos, qvel, qacc_warmstart=None):
+        for x in (qpos, qvel, qacc_warmstart):
+            if x is not None and (x.dtype != self.torch.float32 or not x.is_contiguous()):
+                raise ValueError("state tensors must be contiguous float32")
+        self._check(self.lib.locosim_set_state(self.h, _ptr(qpos), _ptr(qvel), _ptr(qacc_warmstart), self._stream()))
+
+    def counters(self):
+        t = self.torch
+        c = t.empty((self.n_envs, 4), dtype=t.int32, device=self.device)
+        self._check(self.lib.locosim_get_counters(self.h, _ptr(c), self._stream()))
+        return c
+
+    def launch_info(self):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self.lib.locosim_launch_info(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return dict(warps_per_block=a.value, smem_bytes=b.value, blocks=c.value)

@@ -1,0 +1,587 @@
+"""
+LocoEnv facade over the batched CUDA engine.
+
+Same public surface as the reference's `LocoEnv` (/root/reference/loco_mujoco/environments/base.py:25-969):
+`make`, `register`, `get_all_task_names`, `list_registered_loco_mujoco`, `reset`, `step`, `reward`, `is_absorbing`,
+`create_dataset`, `play_trajectory`, `load_trajectory`, `get_obs_idx`, `get_all_observation_keys`,
+`get_kinematic_obs_mask`, `info.observation_space / action_space`, `dt`; plus the additive kwargs
+`num_envs`, `device`, `seed`:
+
+* `num_envs=None` (default): drop-in single-env mode. `reset()` returns a float64 numpy observation, `step(a)` returns
+  `(obs, reward, absorbing, info)`; trajectory sampling uses the legacy global numpy RNG exactly like the reference,
+  so `np.random.seed(0)` reproduces the reference's golden rollouts (to fp32 tolerance). No auto-reset.
+* `num_envs=N`: batched mode. `reset()` -> `obs[N, D]` torch.cuda float32, `step(a[N, nu])` ->
+  `(obs, reward, absorbing, info)` with `info["next_obs"]` (the observation to act on after the in-kernel auto-reset).
+
+All physics runs in the CUDA engine (loco_mujoco_b200/csrc); there is no CPU path.
+"""
+import os
+import warnings
+from copy import deepcopy
+from itertools import product
+
+import numpy as np
+
+from .. import mjcf, modelpack
+from ..task import (TaskSpec, OBS_QPOS, OBS_QVEL, OBS_GOAL, REWARD_NONE, REWARD_TARGET_VELOCITY, REWARD_POS)
+from ..trajectory import Trajectory
+from ..utils.reward import NoReward, CustomReward, TargetVelocityReward, PosReward
+
+
+class ObservationType:
+    """Subset of mushroom_rl.utils.mujoco.ObservationType used by the in-scope envs."""
+    JOINT_POS = "JOINT_POS"
+    JOINT_VEL = "JOINT_VEL"
+    SITE_ROT = "SITE_ROT"
+
+
+class Box:
+    """Minimal stand-in for mushroom_rl.utils.spaces.Box (low / high / shape)."""
+
+    def __init__(self, low, high):
+        self.low = np.array(low, dtype=np.float64)
+        self.high = np.array(high, dtype=np.float64)
+
+    @property
+    def shape(self):
+        return self.low.shape
+
+
+class MDPInfo:
+    def __init__(self, observation_space, action_space, gamma, horizon, dt):
+        self.observation_space = observation_space
+        self.action_space = action_space
+        self.gamma = gamma
+        self.horizon = horizon
+        self.dt = dt
+
+    @property
+    def size(self):
+        return self.observation_space.shape + self.action_space.shape
+
+    @property
+    def shape(self):
+        return self.observation_space.shape + self.action_space.shape
+
+
+class ObservationHelper:
+    """Index bookkeeping of the flat observation (what mushroom's ObservationHelper provides to the reference)."""
+
+    def __init__(self, observation_spec, model):
+        self.observation_spec = list(observation_spec)
+        self.obs_idx_map = {}
+        self.obs_low, self.obs_high = [], []
+        self.joint_pos_idx, self.joint_vel_idx = [], []
+        i = 0
+        for key, name, ot in self.observation_spec:
+            n = 9 if ot == ObservationType.SITE_ROT else 1
+            self.obs_idx_map[key] = list(range(i, i + n))
+            if ot == ObservationType.JOINT_POS:
+                j = model.joint_id(name)
+                if model.jnt_limited[j]:
+                    self.obs_low.append(model.jnt_range[j, 0]); self.obs_high.append(model.jnt_range[j, 1])
+                else:
+                    self.obs_low.append(-np.inf); self.obs_high.append(np.inf)
+                self.joint_pos_idx.append(i)
+            else:
+                self.obs_low += [-np.inf] * n
+                self.obs_high += [np.inf] * n
+                if ot == ObservationType.JOINT_VEL:
+                    self.joint_vel_idx.append(i)
+            i += n
+        self.obs_length = i
+
+    def get_all_observation_keys(self):
+        return [k for k, _, _ in self.observation_spec]
+
+    def get_from_obs(self, obs, key):
+        return obs[self.obs_idx_map[key]]
+
+    def get_joint_pos_from_obs(self, obs):
+        return obs[self.joint_pos_idx]
+
+    def get_joint_vel_from_obs(self, obs):
+        return obs[self.joint_vel_idx]
+
+
+def reference_data_root():
+    """Directory that holds `environments/data` and `datasets` of a loco_mujoco checkout, or None."""
+    if os.environ.get("LOCO_MUJOCO_B200_FORCE_BUNDLED"):
+        return None
+    cands = [os.environ.get("LOCO_MUJOCO_PATH")]
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("loco_mujoco")
+        if spec is not None and spec.origin:
+            cands.append(os.path.dirname(spec.origin))
+    except Exception:
+        pass
+    cands.append("/root/reference/loco_mujoco")
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "environments", "data")):
+            return c
+    return None
+
+
+ASSET_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "assets")
+
+
+class LocoEnv:
+    """Base class of all batched locomotion environments."""
+
+    _registered_envs = dict()
+
+    def __init__(self, xml_handles, action_spec, observation_spec, collision_groups=None, gamma=0.99, horizon=1000,
+                 n_substeps=10, reward_type=None, reward_params=None, traj_params=None, random_start=True,
+                 init_step_no=None, timestep=0.001, use_foot_forces=False, default_camera_mode="follow",
+                 use_absorbing_states=True, domain_randomization_config=None, parallel_dom_rand=True,
+                 N_worker_per_xml_dom_rand=4, num_envs=None, device="cuda:0", seed=0, env_id_offset=0,
+                 compiled_model=None, **viewer_params):
+        if type(xml_handles) != list:
+            xml_handles = [xml_handles]
+        self._xml_handles = xml_handles
+        if len(xml_handles) != 1:
+            raise NotImplementedError("multi-model environments (carry tasks with several weights) are not built yet")
+        if use_foot_forces:
+            raise NotImplementedError("use_foot_forces=True is not built yet (SURVEY.md 8(f) item 2)")
+        if domain_randomization_config is not None:
+            raise NotImplementedError("domain randomisation is not built yet (SURVEY.md 8(a) row a10)")
+        self._timestep = timestep
+        self._n_substeps = n_substeps
+        self._n_intermediate_steps = 1
+        self._use_foot_forces = use_foot_forces
+        self._model = compiled_model if compiled_model is not None else mjcf.compile_model(xml_handles[0], timestep=timestep)
+        if timestep is None:
+            self._timestep = self._model.opt_timestep
+        self._models = [self._model]
+        self._action_spec = list(action_spec) if len(action_spec) else list(self._model.actuator_names)
+        self._action_indices = [self._model.actuator_id(n) for n in self._action_spec]
+        if self._action_indices != list(range(self._model.nu)):
+            raise NotImplementedError("action_spec must cover all actuators of the (modified) model in model order")
+        self.obs_helper = ObservationHelper(observation_spec, self._model)
+        self.obs_helpers = [self.obs_helper]
+        lo = self._model.actuator_ctrlrange[:, 0].copy()
+        hi = self._model.actuator_ctrlrange[:, 1].copy()
+        self.info = MDPInfo(Box(self.obs_helper.obs_low, self.obs_helper.obs_high), Box(lo, hi), gamma, horizon, self.dt)
+
+        self._reward_type, self._reward_params = reward_type, reward_params
+        self._reward_function = self._get_reward_function(reward_type, reward_params)
+        self.info.observation_space = Box(*self._get_observation_space())
+        low, high = self.info.action_space.low.copy(), self.info.action_space.high.copy()
+        self.norm_act_mean = (high + low) / 2.0
+        self.norm_act_delta = (high - low) / 2.0
+        self.info.action_space.low[:] = -1.0
+        self.info.action_space.high[:] = 1.0
+
+        self._dataset = None
+        self.trajectories = None
+        if traj_params:
+            self.load_trajectory(traj_params)
+        self._random_start = random_start
+        self._init_step_no = init_step_no
+        self._use_absorbing_states = use_absorbing_states
+
+        self._num_envs = num_envs
+        self._device = device
+        self._seed = seed
+        self._env_id_offset = env_id_offset
+        self._engine = None
+        self._obs = None
+
+    # ---------------------------------------------------------------------------------------------------
+    # construction helpers
+    # ---------------------------------------------------------------------------------------------------
+    @property
+    def dt(self):
+        return self._timestep * self._n_intermediate_steps * self._n_substeps
+
+    @property
+    def num_envs(self):
+        return 1 if self._num_envs is None else self._num_envs
+
+    @property
+    def batched(self):
+        return self._num_envs is not None
+
+    def load_trajectory(self, traj_params, warn=True):
+        if self.trajectories is not None:
+            warnings.warn("New trajectories loaded, which overrides the old ones.", RuntimeWarning)
+        if "processed" in traj_params:
+            self.trajectories = _ProcessedTrajectory(traj_params["processed"])
+        else:
+            self.trajectories = Trajectory(keys=self.get_all_observation_keys(),
+                                           low=self.info.observation_space.low,
+                                           high=self.info.observation_space.high,
+                                           joint_pos_idx=self.obs_helper.joint_pos_idx,
+                                           interpolate_map=self._interpolate_map,
+                                           interpolate_remap=self._interpolate_remap,
+                                           interpolate_map_params=self._get_interpolate_map_params(),
+                                           interpolate_remap_params=self._get_interpolate_remap_params(),
+                                           warn=warn, **traj_params)
+        self._engine = None
+
+    def get_all_observation_keys(self):
+        return self.obs_helper.get_all_observation_keys()
+
+    # ---------------------------------------------------------------------------------------------------
+    # TaskSpec: flatten obs / done / reward / reset table for the engine
+    # ---------------------------------------------------------------------------------------------------
+    def _has_fallen_terms(self):
+        """list of (observation key, low, high): fallen if value < low or value > high."""
+        raise NotImplementedError
+
+    def _goal_features(self, sample):
+        """Per-episode constant observation features derived from a trajectory sample (goal-conditioned envs)."""
+        return []
+
+    def _n_goal(self):
+        return 0
+
+    def _obs_sources(self):
+        """(src_type, src_idx) for every entry of the final observation vector."""
+        types, idxs = [], []
+        for key, name, ot in self.obs_helper.observation_spec[2:]:
+            if ot == ObservationType.JOINT_POS:
+                types.append(OBS_QPOS); idxs.append(self._model.joint_id(name))
+            elif ot == ObservationType.JOINT_VEL:
+                types.append(OBS_QVEL); idxs.append(self._model.joint_id(name))
+            else:
+                raise NotImplementedError(ot)
+        return types, idxs
+
+    def _reward_spec(self):
+        rt = self._reward_type
+        if rt is None:
+            return REWARD_NONE, [], []
+        if rt == "target_velocity":
+            return REWARD_TARGET_VELOCITY, [self.get_obs_idx("dq_pelvis_tx")[0]], [self._reward_params["target_velocity"]]
+        if rt == "x_pos":
+            return REWARD_POS, [self.get_obs_idx("q_pelvis_tx")[0]], []
+        if rt == "custom":
+            return REWARD_NONE, [], []      # evaluated on the host from the returned tensors
+        raise NotImplementedError(rt)
+
+    def _reset_table(self):
+        """[n_traj, T, nq + nv + n_goal] from the (interpolated) trajectories."""
+        tr = self.trajectories
+        nq = self._model.nq
+        n_traj, T = tr.number_of_trajectories, tr.trajectory_length
+        table = np.zeros((n_traj, T, 2 * nq + self._n_goal()))
+        spec = self.obs_helper.observation_spec
+        for k, (key, name, ot) in enumerate(spec):
+            arr = tr.trajectories[tr.keys.index(key)]
+            if ot == ObservationType.JOINT_POS:
+                table[:, :, self._model.joint_id(name)] = arr
+            elif ot == ObservationType.JOINT_VEL:
+                table[:, :, nq + self._model.joint_id(name)] = arr
+        if self._n_goal():
+            for i in range(n_traj):
+                for j in range(T):
+                    sample = [obs[i][j] for obs in tr.trajectories]
+                    table[i, j, 2 * nq:] = self._goal_features(sample)
+        return table
+
+    def task_spec(self):
+        types, idxs = self._obs_sources()
+        keys_to_idx = {}
+        done_terms = []
+        for key, lo, hi in self._has_fallen_terms():
+            done_terms.append((self.get_obs_idx(key)[0], lo, hi))
+        rtype, rints, rparams = self._reward_spec()
+        spec = self.obs_helper.observation_spec
+        recenter = [self._model.joint_id(spec[0][1]), self._model.joint_id(spec[1][1])]
+        if self.trajectories is None:
+            raise ValueError("the CUDA engine needs trajectory data for resets (pass traj_params)")
+        return TaskSpec(types, idxs, done_terms, rtype, rints, rparams, self.norm_act_mean, self.norm_act_delta,
+                        self._n_substeps, self._reset_table(), self._n_goal(), recenter, self._use_absorbing_states)
+
+    def _get_engine(self):
+        if self._engine is None:
+            from ..engine import CudaEngine
+            import torch
+            dev = torch.device(self._device)
+            self._engine = CudaEngine(modelpack.pack(self._model), self.task_spec().pack(), self.num_envs,
+                                      device=dev.index or 0, seed=self._seed, env_id_offset=self._env_id_offset)
+        return self._engine
+
+    # ---------------------------------------------------------------------------------------------------
+    # the hot path
+    # ---------------------------------------------------------------------------------------------------
+    def reward(self, state, action, next_state, absorbing):
+        return self._reward_function(state, action, next_state, absorbing)
+
+    def reset(self, obs=None):
+        eng = self._get_engine()
+        import torch
+        if obs is not None:
+            raise NotImplementedError("reset(obs=...) is not supported by the batched engine yet")
+        self._reward_function.reset_state()
+        if not self.batched:
+            # reference semantics incl. the legacy global numpy RNG draw order (base.py:187-191, trajectory.py:253-259)
+            np.random.randint(0, len(self._models))
+            if self._random_start:
+                traj_no = np.random.randint(0, self.trajectories.number_of_trajectories)
+                step_no = np.random.randint(0, self.trajectories.trajectory_length)
+            elif self._init_step_no is not None:
+                T = self.trajectories.trajectory_length
+                step_no, traj_no = int(self._init_step_no % T), int(self._init_step_no / T)
+            else:
+                traj_no, step_no = np.random.randint(0, self.trajectories.number_of_trajectories), 0
+            self.trajectories.traj_no, self.trajectories.subtraj_step_no = traj_no, step_no
+            t = torch.tensor([traj_no], dtype=torch.int32, device=eng.device)
+            s = torch.tensor([step_no], dtype=torch.int32, device=eng.device)
+            out = eng.reset(traj_no=t, step_no=s)
+            self._obs = out[0].double().cpu().numpy()
+            return self._obs.copy()
+        out = eng.reset()
+        self._obs = out
+        return out
+
+    def step(self, action):
+        eng = self._get_engine()
+        import torch
+        if not self.batched:
+            a = torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, -1), device=eng.device)
+            obs, reward, done, _ = eng.step(a.contiguous(), auto_reset=False, want_next_obs=False)
+            cur = obs[0].double().cpu().numpy()
+            absorbing = bool(done[0].item())
+            if self._reward_type == "custom":
+                r = self._reward_function(self._obs, np.asarray(action), cur, absorbing)
+            else:
+                r = float(reward[0].item())
+            self._obs = cur
+            return cur.copy(), r, absorbing, {}
+        if action.dtype != torch.float32:
+            action = action.float()
+        obs, reward, done, next_obs = eng.step(action.contiguous(), auto_reset=True)
+        info = {"next_obs": next_obs}
+        if self._reward_type == "custom":
+            cb = self._reward_function._reward_callback
+            reward = cb(self._obs, action, obs) if cb is not None else torch.zeros_like(reward)
+        self._obs = next_obs
+        return obs, reward, done.bool(), info
+
+    def is_absorbing(self, obs):
+        return self._has_fallen(obs) if self._use_absorbing_states else False
+
+    def stop(self):
+        pass
+
+    def render(self, record=False):
+        raise NotImplementedError("rendering is out of scope (headless engine)")
+
+    # ---------------------------------------------------------------------------------------------------
+    # observation bookkeeping (reference: base.py:257-276, 729-775)
+    # ---------------------------------------------------------------------------------------------------
+    def get_kinematic_obs_mask(self):
+        return np.arange(len(self.obs_helper.observation_spec) - 2)
+
+    def get_obs_idx(self, key):
+        return [i - 2 for i in self.obs_helper.obs_idx_map[key]]
+
+    def _get_idx(self, keys):
+        if type(keys) != list:
+            keys = [keys]
+        return np.concatenate([self.obs_helper.obs_idx_map[k] for k in keys]) - 2
+
+    def _get_from_obs(self, obs, keys):
+        obs = np.concatenate([[0.0, 0.0], obs])
+        if type(keys) != list:
+            keys = [keys]
+        return np.concatenate([self.obs_helper.get_from_obs(obs, k) for k in keys])
+
+    def _len_qpos_qvel(self):
+        keys = self.get_all_observation_keys()
+        return len([k for k in keys if k.startswith("q_")]), len([k for k in keys if k.startswith("dq_")])
+
+    def _get_observation_space(self):
+        return self.info.observation_space.low[2:], self.info.observation_space.high[2:]
+
+    def _create_observation(self, obs):
+        return np.concatenate([obs[2:]]).flatten()
+
+    def _preprocess_action(self, action):
+        return (np.asarray(action).copy() * self.norm_act_delta) + self.norm_act_mean
+
+    def _has_fallen(self, obs, return_err_msg=False):
+        fallen, msg = False, ""
+        for key, lo, hi in self._has_fallen_terms():
+            v = obs[self.get_obs_idx(key)[0]]
+            if v < lo or v > hi:
+                fallen = True
+                msg += "%s condition violated (%f not in [%f, %f]).\n" % (key, v, lo, hi)
+        return (fallen, msg) if return_err_msg else fallen
+
+    def _get_reward_function(self, reward_type, reward_params):
+        if reward_type == "custom":
+            return CustomReward(**reward_params)
+        if reward_type == "target_velocity":
+            idx = self.get_obs_idx("dq_pelvis_tx")
+            assert len(idx) == 1
+            return TargetVelocityReward(x_vel_idx=idx[0], **reward_params)
+        if reward_type == "x_pos":
+            idx = self.get_obs_idx("q_pelvis_tx")
+            assert len(idx) == 1
+            return PosReward(pos_idx=idx[0])
+        if reward_type is None:
+            return NoReward()
+        raise NotImplementedError("The specified reward has not been implemented: %s" % reward_type)
+
+    # ---------------------------------------------------------------------------------------------------
+    # datasets / replay (reference: base.py:278-386)
+    # ---------------------------------------------------------------------------------------------------
+    def create_dataset(self, ignore_keys=None):
+        if self._dataset is None:
+            if self.trajectories is None:
+                raise ValueError("No trajectory was passed to the environment. To create a dataset pass a trajectory "
+                                 "first.")
+            dataset = self.trajectories.create_dataset(ignore_keys=ignore_keys)
+            for state in dataset["states"]:
+                fallen, msg = self._has_fallen(state, return_err_msg=True)
+                if fallen:
+                    raise ValueError("Some of the states in the created dataset are terminal states. This should not "
+                                     "happen.\n\nViolations:\n" + msg)
+            self._dataset = deepcopy(dataset)
+            return dataset
+        return deepcopy(self._dataset)
+
+    def play_trajectory(self, n_episodes=None, n_steps_per_episode=None, render=False, record=False,
+                        recorder_params=None):
+        """Kinematic replay (no physics is advanced in the reference either: base.py:314-386)."""
+        assert self.trajectories is not None
+        if render or record:
+            raise NotImplementedError("rendering is out of scope (headless engine)")
+        big = np.iinfo(np.int32).max
+        n_episodes = big if n_episodes is None else n_episodes
+        n_steps_per_episode = big if n_steps_per_episode is None else n_steps_per_episode
+        self.trajectories.reset_trajectory()
+        for _ in range(n_episodes):
+            for _ in range(n_steps_per_episode):
+                sample = self.trajectories.get_next_sample()
+                if sample is None:
+                    self.trajectories.reset_trajectory()
+                    sample = self.trajectories.get_current_sample()
+                obs = self._create_observation(np.concatenate(sample))
+                if self._has_fallen(obs):
+                    print("Has fallen!")
+            self.trajectories.reset_trajectory()
+
+    # ---------------------------------------------------------------------------------------------------
+    # interpolation hooks (identity by default, reference: base.py:855-893)
+    # ---------------------------------------------------------------------------------------------------
+    def _get_interpolate_map_params(self):
+        return None
+
+    def _get_interpolate_remap_params(self):
+        return None
+
+    @staticmethod
+    def _interpolate_map(traj, **interpolate_map_params):
+        return np.array(traj)
+
+    @staticmethod
+    def _interpolate_remap(traj, **interpolate_remap_params):
+        return [obs for obs in traj]
+
+    @staticmethod
+    def _delete_from_xml_handle(xml_handle, joints_to_remove, motors_to_remove, equ_constraints):
+        return xml_handle.delete(joints_to_remove, motors_to_remove, equ_constraints)
+
+    @property
+    def xml_handle(self):
+        return self._xml_handles[0]
+
+    @property
+    def xml_handles(self):
+        return self._xml_handles
+
+    # ---------------------------------------------------------------------------------------------------
+    # registry / factory (reference: base.py:820-832, 950-967; mushroom Environment.make)
+    # ---------------------------------------------------------------------------------------------------
+    @classmethod
+    def register(cls):
+        LocoEnv._registered_envs.setdefault(cls.__name__, cls)
+
+    @staticmethod
+    def list_registered_loco_mujoco():
+        return list(LocoEnv._registered_envs.keys())
+
+    @staticmethod
+    def make(env_name, *args, **kwargs):
+        """`LocoEnv.make("UnitreeA1.simple.real", num_envs=4096)`: dotted id -> env class .generate(*id_parts)."""
+        if "." in env_name:
+            parts = env_name.split(".")
+            env_name, args = parts[0], tuple(parts[1:]) + tuple(args)
+        if env_name not in LocoEnv._registered_envs:
+            raise KeyError("unknown environment %r; registered: %s" % (env_name, LocoEnv.list_registered_loco_mujoco()))
+        env = LocoEnv._registered_envs[env_name]
+        return env.generate(*args, **kwargs) if hasattr(env, "generate") else env(*args, **kwargs)
+
+    @classmethod
+    def get_all_task_names(cls):
+        names = []
+        for e in cls.list_registered_loco_mujoco():
+            env = cls._registered_envs[e]
+            for conf in env.valid_task_confs.get_all_combinations():
+                names.append(".".join([env.__name__] + list(conf.values())))
+        return names
+
+
+class _ProcessedTrajectory(Trajectory):
+    """Trajectory restored from already-interpolated arrays (bundled assets; see tools/build_assets.py)."""
+
+    def __init__(self, d):
+        self.keys = [str(k) for k in d["keys"]]
+        self.trajectories = [np.asarray(d["traj_%d" % i]) for i in range(len(self.keys))]
+        self.split_points = np.asarray(d["split_points"])
+        self._traj_info = None
+        self.traj_dt = self.control_dt = float(d["control_dt"])
+        self.subtraj_step_no = 0
+        self.traj_no = 0
+        self.subtraj = self._get_subtraj(self.traj_no)
+
+    def to_dict(self):
+        d = dict(keys=np.array(self.keys), split_points=self.split_points, control_dt=self.control_dt)
+        for i, t in enumerate(self.trajectories):
+            d["traj_%d" % i] = t
+        return d
+
+
+def processed_trajectory_dict(traj):
+    d = dict(keys=np.array(traj.keys), split_points=np.asarray(traj.split_points), control_dt=traj.control_dt)
+    for i, t in enumerate(traj.trajectories):
+        d["traj_%d" % i] = t
+    return d
+
+
+class ValidTaskConf:
+    """All valid task configurations of an environment (reference: base.py:972-1041)."""
+
+    def __init__(self, tasks=None, modes=None, data_types=None, non_combinable=None):
+        self.tasks, self.modes, self.data_types, self.non_combinable = tasks, modes, data_types, non_combinable
+        if non_combinable is not None:
+            for nc in non_combinable:
+                assert len(nc) == 3
+
+    def get_all(self):
+        return deepcopy(self.tasks), deepcopy(self.modes), deepcopy(self.data_types), deepcopy(self.non_combinable)
+
+    def get_all_combinations(self):
+        confs = []
+        for t, m, dt in product(self.tasks or [None], self.modes or [None], self.data_types or [None]):
+            conf = {}
+            if t is not None:
+                conf["task"] = t
+            if m is not None:
+                conf["mode"] = m
+            if dt is not None:
+                conf["data_type"] = dt
+            if self.non_combinable is not None:
+                # (reference quirk kept: a conf is appended once per non-combinable rule it does not match)
+                for bad_t, bad_m, bad_dt in self.non_combinable:
+                    if not ((t == bad_t or bad_t is None) and (m == bad_m or bad_m is None) and
+                            (dt == bad_dt or bad_dt is None)):
+                        confs.append(conf)
+            else:
+                confs.append(conf)
+        return confs

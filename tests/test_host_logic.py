@@ -1,0 +1,100 @@
+"""Host-side logic: task ids, observation indexing, datasets, rewards, has_fallen, TaskSpec packing (CPU only)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import golden, make_env, blobs, ROOT
+
+
+def test_task_names_and_registry():
+    import loco_mujoco_b200 as lm
+    names = lm.get_all_task_names()
+    assert "UnitreeA1.simple.real" in names and "UnitreeA1.hard.real" in names
+    assert "UnitreeA1" in lm.LocoEnv.list_registered_loco_mujoco()
+    with pytest.raises(ValueError):
+        lm.LocoEnv.make("UnitreeA1.nonexistent")
+
+
+def test_a1_spaces_and_indexing(bundled_only):
+    env = make_env("UnitreeA1.simple")
+    assert env.info.observation_space.shape == (37,)
+    assert env.info.action_space.shape == (12,)
+    assert np.all(env.info.action_space.low == -1) and np.all(env.info.action_space.high == 1)
+    assert env.dt == pytest.approx(0.01)
+    # index contract of the reference docstring table (unitreeA1.py:50-164)
+    assert env.get_obs_idx("q_trunk_tz") == [0]
+    assert env.get_obs_idx("q_FR_hip_joint") == [4]
+    assert env.get_obs_idx("dq_trunk_tx") == [16]
+    lo, hi = env.info.observation_space.low, env.info.observation_space.high
+    assert lo[0] == -np.inf and hi[4] == pytest.approx(0.802851) and lo[6] == pytest.approx(-2.69653)
+    assert list(lo[-3:]) == [-1, -1, -np.inf]
+
+
+def test_reset_row_bit_exact_vs_golden(bundled_only):
+    """reset = trajectory table lookup + goal features; no physics involved."""
+    for task in ("UnitreeA1.simple", "UnitreeA1.hard"):
+        env = make_env(task)
+        g = golden(task)
+        spec = env.task_spec()
+        np.random.seed(0)
+        np.random.randint(0, 1)
+        tr = np.random.randint(0, env.trajectories.number_of_trajectories)
+        st = np.random.randint(0, env.trajectories.trajectory_length)
+        row = spec.table[tr, st].copy()
+        nq = env._model.nq
+        row[spec.recenter] = 0
+        src = {0: row[:nq], 1: row[nq:2 * nq], 2: row[2 * nq:]}
+        obs = np.array([src[t][i] for t, i in zip(spec.obs_src_type, spec.obs_src_idx)])
+        assert np.abs(obs - g[0]).max() < 1e-13
+
+
+def test_create_dataset_and_has_fallen(bundled_only):
+    env = make_env("UnitreeA1.simple")
+    d = env.create_dataset()
+    n_traj, T = env.trajectories.number_of_trajectories, env.trajectories.trajectory_length
+    assert d["states"].shape == (n_traj * (T - 1), 37) and d["next_states"].shape == d["states"].shape
+    assert d["last"].sum() == n_traj and d["absorbing"].sum() == 0
+    assert np.allclose(d["states"][1], d["next_states"][0])
+    g = golden("UnitreeA1.simple")
+    assert env._has_fallen(g[-1]) and not env._has_fallen(g[0])
+    assert env.is_absorbing(g[-1])
+
+
+def test_rewards_match_definitions():
+    from loco_mujoco_b200.utils import VelocityVectorReward, TargetVelocityReward, PosReward, NoReward, CustomReward
+    s = np.arange(10, dtype=float) * 0.1
+    assert NoReward()(s, None, s, False) == 0
+    assert PosReward(3)(s, None, s, False) == pytest.approx(0.3)
+    assert TargetVelocityReward(1.25, 4)(s, None, s, False) == pytest.approx(np.exp(-(0.4 - 1.25) ** 2))
+    r = VelocityVectorReward(0, 1, [-3, -2], [-1])(s, None, s, False)
+    assert r == pytest.approx(np.exp(-5 * np.linalg.norm(np.array([0.0, 0.1]) - 0.9 * np.array([0.7, 0.8]))))
+    assert CustomReward(lambda a, b, c: 7.0)(s, None, s, False) == 7.0
+
+
+def test_taskspec_pack_layout(bundled_only):
+    env = make_env("UnitreeA1.simple")
+    (mi, mr), (ti, tr) = blobs(env)
+    assert ti[0] == 0x5441534B and ti[2] == 37 and ti[5] == 10
+    n_traj, T, ncol = env.task_spec().table.shape
+    assert ncol == 2 * 18 + 3
+    assert len(tr) == 8 + 12 + 12 + 3 + 3 + n_traj * T * ncol
+    assert mi[0] == 0x4C4F434F and mi[2] == env._model.nbody and mi[3] == 18
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/loco_mujoco"), reason="needs the reference checkout")
+def test_bundled_assets_match_live_compile():
+    import subprocess, sys
+    code = ("import numpy as np, os;"
+            "from loco_mujoco_b200 import LocoEnv, modelpack;"
+            "e = LocoEnv.make('UnitreeA1.simple.real', debug=True);"
+            "a = modelpack.pack(e._model); t = e.task_spec().pack();"
+            "np.savez('/tmp/_ls_%s.npz' % os.environ.get('TAG'), a0=a[0], a1=a[1], t0=t[0], t1=t[1])")
+    env = dict(os.environ, PYTHONPATH=ROOT, TAG="live")
+    env.pop("LOCO_MUJOCO_B200_FORCE_BUNDLED", None)
+    subprocess.check_call([sys.executable, "-c", code], env=env)
+    env2 = dict(env, TAG="bundled", LOCO_MUJOCO_B200_FORCE_BUNDLED="1")
+    subprocess.check_call([sys.executable, "-c", code], env=env2)
+    a, b = np.load("/tmp/_ls_live.npz"), np.load("/tmp/_ls_bundled.npz")
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k

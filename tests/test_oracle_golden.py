@@ -1,0 +1,37 @@
+"""
+Pins the CPU oracle (oracle/locosim_ref.c) against the reference's own golden rollouts
+(/root/reference/tests/test_datasets/*.npy, copied verbatim to tests/golden/): seeded reset + randn*0.1 actions
+until has_fallen, compared with np.allclose exactly like /root/reference/tests/test_environments.py:88-94.
+"""
+import numpy as np
+import pytest
+
+from helpers import GOLDEN_TASKS, golden, make_env, blobs, reference_draws
+
+
+@pytest.mark.parametrize("task", GOLDEN_TASKS)
+def test_oracle_reproduces_reference_golden(oracle, bundled_only, task):
+    env = make_env(task)
+    g = golden(task)
+    oe = oracle.env(*blobs(env))
+    traj_no, step_no = reference_draws(env)
+    rows = [oe.reset_to(traj_no, step_no)]
+    absorbing = False
+    while not absorbing and len(rows) < 1001:
+        obs, _, absorbing = oe.step(np.random.randn(env.info.action_space.shape[0]) * 0.1)
+        rows.append(obs)
+    rows = np.array(rows)
+    assert rows.shape == g.shape, "episode length (done-flag timing) differs from the golden"
+    assert np.allclose(rows, g), "max abs err %.3e" % np.abs(rows - g).max()
+    # the reset row is pure table lookup: must be (near) bit-exact
+    assert np.abs(rows[0] - g[0]).max() < 1e-13
+    # terminal row satisfies has_fallen, earlier rows do not
+    assert env._has_fallen(rows[-1]) and not any(env._has_fallen(r) for r in rows[:-1])
+
+
+def test_oracle_rollout_threads_deterministic(oracle, bundled_only):
+    env = make_env("UnitreeA1.simple")
+    mb, tb = blobs(env)
+    n1, r1 = oracle.rollout(mb, tb, n_envs=8, n_steps=30, nthreads=1, seed=3)
+    n2, r2 = oracle.rollout(mb, tb, n_envs=8, n_steps=30, nthreads=4, seed=3)
+    assert n1 == n2 == 240 and r1 == r2 and r1 > 0
