@@ -18,7 +18,7 @@
 #define LOCOSIM_TASK_H
 
 #define LOCOSIM_TASK_MAGIC 0x5441534B
-#define LOCOSIM_TASK_VERSION 1
+#define LOCOSIM_TASK_VERSION 2
 
 enum {
   TKI_MAGIC = 0, TKI_VERSION, TKI_OBS_DIM, TKI_N_DONE, TKI_REWARD_TYPE, TKI_N_SUBSTEPS, TKI_N_TRAJ, TKI_TRAJ_LEN,
@@ -26,7 +26,9 @@ enum {
   TKI_USE_ABSORBING,
   TKI_HEADER_LEN = 16
 };
-/* int arrays after the header: obs_src_type[obs_dim], obs_src_idx[obs_dim], done_obs_idx[n_done] */
+/* int arrays after the header: obs_src_type[obs_dim], obs_src_idx[obs_dim], done_obs_idx[n_done],
+ *                                  act_idx[nu]  (data.ctrl[act_idx[k]] = action[k]*act_delta[k] + act_mean[k]; mushroom's
+ *                                  `self._data.ctrl[self._action_indices] = action`)                                  */
 
 enum { TKR_REWARD_P0 = 0, TKR_REWARD_P1, TKR_HEADER_LEN = 8 };
 /* real arrays after the header: act_mean[nu], act_delta[nu], done_lo[n_done], done_hi[n_done],

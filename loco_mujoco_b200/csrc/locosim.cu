@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) step_kernel(DevModel m, DevTask t, Solver
     e.qacc_ws[i] = st.ws[(size_t)env * nv + i];
     e.qacc[i] = 0;
   }
-  for (int i = lane; i < nu; i += 32) e.ctrl[i] = action[(size_t)env * nu + i] * t.act_delta[i] + t.act_mean[i];
+  for (int i = lane; i < nu; i += 32) e.ctrl[t.act_idx[i]] = action[(size_t)env * nu + i] * t.act_delta[i] + t.act_mean[i];
   if (lane < 4) e.goal[lane] = st.goal[(size_t)env * 4 + lane];
   __syncwarp();
   for (int k = lane; k < D; k += 32) e.obs_prev[k] = obs_value(t, e, k);

@@ -72,7 +72,7 @@ struct DevModel {
 struct DevTask {
   int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter0, recenter1, ri[4], use_absorbing;
   float rp[2];
-  const int *obs_src_type, *obs_src_idx, *done_obs_idx;
+  const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx;
   const float *act_mean, *act_delta, *done_lo, *done_hi, *table;
 };
 

@@ -116,7 +116,7 @@ static inline std::string parse_task(HostTask& t, int nu, int nv, const int* ti,
   for (int k = 0; k < 4; k++) t.ri[k] = ti[TKI_REWARD_I0 + k];
   t.use_absorbing = ti[TKI_USE_ABSORBING];
   t.rp[0] = (float)tr[TKR_REWARD_P0]; t.rp[1] = (float)tr[TKR_REWARD_P1];
-  size_t ni = 2 * (size_t)t.obs_dim + t.n_done;
+  size_t ni = 2 * (size_t)t.obs_dim + t.n_done + (size_t)nu;
   size_t nr = 2 * (size_t)nu + 2 * (size_t)t.n_done + (size_t)t.n_traj * t.traj_len * (2 * nv + t.n_goal);
   if ((size_t)nti != TKI_HEADER_LEN + ni || (size_t)ntr != TKR_HEADER_LEN + nr) return "TaskSpec size mismatch";
   if (t.n_goal > 4) return "n_goal > 4";
@@ -132,7 +132,7 @@ static inline void bind_task(DevTask& d, const HostTask& t, int nu, const int* i
   for (int k = 0; k < 4; k++) d.ri[k] = t.ri[k];
   d.use_absorbing = t.use_absorbing; d.rp[0] = t.rp[0]; d.rp[1] = t.rp[1];
   const int* ip = ibase;
-  d.obs_src_type = ip; ip += t.obs_dim; d.obs_src_idx = ip; ip += t.obs_dim; d.done_obs_idx = ip;
+  d.obs_src_type = ip; ip += t.obs_dim; d.obs_src_idx = ip; ip += t.obs_dim; d.done_obs_idx = ip; ip += t.n_done; d.act_idx = ip;
   const float* rp = rbase;
   d.act_mean = rp; rp += nu; d.act_delta = rp; rp += nu; d.done_lo = rp; rp += t.n_done; d.done_hi = rp; rp += t.n_done;
   d.table = rp;

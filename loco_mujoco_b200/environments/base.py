@@ -156,12 +156,12 @@ class LocoEnv:
         self._models = [self._model]
         self._action_spec = list(action_spec) if len(action_spec) else list(self._model.actuator_names)
         self._action_indices = [self._model.actuator_id(n) for n in self._action_spec]
-        if self._action_indices != list(range(self._model.nu)):
-            raise NotImplementedError("action_spec must cover all actuators of the (modified) model in model order")
+        if sorted(self._action_indices) != list(range(self._model.nu)):
+            raise NotImplementedError("action_spec must cover all actuators of the (modified) model")
         self.obs_helper = ObservationHelper(observation_spec, self._model)
         self.obs_helpers = [self.obs_helper]
-        lo = self._model.actuator_ctrlrange[:, 0].copy()
-        hi = self._model.actuator_ctrlrange[:, 1].copy()
+        lo = self._model.actuator_ctrlrange[self._action_indices, 0].copy()
+        hi = self._model.actuator_ctrlrange[self._action_indices, 1].copy()
         self.info = MDPInfo(Box(self.obs_helper.obs_low, self.obs_helper.obs_high), Box(lo, hi), gamma, horizon, self.dt)
 
         self._reward_type, self._reward_params = reward_type, reward_params
@@ -293,7 +293,8 @@ class LocoEnv:
         if self.trajectories is None:
             raise ValueError("the CUDA engine needs trajectory data for resets (pass traj_params)")
         return TaskSpec(types, idxs, done_terms, rtype, rints, rparams, self.norm_act_mean, self.norm_act_delta,
-                        self._n_substeps, self._reset_table(), self._n_goal(), recenter, self._use_absorbing_states)
+                        self._n_substeps, self._reset_table(), self._n_goal(), recenter, self._use_absorbing_states,
+                        act_idx=self._action_indices)
 
     def _get_engine(self):
         if self._engine is None:

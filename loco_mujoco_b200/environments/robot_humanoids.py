@@ -1,0 +1,174 @@
+"""
+Atlas and Talos (walk task, real dataset) on the batched CUDA engine.
+Mirrors /root/reference/loco_mujoco/environments/humanoids/base_robot_humanoid.py:12-260 (generate, dataset keys),
+atlas.py:275-453,485-598 and talos.py:266-466,523-640 (joint/motor removal, observation/action specification,
+_has_fallen windows).
+"""
+import os
+import warnings
+
+import numpy as np
+
+from .. import mjcf
+from ..utils.checks import check_validity_task_mode_dataset
+from .base import LocoEnv, ObservationType, ValidTaskConf, reference_data_root, ASSET_DIR
+
+_PELVIS = ["pelvis_tx", "pelvis_tz", "pelvis_ty", "pelvis_tilt", "pelvis_list", "pelvis_rotation"]
+_ARMS = ["%s_arm_%s" % (s, j) for s in ("l", "r") for j in ("shz", "shx", "ely", "elx", "wry", "wrx")]
+_LEGS = ["%s_%s" % (j, s) for s in ("r", "l") for j in ("hip_flexion", "hip_adduction", "hip_rotation", "knee_angle",
+                                                        "ankle_angle")]
+
+
+class BaseRobotHumanoid(LocoEnv):
+    _xml_rel = None
+    _mini_dataset = None
+
+    def __init__(self, disable_arms=True, disable_back_joint=True, hold_weight=False, weight_mass=None, **kwargs):
+        if hold_weight:
+            raise NotImplementedError("carry tasks (multi-model batches + weight observation) are not built yet")
+        self._disable_arms, self._disable_back_joint, self._hold_weight = disable_arms, disable_back_joint, hold_weight
+        action_spec = self._get_action_specification()
+        observation_spec = self._get_observation_specification()
+        joints_to_remove, motors_to_remove, equ = self._get_xml_modifications()
+        hide = ["q_" + j for j in joints_to_remove] + ["dq_" + j for j in joints_to_remove]
+        observation_spec = [e for e in observation_spec if e[0] not in hide]
+        action_spec = [a for a in action_spec if a not in motors_to_remove]
+        if kwargs.get("compiled_model") is None:
+            root = reference_data_root()
+            if root is None:
+                raise FileNotFoundError("loco_mujoco model data not found (set LOCO_MUJOCO_PATH)")
+            xml_handle = mjcf.XmlHandle(os.path.join(root, "environments", "data", *self._xml_rel))
+            xml_handle = self._modify_xml(xml_handle)
+            xml_handle = self._delete_from_xml_handle(xml_handle, joints_to_remove, motors_to_remove, equ)
+        else:
+            xml_handle = None
+        super().__init__(xml_handle, action_spec, observation_spec, **kwargs)
+
+    def _modify_xml(self, xml_handle):
+        return xml_handle
+
+    def create_dataset(self, ignore_keys=None):
+        if ignore_keys is None:
+            ignore_keys = ["q_pelvis_tx", "q_pelvis_tz"]
+        return super().create_dataset(ignore_keys)
+
+    def _pelvis_terms(self):
+        return [("q_pelvis_ty", -0.3, 0.1), ("q_pelvis_tilt", -np.pi / 4.5, np.pi / 12),
+                ("q_pelvis_list", -np.pi / 12, np.pi / 8), ("q_pelvis_rotation", -np.pi / 10, np.pi / 10)]
+
+    @classmethod
+    def _generate(cls, dataset_stub, task="walk", dataset_type="real", debug=False,
+                  clip_trajectory_to_joint_ranges=False, **kwargs):
+        check_validity_task_mode_dataset(cls.__name__, task, None, dataset_type, *cls.valid_task_confs.get_all())
+        if dataset_type != "real":
+            raise NotImplementedError("perfect datasets are not shipped (network download in the reference)")
+        if task != "walk":
+            raise NotImplementedError("task %r is not built yet" % task)
+        reward_type = kwargs.pop("reward_type", "target_velocity")
+        reward_params = kwargs.pop("reward_params", dict(target_velocity=1.25))
+        root = reference_data_root()
+        if root is not None:
+            mdp = cls(reward_type=reward_type, reward_params=reward_params, **kwargs)
+            path = os.path.join(root, "datasets", "humanoids", "real", dataset_stub)
+            if debug or not os.path.exists(path):
+                if not os.path.exists(path) and not debug:
+                    warnings.warn("Datasets not found, falling back to test datasets. Please download and install "
+                                  "the datasets to use this environment for imitation learning!")
+                path = os.path.join(root, "datasets", "humanoids", "real", "mini_datasets", dataset_stub)
+            mdp.load_trajectory(dict(traj_path=path, traj_dt=1 / 500.0, control_dt=mdp.dt,
+                                     clip_trajectory_to_joint_ranges=clip_trajectory_to_joint_ranges), warn=False)
+        else:
+            from .. import modelpack
+            asset = np.load(os.path.join(ASSET_DIR, "%s.%s.npz" % (cls.__name__, task)), allow_pickle=False)
+            model = modelpack.from_npz_dict({k[6:]: asset[k] for k in asset.files if k.startswith("model_")})
+            mdp = cls(reward_type=reward_type, reward_params=reward_params, compiled_model=model, **kwargs)
+            mdp.load_trajectory(dict(processed={k[5:]: asset[k] for k in asset.files if k.startswith("traj_")}))
+        return mdp
+
+
+class Atlas(BaseRobotHumanoid):
+    valid_task_confs = ValidTaskConf(tasks=["walk", "carry"], data_types=["real", "perfect"])
+    _xml_rel = ("atlas", "atlas.xml")
+
+    def _get_xml_modifications(self):
+        joints, motors = [], []
+        if self._disable_arms:
+            joints += _ARMS
+            motors += [j + "_actuator" for j in _ARMS]
+        if self._disable_back_joint:
+            joints += ["back_bkz", "back_bky", "back_bkx"]
+            motors += ["back_bkz_actuator", "back_bky_actuator", "back_bkx_actuator"]
+        return joints, motors, []
+
+    def _has_fallen_terms(self):
+        terms = self._pelvis_terms()
+        if not self._disable_back_joint:
+            terms += [("q_back_bky", -np.pi / 4, np.pi / 10), ("q_back_bkx", -np.pi / 10, np.pi / 10),
+                      ("q_back_bkz", -np.pi / 4.5, np.pi / 4.5)]
+        return terms
+
+    @staticmethod
+    def _get_observation_specification():
+        joints = _PELVIS + ["back_bkz", "back_bkx", "back_bky"] + _ARMS + _LEGS
+        return [("q_" + j, j, ObservationType.JOINT_POS) for j in joints] + \
+               [("dq_" + j, j, ObservationType.JOINT_VEL) for j in joints]
+
+    @staticmethod
+    def _get_action_specification():
+        return ["back_bkz_actuator", "back_bky_actuator", "back_bkx_actuator"] + [j + "_actuator" for j in _ARMS] + \
+               [j + "_actuator" for j in _LEGS]
+
+    @staticmethod
+    def generate(task="walk", dataset_type="real", **kwargs):
+        return Atlas._generate("02-constspeed_ATLAS.npz", task, dataset_type, **kwargs)
+
+
+class Talos(BaseRobotHumanoid):
+    valid_task_confs = ValidTaskConf(tasks=["walk", "carry"], data_types=["real", "perfect"])
+    _xml_rel = ("talos", "talos.xml")
+
+    def __init__(self, disable_arms=True, disable_back_joint=False, hold_weight=False, weight_mass=None, **kwargs):
+        super().__init__(disable_arms=disable_arms, disable_back_joint=disable_back_joint, hold_weight=hold_weight,
+                         weight_mass=weight_mass, **kwargs)
+
+    def _modify_xml(self, xml_handle):
+        if self._disable_arms:
+            # arms are kept fixed in a reoriented pose (talos.py:503-521)
+            for name, quat in _TALOS_ARM_QUATS.items():
+                b = xml_handle.find("body", name)
+                b.set("quat", " ".join(repr(float(x)) for x in quat))
+        return xml_handle
+
+    def _get_xml_modifications(self):
+        joints, motors = [], []
+        if self._disable_arms:
+            joints += _ARMS
+            motors += [j + "_actuator" for j in _ARMS]
+        if self._disable_back_joint:
+            joints += ["back_bkz", "back_bky"]
+            motors += ["back_bkz_actuator", "back_bky_actuator"]
+        return joints, motors, []
+
+    def _has_fallen_terms(self):
+        terms = self._pelvis_terms()
+        if not self._disable_back_joint:
+            terms += [("q_back_bky", -np.pi / 4, np.pi / 10), ("q_back_bkz", -np.pi / 10, np.pi / 10)]
+        return terms
+
+    @staticmethod
+    def _get_observation_specification():
+        joints = _PELVIS + ["back_bkz", "back_bky"] + _ARMS + _LEGS
+        return [("q_" + j, j, ObservationType.JOINT_POS) for j in joints] + \
+               [("dq_" + j, j, ObservationType.JOINT_VEL) for j in joints]
+
+    @staticmethod
+    def _get_action_specification():
+        return ["back_bkz_actuator", "back_bky_actuator"] + [j + "_actuator" for j in _ARMS] + \
+               [j + "_actuator" for j in _LEGS]
+
+    @staticmethod
+    def generate(task="walk", dataset_type="real", **kwargs):
+        return Talos._generate("02-constspeed_TALOS.npz", task, dataset_type, **kwargs)
+
+
+_TALOS_ARM_QUATS = {"arm_right_4_link": [1.0, 0.0, -0.25, 0.0], "arm_left_4_link": [1.0, 0.0, -0.25, 0.0]}

@@ -319,6 +319,36 @@ def _eig_inertia(full):
     return w, mat_to_quat(V)
 
 
+def mesh_legacy_inertia(v, f):
+    """
+    Volume, centre of mass and inertia tensor (unit density, about the CoM, mesh frame) of a triangle mesh with
+    MuJoCo 2.3.7's default `inertia="legacy"` rule: pyramids from the area-weighted face centroid to every face,
+    each counted with the ABSOLUTE value of its volume.
+    """
+    tri = v[f]                                        # [nf, 3, 3]
+    cen = tri.mean(axis=1)
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    area2 = np.linalg.norm(nrm, axis=1)
+    ok = area2 > 1e-14
+    tri, cen, nrm, area2 = tri[ok], cen[ok], nrm[ok], area2[ok]
+    area = 0.5 * area2
+    unit = nrm / area2[:, None]
+    facecen = (cen * area[:, None]).sum(axis=0) / area.sum()
+    vol = np.abs(np.einsum("ij,ij->i", unit, cen - facecen) * area / 3.0)
+    volume = vol.sum()
+    com = (vol[:, None] * (0.75 * cen + 0.25 * facecen)).sum(axis=0) / volume
+    t = tri - com
+    cen_c = t.mean(axis=1)
+    vol2 = np.abs(np.einsum("ij,ij->i", unit, cen_c) * area / 3.0)
+    P = np.zeros((3, 3))
+    for k in range(len(t)):
+        a, b, c = t[k]
+        ssum = a + b + c
+        P += vol2[k] / 20.0 * (np.outer(a, a) + np.outer(b, b) + np.outer(c, c) + np.outer(ssum, ssum))
+    I = np.trace(P) * np.eye(3) - P
+    return volume, com, I
+
+
 def _geom_inertia(gtype, size, density, mass_attr, mesh=None):
     """mass and diagonal inertia (in geom frame) of a primitive geom."""
     if gtype == GEOM_SPHERE:
@@ -567,16 +597,39 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64):
         use_geoms = (ifg == "true") or (ifg == "auto" and not B["has_inertial"][b])
         if not use_geoms:
             continue
-        gids = [g for g in range(ngeom_all) if G["body"][g] == b and G["type"][g] not in (GEOM_PLANE, GEOM_MESH)]
+        gids = [g for g in range(ngeom_all) if G["body"][g] == b and G["type"][g] != GEOM_PLANE]
         if not gids:
             continue
         masses, coms, Is = [], [], []
         for g in gids:
-            mass, diag = _geom_inertia(G["type"][g], G["size"][g], G["density"][g], G["mass"][g])
             R = quat_to_mat(G["quat"][g])
+            if G["type"][g] == GEOM_MESH:
+                if G["density"][g] == 0 and G["mass"][g] is None:
+                    continue
+                me = meshes[G["mesh"][g]]
+                if "legacy" not in me:
+                    v, f = _load_mesh_vertices(me["file"])
+                    me["legacy"] = mesh_legacy_inertia(v * me["scale"], f)
+                vol, mcom, mI = me["legacy"]
+                # MuJoCo 2.3.7 treats a mesh geom as its *equivalent inertia box* (the box with the mesh's
+                # principal moments at unit density): mass = density * box volume, inertia = that box's.
+                # (Pinned by the Talos.walk golden: pelvis mass/inertia = 0.93377 x the exact mesh values.)
+                w, pq = _eig_inertia([mI[0, 0], mI[1, 1], mI[2, 2], mI[0, 1], mI[0, 2], mI[1, 2]])
+                bs = np.array([np.sqrt(6 * (w[1] + w[2] - w[0]) / vol), np.sqrt(6 * (w[0] + w[2] - w[1]) / vol),
+                               np.sqrt(6 * (w[0] + w[1] - w[2]) / vol)]) / 2
+                mass = G["mass"][g] if G["mass"][g] is not None else 8 * bs.prod() * G["density"][g]
+                diag = mass / 3.0 * np.array([bs[1] ** 2 + bs[2] ** 2, bs[0] ** 2 + bs[2] ** 2, bs[0] ** 2 + bs[1] ** 2])
+                Rp = R @ quat_to_mat(pq)
+                masses.append(mass)
+                coms.append(G["pos"][g] + R @ mcom)
+                Is.append(Rp @ np.diag(diag) @ Rp.T)
+                continue
+            mass, diag = _geom_inertia(G["type"][g], G["size"][g], G["density"][g], G["mass"][g])
             masses.append(mass)
             coms.append(G["pos"][g])
             Is.append(R @ np.diag(diag) @ R.T)
+        if not masses:
+            continue
         mt = sum(masses)
         if mt <= 0:
             continue
@@ -705,7 +758,7 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64):
     m.geom_rbound = rb
 
     # ---- collision pair filter (static part of mj_collision's broadphase) --------------------------------
-    pairs = []
+    pairs, dropped = [], []
     for g1 in range(m.ngeom):
         for g2 in range(g1 + 1, m.ngeom):
             b1, b2 = m.geom_bodyid[g1], m.geom_bodyid[g2]
@@ -721,8 +774,15 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64):
             a, b = (g1, g2) if m.geom_type[g1] <= m.geom_type[g2] else (g2, g1)
             if m.geom_type[a] == GEOM_PLANE and m.geom_type[b] == GEOM_PLANE:
                 continue
+            ta, tb = m.geom_type[a], m.geom_type[b]
+            supported = (ta == GEOM_PLANE and tb in (GEOM_SPHERE, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH)) or \
+                        (ta, tb) in ((GEOM_SPHERE, GEOM_SPHERE), (GEOM_SPHERE, GEOM_CAPSULE), (GEOM_CAPSULE, GEOM_CAPSULE))
+            if not supported:
+                dropped.append((a, b))      # box/cylinder/mesh vs non-plane (mjc_Convex / mjc_BoxBox): not built yet
+                continue
             pairs.append((a, b))
     m.npair = len(pairs)
+    m.n_dropped_pairs = len(dropped)
     m.pair_geom = np.array(pairs, dtype=np.int32).reshape(-1, 2)
 
     # ---- actuators ------------------------------------------------------------------------------------------
@@ -765,8 +825,10 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64):
     m.actuator_bias = np.array(A["bias"], dtype=np.float64).reshape(-1, 3)
 
     for sec in root.findall("equality"):
-        if len(list(sec)):
-            raise NotImplementedError("equality constraints (the in-scope task configurations remove them all)")
+        for eq in sec:
+            if eq.get("active", "true") == "true":
+                raise NotImplementedError("active equality constraint %r (the in-scope task configurations remove "
+                                          "them all or leave them inactive)" % eq.get("name"))
 
     set_constants(m)
     return m

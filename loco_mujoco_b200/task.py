@@ -5,14 +5,14 @@ TaskSpec: everything of LocoEnv.step()/reset() that is not mj_step, flattened fo
 import numpy as np
 
 MAGIC = 0x5441534B
-VERSION = 1
+VERSION = 2
 OBS_QPOS, OBS_QVEL, OBS_GOAL = 0, 1, 2
 REWARD_NONE, REWARD_TARGET_VELOCITY, REWARD_VELOCITY_VECTOR, REWARD_POS = 0, 1, 2, 3
 
 
 class TaskSpec:
     def __init__(self, obs_src_type, obs_src_idx, done_terms, reward_type, reward_ints, reward_params, act_mean,
-                 act_delta, n_substeps, table, n_goal, recenter, use_absorbing=True):
+                 act_delta, n_substeps, table, n_goal, recenter, use_absorbing=True, act_idx=None):
         """
         obs_src_type/idx : per observation entry, where it is gathered from (qpos / qvel / per-episode goal feature)
         done_terms       : list of (obs_index, lo, hi); fallen if obs < lo or obs > hi (strict, like the reference)
@@ -32,6 +32,8 @@ class TaskSpec:
         self.n_goal = int(n_goal)
         self.recenter = list(recenter)
         self.use_absorbing = bool(use_absorbing)
+        self.act_idx = np.arange(len(self.act_mean), dtype=np.int32) if act_idx is None else \
+            np.asarray(act_idx, dtype=np.int32)
 
     @property
     def obs_dim(self):
@@ -43,7 +45,7 @@ class TaskSpec:
         ih[:16] = [MAGIC, VERSION, self.obs_dim, len(self.done_terms), self.reward_type, self.n_substeps, n_traj,
                    traj_len, self.n_goal, self.recenter[0], self.recenter[1]] + self.reward_ints + [int(self.use_absorbing)]
         ints = np.concatenate([ih, self.obs_src_type, self.obs_src_idx,
-                               np.array([t[0] for t in self.done_terms], dtype=np.int32)]).astype(np.int32)
+                               np.array([t[0] for t in self.done_terms], dtype=np.int32), self.act_idx]).astype(np.int32)
         rh = np.zeros(8, dtype=np.float64)
         rh[:2] = self.reward_params
         reals = np.concatenate([rh, self.act_mean, self.act_delta,

@@ -1371,7 +1371,7 @@ typedef struct {
   int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter[2], ri[4], use_absorbing;
   double rp[2];
   int *ibuf; double* rbuf;
-  const int *obs_src_type, *obs_src_idx, *done_obs_idx;
+  const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx;
   const double *act_mean, *act_delta, *done_lo, *done_hi, *table;
 } Task;
 
@@ -1387,6 +1387,7 @@ static int task_load(Task* t, int nu, int nv, const int* ti, int nti, const doub
   t->rp[0] = tr[TKR_REWARD_P0]; t->rp[1] = tr[TKR_REWARD_P1];
   const int* ip = t->ibuf + TKI_HEADER_LEN;
   t->obs_src_type = ip; ip += t->obs_dim; t->obs_src_idx = ip; ip += t->obs_dim; t->done_obs_idx = ip; ip += t->n_done;
+  t->act_idx = ip; ip += nu;
   const double* rp = t->rbuf + TKR_HEADER_LEN;
   t->act_mean = rp; rp += nu; t->act_delta = rp; rp += nu; t->done_lo = rp; rp += t->n_done; t->done_hi = rp; rp += t->n_done;
   t->table = rp; rp += (long)t->n_traj * t->traj_len * (2 * nv + t->n_goal);
@@ -1457,7 +1458,7 @@ void refenv_step(RefEnv* e, const double* action, double* obs, double* reward, i
   const Task* t = &e->task;
   int nu = e->sim->m.nu;
   double ctrl[MAXNV], cur[128];
-  for (int i = 0; i < nu; i++) ctrl[i] = action[i] * t->act_delta[i] + t->act_mean[i];
+  for (int i = 0; i < nu; i++) ctrl[t->act_idx[i]] = action[i] * t->act_delta[i] + t->act_mean[i];
   ref_step(e->sim, ctrl, t->n_substeps);
   build_obs(e, cur);
   int ab = t->use_absorbing ? has_fallen(t, cur) : 0;
