@@ -640,15 +640,16 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64):
             I += Ii + mi * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
         w, q = _eig_inertia([I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]])
         body_mass[b], body_inertia[b], body_ipos[b], body_iquat[b] = mt, w, com, q
+    # mjCBody::Compile order: enforce the minimum mass / inertia first, then balance the triangle inequality
+    bm, bi = float(comp["boundmass"]), float(comp["boundinertia"])
+    for b in range(1, nbody):
+        body_mass[b] = max(body_mass[b], bm)
+        body_inertia[b] = np.maximum(body_inertia[b], bi)
     if comp["balanceinertia"] == "true":
         for b in range(1, nbody):
             A, Bi, C = body_inertia[b]
             if A + Bi < C or A + C < Bi or Bi + C < A:
                 body_inertia[b] = (A + Bi + C) / 3.0
-    bm, bi = float(comp["boundmass"]), float(comp["boundinertia"])
-    for b in range(1, nbody):
-        body_mass[b] = max(body_mass[b], bm)
-        body_inertia[b] = np.maximum(body_inertia[b], bi)
     m.body_mass, m.body_inertia, m.body_ipos, m.body_iquat = body_mass, body_inertia, body_ipos, body_iquat
 
     # weld ids / root ids

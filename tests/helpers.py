@@ -5,7 +5,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-GOLDEN_TASKS = ["UnitreeA1.simple", "UnitreeA1.hard"]
+GOLDEN_TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "HumanoidTorque.walk", "Atlas.walk", "Talos.walk"]
+
+
+# HumanoidTorque.walk: from row 20 on the reference rollout contains a convex mesh-mesh self-contact (fixed arm/hand
+# bones against the leg, mjc_Convex / libccd MPR in MuJoCo) that the engines do not implement yet (DESIGN.md "gaps");
+# rows 0..19 (190 RK4 steps = 760 dynamics evaluations) are pinned.
+PINNED_ROWS = {"HumanoidTorque.walk": 20}
 
 
 def golden(task):
