@@ -15,7 +15,7 @@
 #define LOCOSIM_MODELPACK_H
 
 #define LOCOSIM_MP_MAGIC   0x4C4F434F
-#define LOCOSIM_MP_VERSION 2
+#define LOCOSIM_MP_VERSION 3
 
 /* int header slots */
 enum {
@@ -46,6 +46,7 @@ enum {
   X(dof_invweight0, nv) \
   X(geom_size, 3 * ng) X(geom_pos, 3 * ng) X(geom_quat, 4 * ng) X(geom_friction, 3 * ng) X(geom_margin, ng) \
   X(geom_gap, ng) X(geom_solref, 2 * ng) X(geom_solimp, 5 * ng) X(geom_solmix, ng) X(geom_rbound, ng) \
+  X(geom_invweight0, 2 * ng) \
   X(mesh_vert, 3 * nm) \
   X(actuator_gear, nu) X(actuator_ctrlrange, 2 * nu) X(actuator_forcerange, 2 * nu) X(actuator_gain, nu) \
   X(actuator_bias, 3 * nu)

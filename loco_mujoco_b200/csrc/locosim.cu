@@ -40,12 +40,13 @@ __device__ __forceinline__ void draw_reset(uint64_t seed, int64_t genv, int epis
 // ----------------------------------------------------------------------------------------------------------
 // reset kernel: one warp per env, no shared memory
 // ----------------------------------------------------------------------------------------------------------
-__global__ void reset_kernel(DevModel m, DevTask t, EngineState st, const uint8_t* mask, const int* traj_no,
+__global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* mask, const int* traj_no,
                              const int* step_no, float* obs, int n_envs, uint64_t seed, int64_t env_off) {
   int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (env >= n_envs) return;
   if (mask && !mask[env]) return;
+  const DevModel& m = c_models[ms];
   const int nv = m.nv, ncol = 2 * nv + t.n_goal;
   int tr, sp;
   int ep = st.episode[env];
@@ -78,7 +79,7 @@ __global__ void reset_kernel(DevModel m, DevTask t, EngineState st, const uint8_
 // step kernel: one warp per env, EnvS in dynamic shared memory
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(128) step_kernel(DevModel m, DevTask t, SolverOpts so, EngineState st,
+__global__ void __launch_bounds__(128) step_kernel(int ms, DevTask t, SolverOpts so, EngineState st,
                                                     const float* __restrict__ action, float* __restrict__ obs,
                                                     float* __restrict__ reward, uint8_t* __restrict__ done,
                                                     float* __restrict__ next_obs, int n_envs, int auto_reset,
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(128) step_kernel(DevModel m, DevTask t, Solver
   const int env = blockIdx.x * (blockDim.x >> 5) + warp;
   if (env >= n_envs) return;
   EnvS<C>& e = reinterpret_cast<EnvS<C>*>(smem_raw)[warp];
+  const DevModel& m = c_models[ms];
   const int nv = m.nv, nu = m.nu, D = t.obs_dim;
 
   // ---- load state ----
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(128) step_kernel(DevModel m, DevTask t, Solver
   __syncwarp();
 
   // ---- physics ----
-  physics_substeps(m, e, so, t.n_substeps);
+  physics_substeps(ms, e, so, t.n_substeps);
 
   // ---- observation, termination, reward ----
   bool bad = false;
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(128) step_kernel(DevModel m, DevTask t, Solver
     int tr, sp;
     draw_reset(seed, env_off + env, ep, t.n_traj, t.traj_len, &tr, &sp);
     __syncwarp();
-    reset_env(m, t, e, tr, sp);
+    reset_env(ms, t, e, tr, sp);
     if (lane == 0) { st.episode[env] = ep + 1; st.counters[(size_t)env * 4 + 1] += 1; }
     for (int k = lane; k < t.n_goal; k += 32) st.goal[(size_t)env * 4 + k] = e.goal[k];
   }
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(128) step_kernel(DevModel m, DevTask t, Solver
 // handle
 // ----------------------------------------------------------------------------------------------------------
 struct locosim_handle {
-  int device = 0, n_envs = 0, cfg = -1, wpb = 4, smem = 0;
+  int device = 0, n_envs = 0, cfg = -1, wpb = 4, smem = 0, slot = -1;
   uint64_t seed = 0;
   int64_t env_off = 0;
   HostModel hm;
@@ -174,6 +176,7 @@ struct locosim_handle {
   std::string err;
 };
 static std::string g_create_error;
+static bool g_slot_used[LS_MAX_SLOTS] = {false};
 
 #define CK(call)                                                                      \
   do {                                                                                \
@@ -186,7 +189,8 @@ static std::string g_create_error;
 
 template <class C>
 static bool cfg_fits(const HostModel& hm, const HostTask& ht) {
-  return hm.nv <= C::NV && hm.nb <= C::NB && hm.ng <= C::NG && ht.obs_dim <= C::MAXOBS;
+  return hm.nv <= C::NV && hm.nb <= C::NB && hm.ng <= C::NG && ht.obs_dim <= C::MAXOBS && hm.cone == (int)C::CONE &&
+         hm.integrator == (int)C::RK4;
 }
 template <class C>
 static int cfg_smem() { return (int)sizeof(EnvS<C>); }
@@ -195,7 +199,7 @@ template <class C>
 static int launch_step(locosim_handle* h, const float* a, float* o, float* r, uint8_t* d, float* no, int auto_reset,
                        cudaStream_t s) {
   int blocks = (h->n_envs + h->wpb - 1) / h->wpb;
-  step_kernel<C><<<blocks, h->wpb * 32, h->smem, s>>>(h->dm, h->dt, h->so, h->st, a, o, r, d, no, h->n_envs, auto_reset,
+  step_kernel<C><<<blocks, h->wpb * 32, h->smem, s>>>(h->slot, h->dt, h->so, h->st, a, o, r, d, no, h->n_envs, auto_reset,
                                                       h->seed, h->env_off);
   CK(cudaGetLastError());
   return 0;
@@ -245,11 +249,10 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   if (device < 0 || device >= ndev) return fail("bad device index");
   ce = cudaSetDevice(device);
   if (ce != cudaSuccess) return fail(cudaGetErrorString(ce));
-  if (cfg_fits<CfgA1>(h->hm, h->ht)) h->cfg = 0;
-  else if (cfg_fits<CfgAtlas>(h->hm, h->ht)) h->cfg = 1;
-  else if (cfg_fits<CfgTalos>(h->hm, h->ht)) h->cfg = 2;
-  else if (cfg_fits<CfgHumanoid>(h->hm, h->ht)) h->cfg = 3;
-  else return fail("model exceeds the compiled capacity configurations (locosim_config.h)");
+  if (cfg_fits<CfgEllEuler>(h->hm, h->ht)) h->cfg = 0;
+  else if (cfg_fits<CfgPyrEuler>(h->hm, h->ht)) h->cfg = 1;
+  else if (cfg_fits<CfgPyrRK4>(h->hm, h->ht)) h->cfg = 2;
+  else return fail("no compiled configuration fits this model (cone / integrator / sizes: see locosim_config.h)");
   h->so.tolerance = 1e-5f; h->so.ls_tolerance = 0.01f; h->so.ls_iter = 16;
   h->so.max_iter = h->hm.iterations < 20 ? h->hm.iterations : 20;
   auto up = [&](void** dst, const void* src, size_t bytes) -> bool {
@@ -269,13 +272,17 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   cudaMemset(h->st.qpos, 0, N * nv * 4); cudaMemset(h->st.qvel, 0, N * nv * 4); cudaMemset(h->st.ws, 0, N * nv * 4);
   cudaMemset(h->st.goal, 0, N * 16); cudaMemset(h->st.episode, 0, N * 4); cudaMemset(h->st.counters, 0, N * 16);
   bind_model(h->dm, h->hm, h->d_mints, h->d_mreals);
+  for (int k = 0; k < LS_MAX_SLOTS && h->slot < 0; k++) if (!g_slot_used[k]) { h->slot = k; g_slot_used[k] = true; }
+  if (h->slot < 0) { locosim_destroy(h); g_create_error = "too many live locosim handles (max 8 per process)"; return 1; }
+  if (cudaMemcpyToSymbol(c_models, &h->dm, sizeof(DevModel), sizeof(DevModel) * h->slot) != cudaSuccess) {
+    g_create_error = std::string("cudaMemcpyToSymbol: ") + cudaGetErrorString(cudaGetLastError()); locosim_destroy(h); return 1;
+  }
   bind_task(h->dt, h->ht, h->hm.nu, h->d_tints, h->d_treals);
   int rc = 0;
   switch (h->cfg) {
-    case 0: rc = setup_cfg<CfgA1>(h); break;
-    case 1: rc = setup_cfg<CfgAtlas>(h); break;
-    case 2: rc = setup_cfg<CfgTalos>(h); break;
-    default: rc = setup_cfg<CfgHumanoid>(h); break;
+    case 0: rc = setup_cfg<CfgEllEuler>(h); break;
+    case 1: rc = setup_cfg<CfgPyrEuler>(h); break;
+    default: rc = setup_cfg<CfgPyrRK4>(h); break;
   }
   if (rc) { g_create_error = h->err; locosim_destroy(h); return 1; }
   *out = h;
@@ -284,6 +291,7 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
 
 void locosim_destroy(locosim_t* h) {
   if (!h) return;
+  if (h->slot >= 0) g_slot_used[h->slot] = false;
   cudaFree(h->d_mints); cudaFree(h->d_mreals); cudaFree(h->d_tints); cudaFree(h->d_treals);
   cudaFree(h->st.qpos); cudaFree(h->st.qvel); cudaFree(h->st.ws); cudaFree(h->st.goal); cudaFree(h->st.episode);
   cudaFree(h->st.counters);
@@ -305,7 +313,7 @@ int locosim_reset(locosim_t* h, const uint8_t* d_mask, const int32_t* d_traj, co
                   void* stream) {
   CK(cudaSetDevice(h->device));
   int threads = 128, blocks = (h->n_envs * 32 + threads - 1) / threads;
-  reset_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(h->dm, h->dt, h->st, d_mask, d_traj, d_step, d_obs, h->n_envs,
+  reset_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(h->slot, h->dt, h->st, d_mask, d_traj, d_step, d_obs, h->n_envs,
                                                              h->seed, h->env_off);
   CK(cudaGetLastError());
   return 0;
@@ -316,10 +324,9 @@ int locosim_step(locosim_t* h, const float* a, float* o, float* r, uint8_t* d, f
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   switch (h->cfg) {
-    case 0: return launch_step<CfgA1>(h, a, o, r, d, no, auto_reset, s);
-    case 1: return launch_step<CfgAtlas>(h, a, o, r, d, no, auto_reset, s);
-    case 2: return launch_step<CfgTalos>(h, a, o, r, d, no, auto_reset, s);
-    default: return launch_step<CfgHumanoid>(h, a, o, r, d, no, auto_reset, s);
+    case 0: return launch_step<CfgEllEuler>(h, a, o, r, d, no, auto_reset, s);
+    case 1: return launch_step<CfgPyrEuler>(h, a, o, r, d, no, auto_reset, s);
+    default: return launch_step<CfgPyrRK4>(h, a, o, r, d, no, auto_reset, s);
   }
 }
 

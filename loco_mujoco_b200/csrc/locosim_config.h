@@ -1,7 +1,7 @@
-// Compile-time capacity configurations (one kernel instantiation per robot family).
-// NV/NB must match the compiled model exactly; NG, MAXCON, MAXROW, MAXOBS are capacities.
+// Compile-time configurations: one step-kernel instantiation per (friction cone, integrator) family.
+// NV / NB / NG / MAXOBS are capacities (model sizes must be <=), MAXCON / MAXROW bound the active contact set.
+// CONE: 0 pyramidal, 1 elliptic (mjModel.opt.cone); RK4: 0 Euler, 1 RK4 (mjModel.opt.integrator).
 #pragma once
-struct CfgA1       { enum { NV = 18, NB = 14, NG = 40,  MAXCON = 16, MAXROW = 64, MAXOBS = 40 }; };   // UnitreeA1 (+dir_arrow body folded)
-struct CfgAtlas    { enum { NV = 16, NB = 28, NG = 72,  MAXCON = 16, MAXROW = 64, MAXOBS = 40 }; };
-struct CfgTalos    { enum { NV = 18, NB = 36, NG = 96,  MAXCON = 16, MAXROW = 64, MAXOBS = 40 }; };
-struct CfgHumanoid { enum { NV = 19, NB = 40, NG = 128, MAXCON = 16, MAXROW = 64, MAXOBS = 40 }; };
+struct CfgEllEuler { enum { NV = 18, NB = 14, NG = 40,  MAXCON = 16, MAXROW = 64, MAXOBS = 40, CONE = 1, RK4 = 0 }; };  // UnitreeA1
+struct CfgPyrEuler { enum { NV = 18, NB = 14, NG = 56,  MAXCON = 16, MAXROW = 64, MAXOBS = 40, CONE = 0, RK4 = 0 }; };  // Talos
+struct CfgPyrRK4   { enum { NV = 19, NB = 14, NG = 104, MAXCON = 16, MAXROW = 64, MAXOBS = 40, CONE = 0, RK4 = 1 }; };  // Atlas, HumanoidTorque

@@ -22,6 +22,7 @@
 
 #ifdef LS_EMULATE
 #define LS_DEV static inline
+#define LS_FN static
 #define PAR_FOR(i, n) for (int i = 0; i < (n); i++)
 #define SYNC() ((void)0)
 #define WARP_SUM(x) (x)
@@ -31,7 +32,8 @@
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #else
 #define LS_DEV __device__ __forceinline__
-#define PAR_FOR(i, n) for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
+#define LS_FN __device__ __noinline__
+#define PAR_FOR(i, n) _Pragma("unroll 1") for (int i = (int)(threadIdx.x & 31); i < (n); i += 32)
 #define SYNC() __syncwarp()
 #define WARP_SUM(x) warp_sum(x)
 #define LANE0 if ((threadIdx.x & 31) == 0)
@@ -43,6 +45,7 @@ LS_DEV float warp_sum(float v) {
 }
 #endif
 
+#define NOUNROLL _Pragma("unroll 1")
 #define LS_MINVAL 1e-15f
 #define LS_MINIMP 0.0001f
 #define LS_MAXIMP 0.9999f
@@ -67,6 +70,7 @@ struct DevModel {
   const int* body_level;     // [nb] depth in the tree (world = 0)
   const int* body_dofmask;   // [nb] bit d set if dof d is on the path root..body
   const int* dof_frow;       // [nv] index of the frictionloss row of dof d, or -1
+  const int* tri_ij;         // [nv(nv+1)/2] packed (i << 8) | j of the lower triangle, row major
 };
 
 struct DevTask {
@@ -75,6 +79,15 @@ struct DevTask {
   const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx;
   const float *act_mean, *act_delta, *done_lo, *done_hi, *table;
 };
+
+
+// Model descriptors live in __constant__ memory (8 slots, one per live handle): every warp reads them uniformly.
+#define LS_MAX_SLOTS 8
+#ifdef LS_EMULATE
+static DevModel c_models[LS_MAX_SLOTS];
+#else
+__constant__ DevModel c_models[LS_MAX_SLOTS];
+#endif
 
 struct SolverOpts {
   float tolerance;     // Newton termination (scaled improvement / gradient), fp32-appropriate
@@ -117,6 +130,7 @@ struct EnvS {
   // solver vectors
   float Ma[NV], grad[NV], Mgrad[NV], search[NV], Mv[NV];
   float Y[6][NV];
+  float coneU[8], coneS[8];
   // task
   float goal[4];
   float obs_prev[C::MAXOBS];
@@ -185,7 +199,8 @@ LS_DEV void crossForce(float* res, const float* vel, const float* f) {
 // kinematics (mj_kinematics): level-synchronous over the tree, then geom centres
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-LS_DEV void kinematics(const DevModel& m, EnvS<C>& e) {
+LS_FN void kinematics(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   LANE0 {
     e.xpos[0][0] = e.xpos[0][1] = e.xpos[0][2] = 0;
     e.xquat[0][0] = 1; e.xquat[0][1] = e.xquat[0][2] = e.xquat[0][3] = 0;
@@ -203,7 +218,7 @@ LS_DEV void kinematics(const DevModel& m, EnvS<C>& e) {
       mulquat(quat, e.xquat[p], m.body_quat + 4 * b);
       int jn = m.body_jntnum[b], ja = m.body_jntadr[b];
       quat2mat(mat, quat);
-      for (int k = 0; k < jn; k++) {
+      NOUNROLL for (int k = 0; k < jn; k++) {
         int j = ja + k;
         mulmatvec3(tmp, mat, m.jnt_pos + 3 * j);
         float anchor[3] = {pos[0] + tmp[0], pos[1] + tmp[1], pos[2] + tmp[2]};
@@ -249,7 +264,8 @@ LS_DEV void kinematics(const DevModel& m, EnvS<C>& e) {
 }
 
 template <class C>
-LS_DEV void geom_mat(const DevModel& m, const EnvS<C>& e, int g, float* mat) {
+LS_DEV void geom_mat(const int ms, const EnvS<C>& e, int g, float* mat) {
+  const DevModel& m = c_models[ms];
   float gq[4];
   mulquat(gq, e.xquat[m.geom_bodyid[g]], m.geom_quat + 4 * g);
   quat2mat(mat, gq);
@@ -259,7 +275,8 @@ LS_DEV void geom_mat(const DevModel& m, const EnvS<C>& e, int g, float* mat) {
 // mj_comPos (single kinematic tree: every body's root is body 1, its subtree CoM is the whole-robot CoM)
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-LS_DEV void com_pos(const DevModel& m, EnvS<C>& e) {
+LS_FN void com_pos(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   float sx = 0, sy = 0, sz = 0, sm = 0;
   PAR_FOR(b, m.nb) {
     float ms = m.body_mass[b];
@@ -307,7 +324,7 @@ LS_DEV void com_pos(const DevModel& m, EnvS<C>& e) {
 // dense Cholesky in shared memory (lower triangle, row stride NVP), wavefront over columns
 // ----------------------------------------------------------------------------------------------------------
 template <int NVP>
-LS_DEV void chol_factor(float (*A)[NVP], int n) {
+LS_FN void chol_factor(float (*A)[NVP], int n) {
   for (int j = 0; j < n; j++) {
     // column j: all rows i >= j in parallel; L[i][j] = (A[i][j] - sum_k<j L[i][k] L[j][k]) / L[j][j]
     PAR_FOR(ii, n - j) {
@@ -329,7 +346,7 @@ LS_DEV void chol_factor(float (*A)[NVP], int n) {
 }
 // solve L L^T x = b in place; x in shared memory
 template <int NVP>
-LS_DEV void chol_solve(float (*L)[NVP], int n, float* x) {
+LS_FN void chol_solve(float (*L)[NVP], int n, float* x) {
   // forward: column oriented
   for (int k = 0; k < n; k++) {
     float xk = x[k] / L[k][k];
@@ -355,7 +372,8 @@ LS_DEV void chol_solve(float (*L)[NVP], int n, float* x) {
 // mj_crb + factor: composite inertias up the tree, joint-space inertia M, L = chol(M)
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-LS_DEV void crb_factor(const DevModel& m, EnvS<C>& e) {
+LS_FN void crb_factor(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   PAR_FOR(b, m.nb) for (int k = 0; k < 10; k++) e.crb[b][k] = e.cinert[b][k];
   SYNC();
   for (int lev = m.nlevel - 2; lev >= 1; lev--) {
@@ -364,7 +382,7 @@ LS_DEV void crb_factor(const DevModel& m, EnvS<C>& e) {
       if (m.body_level[b] != lev) continue;
       float acc[10];
       for (int k = 0; k < 10; k++) acc[k] = e.crb[b][k];
-      for (int c = b + 1; c < m.nb; c++)
+      NOUNROLL for (int c = b + 1; c < m.nb; c++)
         if (m.body_parentid[c] == b) for (int k = 0; k < 10; k++) acc[k] += e.crb[c][k];
       for (int k = 0; k < 10; k++) e.crb[b][k] = acc[k];
     }
@@ -375,7 +393,7 @@ LS_DEV void crb_factor(const DevModel& m, EnvS<C>& e) {
   PAR_FOR(i, m.nv) {
     float buf[6];
     mulInertVec(buf, e.crb[m.jnt_bodyid[i]], e.cdof[i]);
-    for (int j = i; j >= 0; j = m.dof_parentid[j]) {
+    NOUNROLL for (int j = i; j >= 0; j = m.dof_parentid[j]) {
       float v = 0;
       for (int k = 0; k < 6; k++) v += e.cdof[j][k] * buf[k];
       if (j == i) v += m.dof_armature[i];
@@ -579,12 +597,13 @@ LS_DEV int capsule_capsule(RawCon* c, float margin, const float* pos1, const flo
 
 // mid-phase test for one candidate pair (see oracle/locosim_ref.c collision(): no margin in the filter)
 template <class C>
-LS_DEV bool pair_filter(const DevModel& m, const EnvS<C>& e, int p) {
+LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p) {
+  const DevModel& m = c_models[ms];
   int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
   float d[3] = {e.gxpos[g2][0] - e.gxpos[g1][0], e.gxpos[g2][1] - e.gxpos[g1][1], e.gxpos[g2][2] - e.gxpos[g1][2]};
   if (m.geom_type[g1] == LS_GEOM_PLANE) {
     float mat1[9];
-    geom_mat(m, e, g1, mat1);
+    geom_mat(ms, e, g1, mat1);
     float n[3] = {mat1[2], mat1[5], mat1[8]};
     return dot3(d, n) <= m.geom_rbound[g2];
   }
@@ -594,15 +613,16 @@ LS_DEV bool pair_filter(const DevModel& m, const EnvS<C>& e, int p) {
 
 // narrow phase of pair p, appending to the env's contact list (executed by a single lane)
 template <class C>
-LS_DEV void pair_narrow(const DevModel& m, EnvS<C>& e, int p) {
+LS_FN void pair_narrow(const int ms, EnvS<C>& e, int p) {
+  const DevModel& m = c_models[ms];
   int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
   int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
   float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
   const float *pos1 = e.gxpos[g1], *pos2 = e.gxpos[g2];
   const float *size1 = m.geom_size + 3 * g1, *size2 = m.geom_size + 3 * g2;
   float mat1[9], mat2[9];
-  geom_mat(m, e, g1, mat1);
-  geom_mat(m, e, g2, mat2);
+  geom_mat(ms, e, g1, mat1);
+  geom_mat(ms, e, g2, mat2);
   RawCon raw[4];
   int n = 0;
   if (t1 == LS_GEOM_PLANE) {
@@ -622,7 +642,7 @@ LS_DEV void pair_narrow(const DevModel& m, EnvS<C>& e, int p) {
     n = capsule_capsule(raw, margin, pos1, mat1, size1, pos2, mat2, size2);
   }
   int base = e.ncon;
-  for (int k = 0; k < n && base < EnvS<C>::MAXCON; k++) {
+  NOUNROLL for (int k = 0; k < n && base < EnvS<C>::MAXCON; k++) {
     // contact parameters (mj_contactParam)
     int p1 = m.geom_priority[g1], p2 = m.geom_priority[g2];
     float gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
@@ -673,21 +693,22 @@ LS_DEV void pair_narrow(const DevModel& m, EnvS<C>& e, int p) {
 }
 
 template <class C>
-LS_DEV void collision(const DevModel& m, EnvS<C>& e) {
+LS_FN void collision(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   LANE0 { e.ncon = 0; }
   SYNC();
 #ifdef LS_EMULATE
-  for (int p = 0; p < m.np; p++) if (pair_filter(m, e, p)) pair_narrow(m, e, p);
+  for (int p = 0; p < m.np; p++) if (pair_filter(ms, e, p)) pair_narrow(ms, e, p);
 #else
   const int lane = LS_LANE;
   for (int base = 0; base < m.np; base += 32) {
     int p = base + lane;
-    bool hit = (p < m.np) && pair_filter(m, e, p);
+    bool hit = (p < m.np) && pair_filter(ms, e, p);
     unsigned mask = __ballot_sync(0xffffffffu, hit);
     while (mask) {
       int src = __ffs(mask) - 1;
       mask &= mask - 1;
-      if (lane == src) pair_narrow(m, e, p);
+      if (lane == src) pair_narrow(ms, e, p);
       __syncwarp();
     }
   }
@@ -698,6 +719,10 @@ LS_DEV void collision(const DevModel& m, EnvS<C>& e) {
 // ----------------------------------------------------------------------------------------------------------
 // constraint assembly (mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint)
 // ----------------------------------------------------------------------------------------------------------
+LS_DEV float ls_pow(float x, float p) {
+  // x in (0,1); p >= 1. power 2 (MuJoCo's default) is exact, other powers go through exp2/log2
+  return p == 2.0f ? x * x : (p == 1.0f ? x : exp2f(p * log2f(x)));
+}
 LS_DEV void get_impedance(const float* solimp_in, float pos, float margin, float* imp) {
   float s0 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[0])), s1 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[1]));
   float s2 = fmaxf(0.0f, solimp_in[2]), s3 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[3])), s4 = fmaxf(1.0f, solimp_in[4]);
@@ -706,13 +731,14 @@ LS_DEV void get_impedance(const float* solimp_in, float pos, float margin, float
   if (x >= 1 || x <= 0) { *imp = (x >= 1 ? s1 : s0); return; }
   float y;
   if (s4 == 1) y = x;
-  else if (x <= s3) y = powf(x, s4) / powf(s3, s4 - 1);
-  else y = 1 - powf(1 - x, s4) / powf(1 - s3, s4 - 1);
+  else if (x <= s3) y = ls_pow(x, s4) / ls_pow(s3, s4 - 1);
+  else y = 1 - ls_pow(1 - x, s4) / ls_pow(1 - s3, s4 - 1);
   *imp = s0 + y * (s1 - s0);
 }
 
 template <class C>
-LS_DEV void make_constraint(const DevModel& m, EnvS<C>& e) {
+LS_FN void make_constraint(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   typedef EnvS<C> E;
   const int nv = m.nv;
   // ---- unit rows: frictionloss (static row slots) ----
@@ -768,7 +794,7 @@ LS_DEV void make_constraint(const DevModel& m, EnvS<C>& e) {
     int nrow = 0, ncon = e.ncon;
     for (int ci = 0; ci < ncon; ci++) {
       int dim = e.con_dim[ci];
-      int nr = (dim == 1) ? 1 : (m.cone == 1 ? dim : 2 * (dim - 1));
+      int nr = (dim == 1) ? 1 : (C::CONE == 1 ? dim : 2 * (dim - 1));
       if (nrow + nr > E::MAXROW) { ncon = ci; break; }
       e.con_row[ci] = nrow;
       nrow += nr;
@@ -785,8 +811,8 @@ LS_DEV void make_constraint(const DevModel& m, EnvS<C>& e) {
     if ((m.body_dofmask[b2] >> d) & 1) s += 1.0f;
     if ((m.body_dofmask[b1] >> d) & 1) s -= 1.0f;
     int dim = e.con_dim[ci], row0 = e.con_row[ci];
-    int nr = (dim == 1) ? 1 : (m.cone == 1 ? dim : 2 * (dim - 1));
-    if (s == 0) { for (int r = 0; r < nr; r++) e.J[row0 + r][d] = 0; continue; }
+    int nr = (dim == 1) ? 1 : (C::CONE == 1 ? dim : 2 * (dim - 1));
+    if (s == 0) { NOUNROLL for (int r = 0; r < nr; r++) e.J[row0 + r][d] = 0; continue; }
     float off[3] = {e.con_pos[ci][0] - e.com[0], e.con_pos[ci][1] - e.com[1], e.con_pos[ci][2] - e.com[2]};
     const float* cd = e.cdof[d];
     float jp[3], t[3];
@@ -797,7 +823,7 @@ LS_DEV void make_constraint(const DevModel& m, EnvS<C>& e) {
     float jd[6];
     for (int r = 0; r < 3; r++) { jd[r] = dot3(f + 3 * r, jp); jd[3 + r] = dot3(f + 3 * r, jr); }
     if (dim == 1) e.J[row0][d] = jd[0];
-    else if (m.cone == 1) { for (int r = 0; r < dim; r++) e.J[row0 + r][d] = jd[r]; }
+    else if (C::CONE == 1) { for (int r = 0; r < dim; r++) e.J[row0 + r][d] = jd[r]; }
     else {
       for (int r = 1; r < dim; r++) {
         float fr = e.con_fri[ci][r - 1];
@@ -809,12 +835,12 @@ LS_DEV void make_constraint(const DevModel& m, EnvS<C>& e) {
   // ---- contact row metadata ----
   PAR_FOR(ci, ncon) {
     int b1 = m.geom_bodyid[e.con_g1[ci]], b2 = m.geom_bodyid[e.con_g2[ci]];
-    float tran = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
-    float rot = m.body_invweight0[2 * b1 + 1] + m.body_invweight0[2 * b2 + 1];
+    float tran = m.geom_invweight0[2 * e.con_g1[ci]] + m.geom_invweight0[2 * e.con_g2[ci]];
+    float rot = m.geom_invweight0[2 * e.con_g1[ci] + 1] + m.geom_invweight0[2 * e.con_g2[ci] + 1];
     int dim = e.con_dim[ci], row0 = nunit + e.con_row[ci];
-    int nr = (dim == 1) ? 1 : (m.cone == 1 ? dim : 2 * (dim - 1));
-    int tp = (dim == 1) ? ROW_CON_FRICTIONLESS : (m.cone == 1 ? ROW_CON_ELLIPTIC : ROW_CON_PYRAMIDAL);
-    for (int r = 0; r < nr; r++) {
+    int nr = (dim == 1) ? 1 : (C::CONE == 1 ? dim : 2 * (dim - 1));
+    int tp = (dim == 1) ? ROW_CON_FRICTIONLESS : (C::CONE == 1 ? ROW_CON_ELLIPTIC : ROW_CON_PYRAMIDAL);
+    NOUNROLL for (int r = 0; r < nr; r++) {
       int rr = row0 + r;
       e.r_type[rr] = tp; e.r_id[rr] = ci; e.r_sign[rr] = (float)r;   // r_sign = row-within-contact for contact rows
       e.r_pos[rr] = e.con_dist[ci]; e.r_margin[rr] = e.con_incl[ci]; e.r_fl[rr] = 0;
@@ -856,17 +882,17 @@ LS_DEV void make_constraint(const DevModel& m, EnvS<C>& e) {
     int dim = e.con_dim[ci];
     if (dim == 1) continue;
     int i = nunit + e.con_row[ci];
-    if (m.cone == 0) {
+    if (C::CONE == 0) {
       float mu = e.con_fri[ci][0] * rsqrtf(fmaxf(LS_MINVAL, m.impratio));
       e.con_mu[ci] = mu;
       float Rpy = 2 * mu * mu * e.r_R[i];
-      for (int j = 0; j < 2 * (dim - 1); j++) e.r_R[i + j] = Rpy;
+      NOUNROLL for (int j = 0; j < 2 * (dim - 1); j++) e.r_R[i + j] = Rpy;
     } else {
       float R0 = e.r_R[i];
       float R1 = R0 / fmaxf(LS_MINVAL, m.impratio);
       e.r_R[i + 1] = R1;
       e.con_mu[ci] = e.con_fri[ci][0] * sqrtf(R1 / R0);
-      for (int j = 1; j < dim - 1; j++)
+      NOUNROLL for (int j = 1; j < dim - 1; j++)
         e.r_R[i + j + 1] = R1 * e.con_fri[ci][0] * e.con_fri[ci][0] / (e.con_fri[ci][j] * e.con_fri[ci][j]);
     }
   }
@@ -879,7 +905,8 @@ LS_DEV void make_constraint(const DevModel& m, EnvS<C>& e) {
 // velocity-dependent smooth terms: comVel, RNE bias, passive, actuation -> qfrc_smooth, qacc_smooth
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-LS_DEV void smooth_forces(const DevModel& m, EnvS<C>& e) {
+LS_FN void smooth_forces(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   const int nv = m.nv;
   // comVel + cacc + per-body force, level by level (cvel/cacc of parent needed)
   LANE0 {
@@ -894,7 +921,7 @@ LS_DEV void smooth_forces(const DevModel& m, EnvS<C>& e) {
       float cvel[6], cacc[6];
       for (int k = 0; k < 6; k++) { cvel[k] = e.cvel[p][k]; cacc[k] = e.cacc[p][k]; }
       int jn = m.body_jntnum[b], ja = m.body_jntadr[b];
-      for (int k = 0; k < jn; k++) {
+      NOUNROLL for (int k = 0; k < jn; k++) {
         int j = ja + k;
         float cdd[6];
         crossMotion(cdd, cvel, e.cdof[j]);
@@ -921,7 +948,7 @@ LS_DEV void smooth_forces(const DevModel& m, EnvS<C>& e) {
       if (m.body_level[b] != lev) continue;
       float acc[6];
       for (int k = 0; k < 6; k++) acc[k] = e.crb[b][k];
-      for (int c = b + 1; c < m.nb; c++)
+      NOUNROLL for (int c = b + 1; c < m.nb; c++)
         if (m.body_parentid[c] == b) for (int k = 0; k < 6; k++) acc[k] += e.crb[c][k];
       for (int k = 0; k < 6; k++) e.crb[b][k] = acc[k];
     }
@@ -956,7 +983,8 @@ LS_DEV void smooth_forces(const DevModel& m, EnvS<C>& e) {
 // Newton solver (mj_solNewton), warp-parallel over rows / matrix entries
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-LS_DEV void mulM(const DevModel& m, const EnvS<C>& e, float* res, const float* v) {
+LS_FN void mulM(const int ms, const EnvS<C>& e, float* res, const float* v) {
+  const DevModel& m = c_models[ms];
   PAR_FOR(i, m.nv) {
     float a = 0;
     for (int j = 0; j < m.nv; j++) a += e.M[i][j] * v[j];
@@ -965,7 +993,8 @@ LS_DEV void mulM(const DevModel& m, const EnvS<C>& e, float* res, const float* v
 }
 // res[r] = (J v)[r] for all rows
 template <class C>
-LS_DEV void mulJ(const DevModel& m, const EnvS<C>& e, float* res, const float* v) {
+LS_FN void mulJ(const int ms, const EnvS<C>& e, float* res, const float* v) {
+  const DevModel& m = c_models[ms];
   const int nunit = e.nunit, nefc = e.nefc, nv = m.nv;
   PAR_FOR(r, nefc) {
     if (r < nunit) res[r] = e.r_sign[r] * v[e.r_id[r]];
@@ -980,7 +1009,8 @@ LS_DEV void mulJ(const DevModel& m, const EnvS<C>& e, float* res, const float* v
 
 // states, forces, cost from jar (= e.r_jar). Returns the constraint cost (all lanes).
 template <class C>
-LS_DEV float constraint_update(const DevModel& m, EnvS<C>& e) {
+LS_FN float constraint_update(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   const int nefc = e.nefc, nunit = e.nunit;
   float cost = 0;
   PAR_FOR(r, nefc) {
@@ -998,12 +1028,12 @@ LS_DEV float constraint_update(const DevModel& m, EnvS<C>& e) {
       float U[6];
       U[0] = jar * mu;
       float TT = 0;
-      for (int j = 1; j < dim; j++) { U[j] = e.r_jar[r + j] * e.con_fri[ci][j - 1]; TT += U[j] * U[j]; }
+      NOUNROLL for (int j = 1; j < dim; j++) { U[j] = e.r_jar[r + j] * e.con_fri[ci][j - 1]; TT += U[j] * U[j]; }
       float N = U[0], T = sqrtf(TT);
       if (N >= mu * T || (T <= 0 && N >= 0)) {
-        for (int j = 0; j < dim; j++) { e.r_force[r + j] = 0; e.r_state[r + j] = ST_SATISFIED; }
+        NOUNROLL for (int j = 0; j < dim; j++) { e.r_force[r + j] = 0; e.r_state[r + j] = ST_SATISFIED; }
       } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-        for (int j = 0; j < dim; j++) {
+        NOUNROLL for (int j = 0; j < dim; j++) {
           float jj = e.r_jar[r + j], Dj = e.r_D[r + j];
           e.r_force[r + j] = -Dj * jj; e.r_state[r + j] = ST_QUADRATIC; cost += 0.5f * Dj * jj * jj;
         }
@@ -1013,7 +1043,7 @@ LS_DEV float constraint_update(const DevModel& m, EnvS<C>& e) {
         cost += 0.5f * Dm * NmT * NmT;
         float f0 = -Dm * NmT * mu;
         e.r_force[r] = f0; e.r_state[r] = ST_CONE;
-        for (int j = 1; j < dim; j++) { e.r_force[r + j] = -f0 / T * U[j] * e.con_fri[ci][j - 1]; e.r_state[r + j] = ST_CONE; }
+        NOUNROLL for (int j = 1; j < dim; j++) { e.r_force[r + j] = -f0 / T * U[j] * e.con_fri[ci][j - 1]; e.r_state[r + j] = ST_CONE; }
       }
     } else {
       if (jar < 0) { e.r_state[r] = ST_QUADRATIC; e.r_force[r] = -D * jar; cost += 0.5f * D * jar * jar; }
@@ -1028,9 +1058,10 @@ LS_DEV float constraint_update(const DevModel& m, EnvS<C>& e) {
 
 // qfrc_constraint = J^T force ; returns total cost incl. Gauss term
 template <class C>
-LS_DEV float update_constraint(const DevModel& m, EnvS<C>& e, float* gauss_out) {
+LS_FN float update_constraint(const int ms, EnvS<C>& e, float* gauss_out) {
+  const DevModel& m = c_models[ms];
   const int nv = m.nv, nrow = e.nrow, nunit = e.nunit;
-  float cost = constraint_update(m, e);
+  float cost = constraint_update(ms, e);
   float g = 0;
   PAR_FOR(d, nv) {
     float a = 0;
@@ -1050,70 +1081,76 @@ LS_DEV float update_constraint(const DevModel& m, EnvS<C>& e, float* gauss_out) 
 }
 
 template <class C>
-LS_DEV void make_hessian(const DevModel& m, EnvS<C>& e) {
+LS_FN void make_hessian(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   typedef EnvS<C> E;
   const int nv = m.nv, nrow = e.nrow, nunit = e.nunit;
   const int ntri = nv * (nv + 1) / 2;
-  // H = M + J^T diag(D active) J  over the lower triangle
+  // per-row weights: D for rows in the quadratic zone, 0 otherwise (r_Jv is free between line searches)
+  PAR_FOR(r, e.nefc) e.r_Jv[r] = (e.r_state[r] == ST_QUADRATIC) ? e.r_D[r] : 0.0f;
+  SYNC();
+  const float* w = e.r_Jv + nunit;
+  // H = M + J^T diag(w) J  over the lower triangle (index table: m.tri_ij packs (i << 8) | j)
   PAR_FOR(idx, ntri) {
-    // idx -> (i, j), j <= i
-    int i = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
-    while ((i + 1) * (i + 2) / 2 <= idx) i++;
-    while (i * (i + 1) / 2 > idx) i--;
-    int j = idx - i * (i + 1) / 2;
+    const int ij = m.tri_ij[idx];
+    const int i = ij >> 8, j = ij & 255;
     float h = e.M[i][j];
-    for (int r = 0; r < nrow; r++) {
-      if (e.r_state[nunit + r] == ST_QUADRATIC) h += e.r_D[nunit + r] * e.J[r][i] * e.J[r][j];
-    }
+#pragma unroll 4
+    for (int r = 0; r < nrow; r++) h += w[r] * e.J[r][i] * e.J[r][j];
     if (i == j) {
       int fr = m.dof_frow[i];
-      if (fr >= 0 && e.r_state[fr] == ST_QUADRATIC) h += e.r_D[fr];
+      if (fr >= 0) h += e.r_Jv[fr];
       int l0 = e.d_lrow[i][0], l1 = e.d_lrow[i][1];
-      if (l0 >= 0 && e.r_state[l0] == ST_QUADRATIC) h += e.r_D[l0];
-      if (l1 >= 0 && e.r_state[l1] == ST_QUADRATIC) h += e.r_D[l1];
+      if (l0 >= 0) h += e.r_Jv[l0];
+      if (l1 >= 0) h += e.r_Jv[l1];
     }
     e.H[i][j] = h;
   }
   SYNC();
   // cone contacts (elliptic, middle zone): H += Jc^T Hc Jc, one contact at a time
-  for (int ci = 0; ci < e.ncon; ci++) {
-    int r0 = nunit + e.con_row[ci];
-    if (e.r_state[r0] != ST_CONE) continue;
-    int dim = e.con_dim[ci];
-    float mu = e.con_mu[ci];
-    float U[6], scl[6];
-    U[0] = e.r_jar[r0] * mu; scl[0] = mu;
-    float TT = 0;
-    for (int j = 1; j < dim; j++) { scl[j] = e.con_fri[ci][j - 1]; U[j] = e.r_jar[r0 + j] * scl[j]; TT += U[j] * U[j]; }
-    float N = U[0], T = sqrtf(TT);
-    float Dm = e.r_D[r0] / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
-    float invT = 1.0f / T;
-    float c1 = mu * N * invT * invT * invT, c2 = mu * mu - mu * N * invT;
-    // Y[a][d] = sum_b Hc[a][b] J[b][d]
-    PAR_FOR(item, dim * nv) {
-      int a = item / nv, d = item - a * nv;
-      float y = 0;
-      for (int b = 0; b < dim; b++) {
-        float h;
-        if (a == 0 && b == 0) h = 1;
-        else if (a == 0) h = -mu * U[b] * invT;
-        else if (b == 0) h = -mu * U[a] * invT;
-        else h = c1 * U[a] * U[b] + (a == b ? c2 : 0.0f);
-        y += Dm * h * scl[a] * scl[b] * e.J[r0 - nunit + b][d];
+  if (C::CONE == 1) {
+    NOUNROLL for (int ci = 0; ci < e.ncon; ci++) {
+      int r0 = nunit + e.con_row[ci];
+      if (e.r_state[r0] != ST_CONE) continue;
+      int dim = e.con_dim[ci];
+      float mu = e.con_mu[ci];
+      float* U = e.coneU;
+      float* scl = e.coneS;
+      float TT = 0;
+      NOUNROLL for (int j = 1; j < dim; j++) { float u = e.r_jar[r0 + j] * e.con_fri[ci][j - 1]; TT += u * u; }
+      PAR_FOR(j, dim) {
+        float sc = j == 0 ? mu : e.con_fri[ci][j - 1];
+        scl[j] = sc; U[j] = e.r_jar[r0 + j] * sc;
       }
-      e.Y[a][d] = y;
+      SYNC();
+      float N = e.r_jar[r0] * mu, T = sqrtf(TT);
+      float Dm = e.r_D[r0] / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
+      float invT = 1.0f / T;
+      float c1 = mu * N * invT * invT * invT, c2 = mu * mu - mu * N * invT;
+      // Y[a][d] = sum_b Hc[a][b] J[b][d]
+      PAR_FOR(item, dim * nv) {
+        int a = item / nv, d = item - a * nv;
+        float y = 0;
+        NOUNROLL for (int b = 0; b < dim; b++) {
+          float h;
+          if (a == 0 && b == 0) h = 1;
+          else if (a == 0) h = -mu * U[b] * invT;
+          else if (b == 0) h = -mu * U[a] * invT;
+          else h = c1 * U[a] * U[b] + (a == b ? c2 : 0.0f);
+          y += Dm * h * scl[a] * scl[b] * e.J[r0 - nunit + b][d];
+        }
+        e.Y[a][d] = y;
+      }
+      SYNC();
+      PAR_FOR(idx, ntri) {
+        const int ij = m.tri_ij[idx];
+        const int i = ij >> 8, j = ij & 255;
+        float h = 0;
+        NOUNROLL for (int a = 0; a < dim; a++) h += e.J[r0 - nunit + a][i] * e.Y[a][j];
+        e.H[i][j] += h;
+      }
+      SYNC();
     }
-    SYNC();
-    PAR_FOR(idx, ntri) {
-      int i = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
-      while ((i + 1) * (i + 2) / 2 <= idx) i++;
-      while (i * (i + 1) / 2 > idx) i--;
-      int j = idx - i * (i + 1) / 2;
-      float h = 0;
-      for (int a = 0; a < dim; a++) h += e.J[r0 - nunit + a][i] * e.Y[a][j];
-      e.H[i][j] += h;
-    }
-    SYNC();
   }
   chol_factor<E::NVP>(e.H, nv);
 }
@@ -1121,7 +1158,8 @@ LS_DEV void make_hessian(const DevModel& m, EnvS<C>& e) {
 struct LSPoint { float alpha, cost, d1, d2; };
 
 template <class C>
-LS_DEV LSPoint ls_eval(const DevModel& m, const EnvS<C>& e, const float* qg, float alpha) {
+LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alpha) {
+  const DevModel& m = c_models[ms];
   const int nefc = e.nefc;
   float c = 0, d1 = 0, d2 = 0;
   PAR_FOR(r, nefc) {
@@ -1139,7 +1177,7 @@ LS_DEV LSPoint ls_eval(const DevModel& m, const EnvS<C>& e, const float* qg, flo
       float mu = e.con_mu[ci];
       float U0 = ja * mu, V0 = jv * mu, UU = 0, UV = 0, VV = 0;
       float qc = 0.5f * D * x * x, q1 = D * x * jv, q2 = D * jv * jv;   // quadratic (bottom zone) pieces
-      for (int j = 1; j < dim; j++) {
+      NOUNROLL for (int j = 1; j < dim; j++) {
         float fr = e.con_fri[ci][j - 1];
         float aj = e.r_jar[r + j], vj = e.r_Jv[r + j], Dj = e.r_D[r + j];
         float u = aj * fr, v = vj * fr;
@@ -1178,11 +1216,12 @@ LS_DEV LSPoint ls_eval(const DevModel& m, const EnvS<C>& e, const float* qg, flo
 }
 
 template <class C>
-LS_DEV float line_search(const DevModel& m, EnvS<C>& e, const SolverOpts& so, float gauss, float scale) {
+LS_FN float line_search(const int ms, EnvS<C>& e, const SolverOpts so, float gauss, float scale) {
+  const DevModel& m = c_models[ms];
   const int nv = m.nv;
   float sn = 0, q1 = 0, q2 = 0;
-  mulM(m, e, e.Mv, e.search);
-  mulJ(m, e, e.r_Jv, e.search);
+  mulM(ms, e, e.Mv, e.search);
+  mulJ(ms, e, e.r_Jv, e.search);
   SYNC();
   PAR_FOR(i, nv) {
     float s = e.search[i];
@@ -1195,8 +1234,8 @@ LS_DEV float line_search(const DevModel& m, EnvS<C>& e, const SolverOpts& so, fl
   if (snorm < LS_MINVAL) return 0;
   float gtol = so.tolerance * so.ls_tolerance * snorm / scale;
   float qg[3] = {gauss, q1, q2};
-  LSPoint p0 = ls_eval(m, e, qg, 0.0f);
-  LSPoint p1 = ls_eval(m, e, qg, p0.alpha - p0.d1 / p0.d2);
+  LSPoint p0 = ls_eval(ms, e, qg, 0.0f);
+  LSPoint p1 = ls_eval(ms, e, qg, p0.alpha - p0.d1 / p0.d2);
   if (p0.cost < p1.cost) p1 = p0;
   if (fabsf(p1.d1) < gtol) return p1.alpha;
   int iter = 0;
@@ -1204,7 +1243,7 @@ LS_DEV float line_search(const DevModel& m, EnvS<C>& e, const SolverOpts& so, fl
   LSPoint p2 = p1;
   while (p1.d1 * dir <= -gtol && iter < so.ls_iter) {
     p2 = p1;
-    p1 = ls_eval(m, e, qg, p1.alpha - p1.d1 / p1.d2);
+    p1 = ls_eval(ms, e, qg, p1.alpha - p1.d1 / p1.d2);
     iter++;
     if (fabsf(p1.d1) < gtol) return p1.alpha;
   }
@@ -1217,7 +1256,7 @@ LS_DEV float line_search(const DevModel& m, EnvS<C>& e, const SolverOpts& so, fl
     float a = best.alpha - best.d1 / best.d2;
     if (!(a > amin && a < amax)) a = 0.5f * (lo.alpha + hi.alpha);
     if (!(a > amin && a < amax)) break;
-    LSPoint pm = ls_eval(m, e, qg, a);
+    LSPoint pm = ls_eval(ms, e, qg, a);
     iter++;
     if (pm.cost < best.cost) best = pm;
     if (fabsf(pm.d1) < gtol) return pm.alpha;
@@ -1228,7 +1267,8 @@ LS_DEV float line_search(const DevModel& m, EnvS<C>& e, const SolverOpts& so, fl
 }
 
 template <class C>
-LS_DEV void update_gradient(const DevModel& m, EnvS<C>& e) {
+LS_FN void update_gradient(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   PAR_FOR(i, m.nv) {
     float g = e.Ma[i] - e.qfrc_smooth[i] - e.qfrc_constraint[i];
     e.grad[i] = g; e.Mgrad[i] = g;
@@ -1238,7 +1278,8 @@ LS_DEV void update_gradient(const DevModel& m, EnvS<C>& e) {
 }
 
 template <class C>
-LS_DEV void fwd_constraint(const DevModel& m, EnvS<C>& e, const SolverOpts& so) {
+LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
+  const DevModel& m = c_models[ms];
   const int nv = m.nv, nefc = e.nefc;
   if (nefc == 0) {
     PAR_FOR(i, nv) { e.qacc[i] = e.qacc_smooth[i]; e.qacc_ws[i] = e.qacc_smooth[i]; e.qfrc_constraint[i] = 0; }
@@ -1248,26 +1289,26 @@ LS_DEV void fwd_constraint(const DevModel& m, EnvS<C>& e, const SolverOpts& so) 
   // ---- warmstart choice ----
   PAR_FOR(i, nv) e.qacc[i] = e.qacc_ws[i];
   SYNC();
-  mulM(m, e, e.Ma, e.qacc);
-  mulJ(m, e, e.r_jar, e.qacc);
+  mulM(ms, e, e.Ma, e.qacc);
+  mulJ(ms, e, e.r_jar, e.qacc);
   SYNC();
   PAR_FOR(r, nefc) e.r_jar[r] -= e.r_aref[r];
   SYNC();
-  float cw = constraint_update(m, e);
+  float cw = constraint_update(ms, e);
   float g = 0;
   PAR_FOR(i, nv) g += 0.5f * (e.Ma[i] - e.qfrc_smooth[i]) * (e.qacc[i] - e.qacc_smooth[i]);
   cw += WARP_SUM(g);
   SYNC();
-  mulJ(m, e, e.r_Jv, e.qacc_smooth);   // r_Jv used as scratch for J*qacc_smooth
+  mulJ(ms, e, e.r_Jv, e.qacc_smooth);   // r_Jv used as scratch for J*qacc_smooth
   SYNC();
   // cost at qacc_smooth: swap in jar = J qacc_smooth - aref
   PAR_FOR(r, nefc) { float t = e.r_jar[r]; e.r_jar[r] = e.r_Jv[r] - e.r_aref[r]; e.r_Jv[r] = t; }
   SYNC();
-  float cs = constraint_update(m, e);
+  float cs = constraint_update(ms, e);
   if (cw > cs) {
     PAR_FOR(i, nv) e.qacc[i] = e.qacc_smooth[i];
     SYNC();
-    mulM(m, e, e.Ma, e.qacc);
+    mulM(ms, e, e.Ma, e.qacc);
   } else {
     PAR_FOR(r, nefc) e.r_jar[r] = e.r_Jv[r];
   }
@@ -1275,22 +1316,22 @@ LS_DEV void fwd_constraint(const DevModel& m, EnvS<C>& e, const SolverOpts& so) 
   // ---- Newton iterations ----
   float scale = 1.0f / (m.meaninertia * (nv > 1 ? nv : 1));
   float gauss;
-  float cost = update_constraint(m, e, &gauss);
-  make_hessian(m, e);
-  update_gradient(m, e);
+  float cost = update_constraint(ms, e, &gauss);
+  make_hessian(ms, e);
+  update_gradient(ms, e);
   PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
   SYNC();
   int iter = 0;
   while (iter < so.max_iter) {
-    float alpha = line_search(m, e, so, gauss, scale);
+    float alpha = line_search(ms, e, so, gauss, scale);
     if (alpha == 0) break;
     PAR_FOR(i, nv) { e.qacc[i] += alpha * e.search[i]; e.Ma[i] += alpha * e.Mv[i]; }
     PAR_FOR(r, nefc) e.r_jar[r] += alpha * e.r_Jv[r];
     SYNC();
     float oldcost = cost;
-    cost = update_constraint(m, e, &gauss);
-    make_hessian(m, e);
-    update_gradient(m, e);
+    cost = update_constraint(ms, e, &gauss);
+    make_hessian(ms, e);
+    update_gradient(ms, e);
     float gn = 0;
     PAR_FOR(i, nv) gn += e.grad[i] * e.grad[i];
     gn = WARP_SUM(gn);
@@ -1311,18 +1352,20 @@ LS_DEV void fwd_constraint(const DevModel& m, EnvS<C>& e, const SolverOpts& so) 
 // forward dynamics + integrators
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-LS_DEV void forward(const DevModel& m, EnvS<C>& e, const SolverOpts& so) {
-  kinematics(m, e);
-  com_pos(m, e);
-  crb_factor(m, e);
-  collision(m, e);
-  make_constraint(m, e);
-  smooth_forces(m, e);
-  fwd_constraint(m, e, so);
+LS_FN void forward(const int ms, EnvS<C>& e, const SolverOpts so) {
+  const DevModel& m = c_models[ms];
+  kinematics(ms, e);
+  com_pos(ms, e);
+  crb_factor(ms, e);
+  collision(ms, e);
+  make_constraint(ms, e);
+  smooth_forces(ms, e);
+  fwd_constraint(ms, e, so);
 }
 
 template <class C>
-LS_DEV void euler_step(const DevModel& m, EnvS<C>& e) {
+LS_FN void euler_step(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
   typedef EnvS<C> E;
   const int nv = m.nv;
   const float h = m.timestep;
@@ -1342,7 +1385,8 @@ LS_DEV void euler_step(const DevModel& m, EnvS<C>& e) {
 }
 
 template <class C>
-LS_DEV void rk4_step(const DevModel& m, EnvS<C>& e, const SolverOpts& so) {
+LS_FN void rk4_step(const int ms, EnvS<C>& e, const SolverOpts so) {
+  const DevModel& m = c_models[ms];
   // classic RK4 (mj_RungeKutta N=4); forward() for stage 0 has already been evaluated by the caller
   const int nv = m.nv;
   const float h = m.timestep;
@@ -1360,7 +1404,7 @@ LS_DEV void rk4_step(const DevModel& m, EnvS<C>& e, const SolverOpts& so) {
       e.qvel[i] = e.x0v[i] + h * A[s] * fa;
     }
     SYNC();
-    forward(m, e, so);
+    forward(ms, e, so);
     PAR_FOR(i, nv) { e.accq[i] += B[s] * e.qvel[i]; e.accv[i] += B[s] * e.qacc[i]; }
     SYNC();
   }
@@ -1369,10 +1413,11 @@ LS_DEV void rk4_step(const DevModel& m, EnvS<C>& e, const SolverOpts& so) {
 }
 
 template <class C>
-LS_DEV void physics_substeps(const DevModel& m, EnvS<C>& e, const SolverOpts& so, int nsub) {
+LS_FN void physics_substeps(const int ms, EnvS<C>& e, const SolverOpts so, int nsub) {
+  const DevModel& m = c_models[ms];
   for (int k = 0; k < nsub; k++) {
-    forward(m, e, so);
-    if (m.integrator == 1) rk4_step(m, e, so); else euler_step(m, e);
+    forward(ms, e, so);
+    if (C::RK4 == 1) rk4_step(ms, e, so); else euler_step(ms, e);
   }
 }
 
@@ -1387,7 +1432,8 @@ LS_DEV float obs_value(const DevTask& t, const EnvS<C>& e, int k) {
 }
 
 template <class C>
-LS_DEV void reset_env(const DevModel& m, const DevTask& t, EnvS<C>& e, int traj_no, int step_no) {
+LS_FN void reset_env(const int ms, const DevTask& t, EnvS<C>& e, int traj_no, int step_no) {
+  const DevModel& m = c_models[ms];
   const int nv = m.nv, ncol = 2 * nv + t.n_goal;
   const float* row = t.table + ((size_t)traj_no * t.traj_len + step_no) * ncol;
   PAR_FOR(i, nv) {

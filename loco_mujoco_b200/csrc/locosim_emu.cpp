@@ -8,59 +8,81 @@
 #include "locosim_config.h"
 #include "locosim_host.h"
 
-typedef CfgHumanoid EmuCfg;   // the largest capacity config
-
-struct Emu {
+struct EmuBase {
   HostModel hm;
   DevModel m;
-  EnvS<EmuCfg> e;
   SolverOpts so;
+  virtual ~EmuBase() {}
+  virtual void reset(const double* q, const double* v) = 0;
+  virtual void step(const double* ctrl, int nsub) = 0;
+  virtual void fwd(const double* ctrl) = 0;
+  virtual void get(double* q, double* v, double* qacc, double* ws) = 0;
+  virtual void set_ws(const double* w) = 0;
+  virtual int info(int k) = 0;
+};
+template <class C>
+struct EmuT : EmuBase {
+  EnvS<C> e;
+  EmuT() { memset(&e, 0, sizeof(e)); }
+  void reset(const double* q, const double* v) override {
+    for (int i = 0; i < m.nv; i++) { e.qpos[i] = (float)q[i]; e.qvel[i] = (float)v[i]; e.qacc_ws[i] = 0; e.qacc[i] = 0; }
+  }
+  void step(const double* ctrl, int nsub) override {
+    for (int i = 0; i < m.nu; i++) e.ctrl[i] = (float)ctrl[i];
+    c_models[0] = m;
+    physics_substeps(0, e, so, nsub);
+  }
+  void fwd(const double* ctrl) override {
+    for (int i = 0; i < m.nu; i++) e.ctrl[i] = (float)ctrl[i];
+    c_models[0] = m;
+    forward(0, e, so);
+  }
+  void get(double* q, double* v, double* qacc, double* ws) override {
+    for (int i = 0; i < m.nv; i++) {
+      if (q) q[i] = e.qpos[i];
+      if (v) v[i] = e.qvel[i];
+      if (qacc) qacc[i] = e.qacc[i];
+      if (ws) ws[i] = e.qacc_ws[i];
+    }
+  }
+  void set_ws(const double* w) override { for (int i = 0; i < m.nv; i++) e.qacc_ws[i] = (float)w[i]; }
+  int info(int k) override { return k == 0 ? e.ncon : (k == 1 ? e.nefc : e.solver_iter); }
 };
 
 extern "C" {
-Emu* emu_create(const int* ints, int n_ints, const double* reals, int n_reals) {
-  Emu* s = new Emu();
-  std::string err = parse_model(s->hm, ints, n_ints, reals, n_reals);
-  if (!err.empty()) { fprintf(stderr, "emu: %s\n", err.c_str()); delete s; return nullptr; }
+EmuBase* emu_create(const int* ints, int n_ints, const double* reals, int n_reals) {
+  HostModel hm;
+  std::string err = parse_model(hm, ints, n_ints, reals, n_reals);
+  if (!err.empty()) { fprintf(stderr, "emu: %s\n", err.c_str()); return nullptr; }
+  EmuBase* s;
+  if (hm.cone == 1 && hm.integrator == 0) s = new EmuT<CfgEllEuler>();
+  else if (hm.cone == 0 && hm.integrator == 0) s = new EmuT<CfgPyrEuler>();
+  else if (hm.cone == 0 && hm.integrator == 1) s = new EmuT<CfgPyrRK4>();
+  else { fprintf(stderr, "emu: no config\n"); return nullptr; }
+  s->hm = hm;
   bind_model(s->m, s->hm, s->hm.ints.data(), s->hm.reals.data());
-  memset(&s->e, 0, sizeof(s->e));
-  s->so.tolerance = 1e-6f; s->so.ls_tolerance = 0.01f; s->so.max_iter = 8; s->so.ls_iter = 16;
+  s->so.tolerance = 1e-5f; s->so.ls_tolerance = 0.01f; s->so.max_iter = 20; s->so.ls_iter = 16;
   return s;
 }
-void emu_destroy(Emu* s) { delete s; }
-void emu_set_opts(Emu* s, float tol, float ls_tol, int max_iter, int ls_iter) {
+void emu_destroy(EmuBase* s) { delete s; }
+void emu_set_opts(EmuBase* s, float tol, float ls_tol, int max_iter, int ls_iter) {
   s->so.tolerance = tol; s->so.ls_tolerance = ls_tol; s->so.max_iter = max_iter; s->so.ls_iter = ls_iter;
 }
-void emu_reset(Emu* s, const double* qpos, const double* qvel) {
-  for (int i = 0; i < s->m.nv; i++) {
-    s->e.qpos[i] = (float)qpos[i]; s->e.qvel[i] = (float)qvel[i]; s->e.qacc_ws[i] = 0; s->e.qacc[i] = 0;
-  }
-}
-void emu_step(Emu* s, const double* ctrl, int nsub) {
-  for (int i = 0; i < s->m.nu; i++) s->e.ctrl[i] = (float)ctrl[i];
-  physics_substeps(s->m, s->e, s->so, nsub);
-}
-void emu_get_state(Emu* s, double* qpos, double* qvel) {
-  for (int i = 0; i < s->m.nv; i++) { qpos[i] = s->e.qpos[i]; qvel[i] = s->e.qvel[i]; }
-}
-int emu_ncon(Emu* s) { return s->e.ncon; }
-int emu_nefc(Emu* s) { return s->e.nefc; }
-int emu_iter(Emu* s) { return s->e.solver_iter; }
+void emu_reset(EmuBase* s, const double* qpos, const double* qvel) { s->reset(qpos, qvel); }
+void emu_step(EmuBase* s, const double* ctrl, int nsub) { s->step(ctrl, nsub); }
+void emu_forward(EmuBase* s, const double* ctrl) { s->fwd(ctrl); }
+void emu_get_state(EmuBase* s, double* qpos, double* qvel) { s->get(qpos, qvel, nullptr, nullptr); }
+void emu_get_qacc(EmuBase* s, double* qacc) { s->get(nullptr, nullptr, qacc, nullptr); }
+void emu_get_ws(EmuBase* s, double* w) { s->get(nullptr, nullptr, nullptr, w); }
+void emu_set_ws(EmuBase* s, const double* w) { s->set_ws(w); }
+int emu_ncon(EmuBase* s) { return s->info(0); }
+int emu_nefc(EmuBase* s) { return s->info(1); }
+int emu_iter(EmuBase* s) { return s->info(2); }
 int emu_sizeof_env(int which) {
   switch (which) {
-    case 0: return (int)sizeof(EnvS<CfgA1>);
-    case 1: return (int)sizeof(EnvS<CfgAtlas>);
-    case 2: return (int)sizeof(EnvS<CfgTalos>);
-    default: return (int)sizeof(EnvS<CfgHumanoid>);
+    case 0: return (int)sizeof(EnvS<CfgEllEuler>);
+    case 1: return (int)sizeof(EnvS<CfgPyrEuler>);
+    default: return (int)sizeof(EnvS<CfgPyrRK4>);
   }
 }
-}
-extern "C" {
-void emu_forward(Emu* s, const double* ctrl) {
-  for (int i = 0; i < s->m.nu; i++) s->e.ctrl[i] = (float)ctrl[i];
-  forward(s->m, s->e, s->so);
-}
-void emu_get_qacc(Emu* s, double* qacc) { for (int i = 0; i < s->m.nv; i++) qacc[i] = s->e.qacc[i]; }
-void emu_get_ws(Emu* s, double* w) { for (int i = 0; i < s->m.nv; i++) w[i] = s->e.qacc_ws[i]; }
-void emu_set_ws(Emu* s, const double* w) { for (int i = 0; i < s->m.nv; i++) s->e.qacc_ws[i] = (float)w[i]; }
 }

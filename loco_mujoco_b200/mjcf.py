@@ -381,7 +381,7 @@ def _geom_inertia(gtype, size, density, mass_attr, mesh=None):
 # ----------------------------------------------------------------------------------------------------------
 # the compiler
 # ----------------------------------------------------------------------------------------------------------
-def compile_model(handle, timestep=None, collision_mesh_max_verts=64):
+def compile_model(handle, timestep=None, collision_mesh_max_verts=64, fuse_static=True):
     """
     Compile an XmlHandle into a Model.
 
@@ -832,6 +832,8 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64):
                                           "them all or leave them inactive)" % eq.get("name"))
 
     set_constants(m)
+    if fuse_static:
+        fuse_static_bodies(m)
     return m
 
 
@@ -938,4 +940,85 @@ def set_constants(m):
         if m.body_weldid[b] == 0:
             biw[b] = 0
     m.body_invweight0 = biw
+    # contacts look invweight up through the geom's body; keeping it per geom makes static-body fusion exact
+    m.geom_invweight0 = biw[m.geom_bodyid].copy() if m.ngeom else np.zeros((0, 2))
     m.stat_meaninertia = float(np.mean(np.diag(M))) if m.nv else 1.0
+
+
+def fuse_static_bodies(m):
+    """
+    Merge every joint-less body into its parent (inertia composed, geoms / sites / child bodies re-expressed in the
+    parent frame). Dynamically identical to the unfused tree (MuJoCo's own `fusestatic`), but the engine then walks
+    9-14 bodies instead of 33-46. Compile-time constants that MuJoCo evaluates per *original* body (body_invweight0
+    used by contacts) were already baked per geom (geom_invweight0) before fusing.
+    """
+    nb = m.nbody
+    parent = m.body_parentid.copy()
+    pos, quat = m.body_pos.copy(), m.body_quat.copy()
+    mass = m.body_mass.copy()
+    ipos = m.body_ipos.copy()
+    # full inertia tensors about the body CoM, in the body frame
+    Ifull = np.zeros((nb, 3, 3))
+    for b in range(nb):
+        R = quat_to_mat(m.body_iquat[b])
+        Ifull[b] = R @ np.diag(m.body_inertia[b]) @ R.T
+    gpos, gquat, gbody = m.geom_pos.copy(), m.geom_quat.copy(), m.geom_bodyid.copy()
+    spos, squat, sbody = m.site_pos.copy(), m.site_quat.copy(), m.site_bodyid.copy()
+    alive = np.ones(nb, dtype=bool)
+    for b in range(nb - 1, 0, -1):
+        p = parent[b]
+        if m.body_jntnum[b] != 0 or p == 0:
+            continue
+        Rb = quat_to_mat(quat[b])
+        # inertia of b expressed in p's frame
+        cb = pos[b] + Rb @ ipos[b]
+        Ib = Rb @ Ifull[b] @ Rb.T
+        mt = mass[p] + mass[b]
+        if mt > 0:
+            c = (mass[p] * ipos[p] + mass[b] * cb) / mt
+            def shift(I, ms, d):
+                return I + ms * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+            Ifull[p] = shift(Ifull[p], mass[p], ipos[p] - c) + shift(Ib, mass[b], cb - c)
+            ipos[p], mass[p] = c, mt
+        for g in range(m.ngeom):
+            if gbody[g] == b:
+                gpos[g] = pos[b] + Rb @ gpos[g]
+                gquat[g] = quat_mul(quat[b], gquat[g])
+                gbody[g] = p
+        for k in range(len(sbody)):
+            if sbody[k] == b:
+                spos[k] = pos[b] + Rb @ spos[k]
+                squat[k] = quat_mul(quat[b], squat[k])
+                sbody[k] = p
+        for c2 in range(b + 1, nb):
+            if alive[c2] and parent[c2] == b:
+                pos[c2] = pos[b] + Rb @ pos[c2]
+                quat[c2] = quat_mul(quat[b], quat[c2])
+                parent[c2] = p
+        alive[b] = False
+    keep = np.nonzero(alive)[0]
+    remap = -np.ones(nb, dtype=np.int64)
+    remap[keep] = np.arange(len(keep))
+    inertia, iquat = np.zeros((len(keep), 3)), np.zeros((len(keep), 4))
+    for k, b in enumerate(keep):
+        I = Ifull[b]
+        if mass[b] > 0 or np.any(I != 0):
+            w, q = _eig_inertia([I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]])
+        else:
+            w, q = np.zeros(3), np.array([1.0, 0, 0, 0])
+        inertia[k], iquat[k] = w, q
+    m.nbody = len(keep)
+    m.body_names = [m.body_names[b] for b in keep]
+    m.body_parentid = remap[parent[keep]].astype(np.int32)
+    m.body_parentid[0] = 0
+    m.body_pos, m.body_quat = pos[keep], quat[keep]
+    m.body_ipos, m.body_iquat, m.body_mass, m.body_inertia = ipos[keep], iquat, mass[keep], inertia
+    for name in ("body_jntadr", "body_jntnum", "body_dofadr", "body_dofnum", "body_lastdof"):
+        setattr(m, name, getattr(m, name)[keep])
+    m.body_invweight0 = m.body_invweight0[keep]
+    m.body_weldid = np.arange(m.nbody, dtype=np.int32)
+    m.body_rootid = np.array([0] + [1] * (m.nbody - 1), dtype=np.int32)
+    m.jnt_bodyid = remap[m.jnt_bodyid].astype(np.int32)
+    m.dof_bodyid = m.jnt_bodyid.copy()
+    m.geom_bodyid, m.geom_pos, m.geom_quat = remap[gbody].astype(np.int32), gpos, gquat
+    m.site_bodyid, m.site_pos, m.site_quat = remap[sbody].astype(np.int32), spos, squat

@@ -6,7 +6,7 @@ Also (de)serialises to .npz so compiled models can ship with the package (the GP
 import numpy as np
 
 MAGIC = 0x4C4F434F
-VERSION = 2
+VERSION = 3
 
 INT_FIELDS = ["body_parentid", "body_jntadr", "body_jntnum", "body_lastdof", "body_rootid",
               "jnt_type", "jnt_bodyid", "jnt_limited", "dof_parentid",
@@ -18,7 +18,7 @@ REAL_FIELDS = ["body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", 
                "qpos0", "qpos_spring",
                "dof_armature", "dof_damping", "dof_frictionloss", "dof_solref", "dof_solimp", "dof_invweight0",
                "geom_size", "geom_pos", "geom_quat", "geom_friction", "geom_margin", "geom_gap", "geom_solref",
-               "geom_solimp", "geom_solmix", "geom_rbound",
+               "geom_solimp", "geom_solmix", "geom_rbound", "geom_invweight0",
                "mesh_vert",
                "actuator_gear", "actuator_ctrlrange", "actuator_forcerange", "actuator_gain", "actuator_bias"]
 SCALARS = ["nbody", "njnt", "nq", "nv", "ngeom", "nu", "npair", "opt_timestep", "opt_integrator", "opt_cone",

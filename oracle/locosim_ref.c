@@ -785,8 +785,8 @@ static void make_constraint(RefSim* s) {
         }
         jd[r][d] = vp; jd[3 + r][d] = vr;
       }
-    double tran = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2];
-    double rot = m->body_invweight0[2 * b1 + 1] + m->body_invweight0[2 * b2 + 1];
+    double tran = m->geom_invweight0[2 * c->geom1] + m->geom_invweight0[2 * c->geom2];
+    double rot = m->geom_invweight0[2 * c->geom1 + 1] + m->geom_invweight0[2 * c->geom2 + 1];
     c->efc_address = n;
     if (dim == 1) {
       memcpy(s->J[n], jd[0], sizeof(double) * nv);
