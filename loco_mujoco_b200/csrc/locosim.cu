@@ -102,8 +102,15 @@ __global__ void __launch_bounds__(128) step_kernel(int ms, DevTask t, SolverOpts
   for (int i = lane; i < nu; i += 32) e.ctrl[t.act_idx[i]] = action[(size_t)env * nu + i] * t.act_delta[i] + t.act_mean[i];
   if (lane < 4) e.goal[lane] = st.goal[(size_t)env * 4 + lane];
   __syncwarp();
-  for (int k = lane; k < D; k += 32) e.obs_prev[k] = obs_value(t, e, k);
-  __syncwarp();
+  // reward depends on the *previous* observation only (utils/reward.py via base.py:170-176): evaluate it now
+  float rew = 0;
+  if (t.reward_type == LS_REWARD_TARGET_VELOCITY) { float d = obs_value(t, e, t.ri[0]) - t.rp[0]; rew = expf(-d * d); }
+  else if (t.reward_type == LS_REWARD_VELOCITY_VECTOR) {
+    float g = obs_value(t, e, t.ri[3]);
+    float dx = obs_value(t, e, t.ri[0]) - g * obs_value(t, e, t.ri[2]);
+    float dy = obs_value(t, e, t.ri[1]) - g * obs_value(t, e, t.ri[2] + 1);
+    rew = expf(-5.0f * sqrtf(dx * dx + dy * dy));
+  } else if (t.reward_type == LS_REWARD_POS) rew = obs_value(t, e, t.ri[0]);
 
   // ---- physics ----
   physics_substeps(ms, e, so, t.n_substeps);
@@ -125,14 +132,7 @@ __global__ void __launch_bounds__(128) step_kernel(int ms, DevTask t, SolverOpts
     obs[(size_t)env * D + k] = v;
   }
   if (lane == 0) {
-    float r = 0;
-    const float* p = e.obs_prev;
-    if (t.reward_type == LS_REWARD_TARGET_VELOCITY) { float d = p[t.ri[0]] - t.rp[0]; r = expf(-d * d); }
-    else if (t.reward_type == LS_REWARD_VELOCITY_VECTOR) {
-      float g = p[t.ri[3]];
-      float dx = p[t.ri[0]] - g * p[t.ri[2]], dy = p[t.ri[1]] - g * p[t.ri[2] + 1];
-      r = expf(-5.0f * sqrtf(dx * dx + dy * dy));
-    } else if (t.reward_type == LS_REWARD_POS) r = p[t.ri[0]];
+    float r = rew;
     reward[env] = r;
     done[env] = is_done ? 1 : 0;
     int* cnt = st.counters + (size_t)env * 4;

@@ -100,41 +100,52 @@ struct SolverOpts {
 // per-environment working set (shared memory, one per warp)
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-struct EnvS {
-  enum { NV = C::NV, NB = C::NB, NG = C::NG, NVP = C::NV + 1, MAXCON = C::MAXCON, MAXROW = C::MAXROW,
-         MAXUNIT = 2 * C::NV, MAXEFC = 2 * C::NV + C::MAXROW };
-  // state
+struct alignas(16) EnvS {
+  enum { NV = C::NV, NB = C::NB, NG = C::NG, NVP = C::NV + 1, JS = (C::NV + 3) & ~3, MAXCON = C::MAXCON, MAXROW = C::MAXROW,
+         MAXUNIT = 2 * C::NV, MAXEFC = 2 * C::NV + C::MAXROW, NRK = C::RK4 ? C::NV : 1 };
+  // state + per-sub-step vectors
   float qpos[NV], qvel[NV], qacc[NV], qacc_ws[NV], ctrl[NV];
   float qfrc_smooth[NV], qacc_smooth[NV], qfrc_constraint[NV];
-  // RK4 scratch
-  float x0q[NV], x0v[NV], accq[NV], accv[NV];
-  // kinematics
-  float xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[NB][3], ximat[NB][9];
-  float xanchor[NV][3], xaxis[NV][3];
+  float x0q[NRK], x0v[NRK], accq[NRK], accv[NRK];           // RK4 accumulators (RK4 configurations only)
+  // kinematics that stays alive through collision / constraint assembly
+  float xpos[NB][3], xquat[NB][4], xmat[NB][9];
   float gxpos[NG][3];
   float com[4];
-  float cinert[NB][10], crb[NB][10], cdof[NV][6], cdof_dot[NV][6], cvel[NB][6], cacc[NB][6];
-  float M[NV][NVP], L[NV][NVP], H[NV][NVP];
+  float cdof[NV][6];
+  float M[NV][NVP], H[NV][NVP];                              // H: chol(M) during smooth_forces, then the Newton Hessian factor
   // contacts
-  int ncon, nunit, nrow, nefc, nlim, solver_iter, pad0, pad1;
-  float con_dist[MAXCON], con_pos[MAXCON][3], con_frame[MAXCON][9], con_fri[MAXCON][5], con_solref[MAXCON][2],
-      con_solimp[MAXCON][5], con_incl[MAXCON], con_mu[MAXCON];
+  int ncon, nunit, nrow, nefc, solver_iter, pad0, pad1, pad2;
+  float con_dist[MAXCON], con_pos[MAXCON][3], con_frame[MAXCON][9], con_fri[MAXCON][5], con_imp[MAXCON], con_K[MAXCON],
+      con_B[MAXCON], con_incl[MAXCON], con_mu[MAXCON];
   int con_dim[MAXCON], con_g1[MAXCON], con_g2[MAXCON], con_row[MAXCON];
-  // constraint rows: [0,nunit) unit rows (friction then limits), [nunit, nunit+nrow) contact rows
-  int r_type[MAXEFC], r_id[MAXEFC], r_state[MAXEFC];
-  float r_sign[MAXEFC];   // unit rows: J entry (+1 friction, -side for limits)
-  float r_pos[MAXEFC], r_margin[MAXEFC], r_fl[MAXEFC], r_diag[MAXEFC];
-  float r_R[MAXEFC], r_D[MAXEFC], r_aref[MAXEFC], r_jar[MAXEFC], r_Jv[MAXEFC], r_force[MAXEFC];
+  // Two phases share storage: (a) smooth dynamics scratch, dead once qfrc_smooth / qacc_smooth are known;
+  // (b) constraint rows [0,nunit) unit rows (frictionloss, then joint limits), [nunit, nunit+nrow) contact rows.
+  union {
+    struct {
+      float xipos[NB][3], ximat[NB][9], xanchor[NV][3], xaxis[NV][3];
+      float cinert[NB][10], crb[NB][10], cdof_dot[NV][6], cvel[NB][6], cacc[NB][6];
+    };
+    struct {
+      int r_ti[MAXEFC];                                      // type | id << 8 | k << 24  (k: row within contact / limit side)
+      float r_D[MAXEFC], r_aref[MAXEFC], r_jar[MAXEFC], r_Jv[MAXEFC], r_force[MAXEFC];
+      unsigned char r_state[MAXEFC];
+    };
+  };
   int d_lrow[NV][2];      // limit row of dof d (side 0/1) or -1
-  float J[MAXROW][NV];
+  alignas(16) float J[MAXROW][JS];   // contact Jacobian rows, zero padded to a float4 multiple
   // solver vectors
   float Ma[NV], grad[NV], Mgrad[NV], search[NV], Mv[NV];
+#ifdef LS_EMULATE
   float Y[6][NV];
+#endif
   float coneU[8], coneS[8];
   // task
   float goal[4];
-  float obs_prev[C::MAXOBS];
 };
+#define ROW_TYPE(ti) ((ti) & 255)
+#define ROW_ID(ti) (((ti) >> 8) & 0xffff)
+#define ROW_K(ti) ((ti) >> 24)
+#define ROW_PACK(type, id, k) ((type) | ((id) << 8) | ((k) << 24))
 
 // ----------------------------------------------------------------------------------------------------------
 // small math
@@ -193,6 +204,34 @@ LS_DEV void crossForce(float* res, const float* vel, const float* f) {
   cross3(b, vel + 3, f + 3);
   res[0] = a[0] + b[0]; res[1] = a[1] + b[1]; res[2] = a[2] + b[2];
   cross3(res + 3, vel, f + 3);
+}
+
+// ---- constraint impedance helpers (mj_makeImpedance) ----
+LS_DEV float ls_pow(float x, float p) {
+  // x in (0,1); p >= 1. power 2 (MuJoCo's default) is exact, other powers go through exp2/log2
+  return p == 2.0f ? x * x : (p == 1.0f ? x : exp2f(p * log2f(x)));
+}
+LS_DEV void get_impedance(const float* solimp_in, float pos, float margin, float* imp) {
+  float s0 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[0])), s1 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[1]));
+  float s2 = fmaxf(0.0f, solimp_in[2]), s3 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[3])), s4 = fmaxf(1.0f, solimp_in[4]);
+  if (s0 == s1 || s2 <= LS_MINVAL) { *imp = 0.5f * (s0 + s1); return; }
+  float x = fabsf((pos - margin) / s2);
+  if (x >= 1 || x <= 0) { *imp = (x >= 1 ? s1 : s0); return; }
+  float y;
+  if (s4 == 1) y = x;
+  else if (x <= s3) y = ls_pow(x, s4) / ls_pow(s3, s4 - 1);
+  else y = 1 - ls_pow(1 - x, s4) / ls_pow(1 - s3, s4 - 1);
+  *imp = s0 + y * (s1 - s0);
+}
+
+LS_DEV void impedance_KB(const float* solref, const float* solimp, float pos, float margin, float timestep, float* imp,
+                         float* K, float* B) {
+  float sr0 = solref[0], sr1 = solref[1];
+  if (sr0 > 0) sr0 = fmaxf(sr0, 2 * timestep);
+  get_impedance(solimp, pos, margin, imp);
+  float dmax = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp[1]));
+  if (sr0 > 0) { *K = 1 / fmaxf(LS_MINVAL, dmax * dmax * sr0 * sr0 * sr1 * sr1); *B = 2 / fmaxf(LS_MINVAL, dmax * sr0); }
+  else { *K = -sr0 / fmaxf(LS_MINVAL, dmax * dmax); *B = -sr1 / fmaxf(LS_MINVAL, dmax); }
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -321,52 +360,103 @@ LS_FN void com_pos(const int ms, EnvS<C>& e) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// dense Cholesky in shared memory (lower triangle, row stride NVP), wavefront over columns
+// dense SPD solves, n <= NV (matrices are identity-padded to NV).  Storage: lower triangle in shared memory,
+// row stride NVP.  CUDA build: "row owner" algorithm - lane i keeps row i in registers, columns are exchanged
+// with warp shuffles (no shared-memory round trips, no __syncwarp inside); the factor is written back with
+// 1/L_ii on the diagonal.  Emulation build: plain serial Cholesky (L_ii on the diagonal).
 // ----------------------------------------------------------------------------------------------------------
-template <int NVP>
-LS_FN void chol_factor(float (*A)[NVP], int n) {
+#ifdef LS_EMULATE
+template <int NV, int NVP>
+LS_FN void chol_factor(float (*A)[NVP]) {
+  const int n = NV;
   for (int j = 0; j < n; j++) {
-    // column j: all rows i >= j in parallel; L[i][j] = (A[i][j] - sum_k<j L[i][k] L[j][k]) / L[j][j]
-    PAR_FOR(ii, n - j) {
-      int i = j + ii;
+    float d = A[j][j];
+    for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
+    if (d < 1e-12f) d = 1e-12f;
+    d = sqrtf(d);
+    A[j][j] = d;
+    for (int i = j + 1; i < n; i++) {
       float v = A[i][j];
       for (int k = 0; k < j; k++) v -= A[i][k] * A[j][k];
-      A[i][j] = v;   // unscaled for now
+      A[i][j] = v / d;
     }
-    SYNC();
-    float d = A[j][j];
-    if (d < 1e-12f) d = 1e-12f;
-    float inv = rsqrtf(d);
-    PAR_FOR(ii, n - j) {
-      int i = j + ii;
-      A[i][j] = (ii == 0) ? d * inv : A[i][j] * inv;
-    }
-    SYNC();
   }
 }
-// solve L L^T x = b in place; x in shared memory
-template <int NVP>
-LS_FN void chol_solve(float (*L)[NVP], int n, float* x) {
-  // forward: column oriented
-  for (int k = 0; k < n; k++) {
-    float xk = x[k] / L[k][k];
-    SYNC();
-    PAR_FOR(ii, n - k) {
-      int i = k + ii;
-      if (ii == 0) x[k] = xk; else x[i] -= L[i][k] * xk;
-    }
-    SYNC();
+template <int NV, int NVP>
+LS_FN void chol_solve(float (*L)[NVP], float* x) {
+  const int n = NV;
+  for (int i = 0; i < n; i++) {
+    float v = x[i];
+    for (int k = 0; k < i; k++) v -= L[i][k] * x[k];
+    x[i] = v / L[i][i];
   }
-  // backward: x_i = (y_i - sum_{k>i} L[k][i] x_k) / L[i][i]  -> column oriented on L^T
-  for (int k = n - 1; k >= 0; k--) {
-    float xk = x[k] / L[k][k];
-    SYNC();
-    PAR_FOR(i, k + 1) {
-      if (i == k) x[k] = xk; else x[i] -= L[k][i] * xk;
-    }
-    SYNC();
+  for (int i = n - 1; i >= 0; i--) {
+    float v = x[i];
+    for (int k = i + 1; k < n; k++) v -= L[k][i] * x[k];
+    x[i] = v / L[i][i];
   }
 }
+#else
+// in-register right-looking Cholesky of the rows held by the lanes: a[j] = A[lane][j] (j <= lane meaningful).
+// On return a[j] = L[lane][j] for j < lane and `inv` = 1 / L[lane][lane].
+template <int NV>
+LS_DEV void chol_rows(float (&a)[NV], float& inv, const int lane) {
+  inv = 1.0f;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    float djj = fmaxf(__shfl_sync(0xffffffffu, a[j], j), 1e-12f);
+    float r = rsqrtf(djj);
+    if (lane == j) inv = r;
+    a[j] *= r;
+#pragma unroll
+    for (int k = j + 1; k < NV; k++) {
+      float lkj = __shfl_sync(0xffffffffu, a[j], k);
+      a[k] = fmaf(-a[j], lkj, a[k]);
+    }
+  }
+}
+template <int NV, int NVP>
+LS_DEV void store_factor(float (*A)[NVP], const float (&a)[NV], float inv, const int lane) {
+  if (lane < NV) {
+#pragma unroll
+    for (int j = 0; j < NV; j++) A[lane][j] = (j == lane) ? inv : a[j];
+  }
+  __syncwarp();
+}
+template <int NV, int NVP>
+LS_FN void chol_factor(float (*A)[NVP]) {
+  const int lane = LS_LANE, li = lane < NV ? lane : NV - 1;
+  float a[NV], inv;
+#pragma unroll
+  for (int j = 0; j < NV; j++) a[j] = A[li][j];
+  __syncwarp();
+  chol_rows<NV>(a, inv, lane);
+  store_factor<NV, NVP>(A, a, inv, lane);
+}
+// solve L L^T x = b in place (x: shared memory vector, length >= NV, padded entries must be finite)
+template <int NV, int NVP>
+LS_FN void chol_solve(float (*L)[NVP], float* xs) {
+  const int lane = LS_LANE, li = lane < NV ? lane : NV - 1;
+  float x = lane < NV ? xs[lane] : 0.0f;
+  const float inv = L[li][li];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    float t = x * inv;
+    float yj = __shfl_sync(0xffffffffu, t, j);
+    float lij = L[li][j];
+    x = (lane == j) ? t : ((lane > j) ? fmaf(-lij, yj, x) : x);
+  }
+#pragma unroll
+  for (int j = NV - 1; j >= 0; j--) {
+    float t = x * inv;
+    float xj = __shfl_sync(0xffffffffu, t, j);
+    float lji = L[j][li];
+    x = (lane == j) ? t : ((lane < j) ? fmaf(-lji, xj, x) : x);
+  }
+  if (lane < NV) xs[lane] = x;
+  __syncwarp();
+}
+#endif
 
 // ----------------------------------------------------------------------------------------------------------
 // mj_crb + factor: composite inertias up the tree, joint-space inertia M, L = chol(M)
@@ -388,7 +478,10 @@ LS_FN void crb_factor(const int ms, EnvS<C>& e) {
     }
     SYNC();
   }
-  PAR_FOR(idx, m.nv * EnvS<C>::NVP) (&e.M[0][0])[idx] = 0;
+  PAR_FOR(idx, EnvS<C>::NV * EnvS<C>::NVP) {
+    int i = idx / EnvS<C>::NVP, j = idx - i * EnvS<C>::NVP;
+    (&e.M[0][0])[idx] = (i == j && i >= m.nv) ? 1.0f : 0.0f;
+  }
   SYNC();
   PAR_FOR(i, m.nv) {
     float buf[6];
@@ -402,9 +495,9 @@ LS_FN void crb_factor(const int ms, EnvS<C>& e) {
     }
   }
   SYNC();
-  PAR_FOR(idx, m.nv * EnvS<C>::NVP) (&e.L[0][0])[idx] = (&e.M[0][0])[idx];
+  PAR_FOR(idx, EnvS<C>::NV * EnvS<C>::NVP) (&e.H[0][0])[idx] = (&e.M[0][0])[idx];
   SYNC();
-  chol_factor<EnvS<C>::NVP>(e.L, m.nv);
+  chol_factor<EnvS<C>::NV, EnvS<C>::NVP>(e.H);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -649,12 +742,12 @@ LS_FN void pair_narrow(const int ms, EnvS<C>& e, int p) {
     float incl = margin - gap;
     if (raw[k].dist >= incl) continue;   // not active: never enters the constraint set
     int ci = base++;
-    float fri[3];
+    float fri[3], solref[2], solimp[5];
     if (p1 != p2) {
       int g = p1 > p2 ? g1 : g2;
       e.con_dim[ci] = m.geom_condim[g];
-      for (int c = 0; c < 2; c++) e.con_solref[ci][c] = m.geom_solref[2 * g + c];
-      for (int c = 0; c < 5; c++) e.con_solimp[ci][c] = m.geom_solimp[5 * g + c];
+      for (int c = 0; c < 2; c++) solref[c] = m.geom_solref[2 * g + c];
+      for (int c = 0; c < 5; c++) solimp[c] = m.geom_solimp[5 * g + c];
       for (int c = 0; c < 3; c++) fri[c] = m.geom_friction[3 * g + c];
     } else {
       e.con_dim[ci] = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
@@ -664,11 +757,12 @@ LS_FN void pair_narrow(const int ms, EnvS<C>& e, int p) {
       else if (s1 < LS_MINVAL) mix = 0.0f;
       else mix = 1.0f;
       const float *r1 = m.geom_solref + 2 * g1, *r2 = m.geom_solref + 2 * g2;
-      if (r1[0] > 0 && r2[0] > 0) for (int c = 0; c < 2; c++) e.con_solref[ci][c] = mix * r1[c] + (1 - mix) * r2[c];
-      else for (int c = 0; c < 2; c++) e.con_solref[ci][c] = fminf(r1[c], r2[c]);
-      for (int c = 0; c < 5; c++) e.con_solimp[ci][c] = mix * m.geom_solimp[5 * g1 + c] + (1 - mix) * m.geom_solimp[5 * g2 + c];
+      if (r1[0] > 0 && r2[0] > 0) for (int c = 0; c < 2; c++) solref[c] = mix * r1[c] + (1 - mix) * r2[c];
+      else for (int c = 0; c < 2; c++) solref[c] = fminf(r1[c], r2[c]);
+      for (int c = 0; c < 5; c++) solimp[c] = mix * m.geom_solimp[5 * g1 + c] + (1 - mix) * m.geom_solimp[5 * g2 + c];
       for (int c = 0; c < 3; c++) fri[c] = fmaxf(m.geom_friction[3 * g1 + c], m.geom_friction[3 * g2 + c]);
     }
+    impedance_KB(solref, solimp, raw[k].dist, incl, m.timestep, &e.con_imp[ci], &e.con_K[ci], &e.con_B[ci]);
     e.con_fri[ci][0] = fri[0]; e.con_fri[ci][1] = fri[0]; e.con_fri[ci][2] = fri[1]; e.con_fri[ci][3] = fri[2];
     e.con_fri[ci][4] = fri[2];
     e.con_incl[ci] = incl;
@@ -719,23 +813,6 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
 // ----------------------------------------------------------------------------------------------------------
 // constraint assembly (mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint)
 // ----------------------------------------------------------------------------------------------------------
-LS_DEV float ls_pow(float x, float p) {
-  // x in (0,1); p >= 1. power 2 (MuJoCo's default) is exact, other powers go through exp2/log2
-  return p == 2.0f ? x * x : (p == 1.0f ? x : exp2f(p * log2f(x)));
-}
-LS_DEV void get_impedance(const float* solimp_in, float pos, float margin, float* imp) {
-  float s0 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[0])), s1 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[1]));
-  float s2 = fmaxf(0.0f, solimp_in[2]), s3 = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp_in[3])), s4 = fmaxf(1.0f, solimp_in[4]);
-  if (s0 == s1 || s2 <= LS_MINVAL) { *imp = 0.5f * (s0 + s1); return; }
-  float x = fabsf((pos - margin) / s2);
-  if (x >= 1 || x <= 0) { *imp = (x >= 1 ? s1 : s0); return; }
-  float y;
-  if (s4 == 1) y = x;
-  else if (x <= s3) y = ls_pow(x, s4) / ls_pow(s3, s4 - 1);
-  else y = 1 - ls_pow(1 - x, s4) / ls_pow(1 - s3, s4 - 1);
-  *imp = s0 + y * (s1 - s0);
-}
-
 template <class C>
 LS_FN void make_constraint(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
@@ -744,10 +821,7 @@ LS_FN void make_constraint(const int ms, EnvS<C>& e) {
   // ---- unit rows: frictionloss (static row slots) ----
   PAR_FOR(d, nv) {
     int r = m.dof_frow[d];
-    if (r >= 0) {
-      e.r_type[r] = ROW_FRICTION; e.r_id[r] = d; e.r_sign[r] = 1.0f;
-      e.r_pos[r] = 0; e.r_margin[r] = 0; e.r_fl[r] = m.dof_frictionloss[d]; e.r_diag[r] = m.dof_invweight0[d];
-    }
+    if (r >= 0) e.r_ti[r] = ROW_PACK(ROW_FRICTION, d, 0);
     e.d_lrow[d][0] = -1; e.d_lrow[d][1] = -1;
   }
   SYNC();
@@ -760,8 +834,7 @@ LS_FN void make_constraint(const int ms, EnvS<C>& e) {
       float dist = side == 0 ? e.qpos[d] - m.jnt_range[2 * d] : m.jnt_range[2 * d + 1] - e.qpos[d];
       if (dist < m.jnt_margin[d]) {
         int r = nunit++;
-        e.r_type[r] = ROW_LIMIT; e.r_id[r] = d; e.r_sign[r] = side == 0 ? 1.0f : -1.0f;
-        e.r_pos[r] = dist; e.r_margin[r] = m.jnt_margin[d]; e.r_fl[r] = 0; e.r_diag[r] = m.dof_invweight0[d];
+        e.r_ti[r] = ROW_PACK(ROW_LIMIT, d, side);
         e.d_lrow[d][side] = r;
       }
     }
@@ -769,20 +842,18 @@ LS_FN void make_constraint(const int ms, EnvS<C>& e) {
 #else
   {
     const int lane = LS_LANE;
-    for (int base = 0; base < 2 * nv; base += 32) {
+    NOUNROLL for (int base = 0; base < 2 * nv; base += 32) {
       int idx = base + lane;
       int d = idx >> 1, side = idx & 1;
       bool act = false;
-      float dist = 0;
       if (idx < 2 * nv && m.jnt_limited[d]) {
-        dist = side == 0 ? e.qpos[d] - m.jnt_range[2 * d] : m.jnt_range[2 * d + 1] - e.qpos[d];
+        float dist = side == 0 ? e.qpos[d] - m.jnt_range[2 * d] : m.jnt_range[2 * d + 1] - e.qpos[d];
         act = dist < m.jnt_margin[d];
       }
       unsigned mask = __ballot_sync(0xffffffffu, act);
       if (act) {
         int r = nunit + __popc(mask & ((1u << lane) - 1));
-        e.r_type[r] = ROW_LIMIT; e.r_id[r] = d; e.r_sign[r] = side == 0 ? 1.0f : -1.0f;
-        e.r_pos[r] = dist; e.r_margin[r] = m.jnt_margin[d]; e.r_fl[r] = 0; e.r_diag[r] = m.dof_invweight0[d];
+        e.r_ti[r] = ROW_PACK(ROW_LIMIT, d, side);
         e.d_lrow[d][side] = r;
       }
       nunit += __popc(mask);
@@ -792,7 +863,7 @@ LS_FN void make_constraint(const int ms, EnvS<C>& e) {
   // ---- contact rows: row offsets (serial, tiny) ----
   LANE0 {
     int nrow = 0, ncon = e.ncon;
-    for (int ci = 0; ci < ncon; ci++) {
+    NOUNROLL for (int ci = 0; ci < ncon; ci++) {
       int dim = e.con_dim[ci];
       int nr = (dim == 1) ? 1 : (C::CONE == 1 ? dim : 2 * (dim - 1));
       if (nrow + nr > E::MAXROW) { ncon = ci; break; }
@@ -804,12 +875,14 @@ LS_FN void make_constraint(const int ms, EnvS<C>& e) {
   SYNC();
   const int ncon = e.ncon;
   // ---- contact Jacobian rows: one work item per (contact, dof) ----
-  PAR_FOR(item, ncon * nv) {
-    int ci = item / nv, d = item - ci * nv;
+  PAR_FOR(item, ncon * E::JS) {
+    int ci = item / E::JS, d = item - ci * E::JS;      // d >= nv: zero padding columns
     int b1 = m.geom_bodyid[e.con_g1[ci]], b2 = m.geom_bodyid[e.con_g2[ci]];
     float s = 0;
-    if ((m.body_dofmask[b2] >> d) & 1) s += 1.0f;
-    if ((m.body_dofmask[b1] >> d) & 1) s -= 1.0f;
+    if (d < nv) {
+      if ((m.body_dofmask[b2] >> d) & 1) s += 1.0f;
+      if ((m.body_dofmask[b1] >> d) & 1) s -= 1.0f;
+    }
     int dim = e.con_dim[ci], row0 = e.con_row[ci];
     int nr = (dim == 1) ? 1 : (C::CONE == 1 ? dim : 2 * (dim - 1));
     if (s == 0) { NOUNROLL for (int r = 0; r < nr; r++) e.J[row0 + r][d] = 0; continue; }
@@ -823,81 +896,82 @@ LS_FN void make_constraint(const int ms, EnvS<C>& e) {
     float jd[6];
     for (int r = 0; r < 3; r++) { jd[r] = dot3(f + 3 * r, jp); jd[3 + r] = dot3(f + 3 * r, jr); }
     if (dim == 1) e.J[row0][d] = jd[0];
-    else if (C::CONE == 1) { for (int r = 0; r < dim; r++) e.J[row0 + r][d] = jd[r]; }
-    else {
-      for (int r = 1; r < dim; r++) {
-        float fr = e.con_fri[ci][r - 1];
-        e.J[row0 + 2 * (r - 1)][d] = jd[0] + fr * jd[r];
-        e.J[row0 + 2 * (r - 1) + 1][d] = jd[0] - fr * jd[r];
+    else if (C::CONE == 1) {
+#pragma unroll
+      for (int r = 0; r < 6; r++) if (r < dim) e.J[row0 + r][d] = jd[r];
+    } else {
+#pragma unroll
+      for (int r = 1; r < 6; r++) {
+        if (r < dim) {
+          float fr = e.con_fri[ci][r - 1];
+          e.J[row0 + 2 * (r - 1)][d] = jd[0] + fr * jd[r];
+          e.J[row0 + 2 * (r - 1) + 1][d] = jd[0] - fr * jd[r];
+        }
       }
     }
   }
-  // ---- contact row metadata ----
+  // ---- contact row headers ----
   PAR_FOR(ci, ncon) {
-    int b1 = m.geom_bodyid[e.con_g1[ci]], b2 = m.geom_bodyid[e.con_g2[ci]];
-    float tran = m.geom_invweight0[2 * e.con_g1[ci]] + m.geom_invweight0[2 * e.con_g2[ci]];
-    float rot = m.geom_invweight0[2 * e.con_g1[ci] + 1] + m.geom_invweight0[2 * e.con_g2[ci] + 1];
     int dim = e.con_dim[ci], row0 = nunit + e.con_row[ci];
     int nr = (dim == 1) ? 1 : (C::CONE == 1 ? dim : 2 * (dim - 1));
     int tp = (dim == 1) ? ROW_CON_FRICTIONLESS : (C::CONE == 1 ? ROW_CON_ELLIPTIC : ROW_CON_PYRAMIDAL);
-    NOUNROLL for (int r = 0; r < nr; r++) {
-      int rr = row0 + r;
-      e.r_type[rr] = tp; e.r_id[rr] = ci; e.r_sign[rr] = (float)r;   // r_sign = row-within-contact for contact rows
-      e.r_pos[rr] = e.con_dist[ci]; e.r_margin[rr] = e.con_incl[ci]; e.r_fl[rr] = 0;
-      if (tp == ROW_CON_PYRAMIDAL) e.r_diag[rr] = tran + e.con_fri[ci][0] * e.con_fri[ci][0] * tran;
-      else e.r_diag[rr] = r < 3 ? tran : rot;
-    }
+    NOUNROLL for (int r = 0; r < nr; r++) e.r_ti[row0 + r] = ROW_PACK(tp, ci, r);
   }
   SYNC();
-  // ---- impedance, R, reference acceleration ----
+  // ---- impedance -> D = 1/R, reference acceleration (mj_makeImpedance + mj_referenceConstraint) ----
   const int nefc = e.nefc;
   PAR_FOR(r, nefc) {
-    int tp = e.r_type[r], id = e.r_id[r];
-    const float *solref, *solimp;
-    if (tp == ROW_FRICTION) { solref = m.dof_solref + 2 * id; solimp = m.dof_solimp + 5 * id; }
-    else if (tp == ROW_LIMIT) { solref = m.jnt_solref + 2 * id; solimp = m.jnt_solimp + 5 * id; }
-    else { solref = e.con_solref[id]; solimp = e.con_solimp[id]; }
-    float sr0 = solref[0], sr1 = solref[1];
-    if (sr0 > 0) sr0 = fmaxf(sr0, 2 * m.timestep);
-    float imp;
-    get_impedance(solimp, e.r_pos[r], e.r_margin[r], &imp);
-    e.r_R[r] = fmaxf(LS_MINVAL, (1 - imp) * e.r_diag[r] / imp);
-    float dmax = fminf(LS_MAXIMP, fmaxf(LS_MINIMP, solimp[1]));
-    float K, B;
-    if (sr0 > 0) { K = 1 / fmaxf(LS_MINVAL, dmax * dmax * sr0 * sr0 * sr1 * sr1); B = 2 / fmaxf(LS_MINVAL, dmax * sr0); }
-    else { K = -sr0 / fmaxf(LS_MINVAL, dmax * dmax); B = -sr1 / fmaxf(LS_MINVAL, dmax); }
-    bool friction_row = (tp == ROW_FRICTION) || (tp == ROW_CON_ELLIPTIC && e.r_sign[r] > 0.5f);
-    if (friction_row) K = 0;
-    float vel;
-    if (r < nunit) vel = e.r_sign[r] * e.qvel[id];
-    else {
+    const int ti = e.r_ti[r];
+    const int tp = ROW_TYPE(ti), id = ROW_ID(ti), k = ROW_K(ti);
+    float pos, margin, diag, vel, imp, K, B;
+    if (tp == ROW_FRICTION) {
+      pos = 0; margin = 0; diag = m.dof_invweight0[id]; vel = e.qvel[id];
+      impedance_KB(m.dof_solref + 2 * id, m.dof_solimp + 5 * id, pos, margin, m.timestep, &imp, &K, &B);
+    } else if (tp == ROW_LIMIT) {
+      pos = k == 0 ? e.qpos[id] - m.jnt_range[2 * id] : m.jnt_range[2 * id + 1] - e.qpos[id];
+      margin = m.jnt_margin[id]; diag = m.dof_invweight0[id]; vel = k == 0 ? e.qvel[id] : -e.qvel[id];
+      impedance_KB(m.jnt_solref + 2 * id, m.jnt_solimp + 5 * id, pos, margin, m.timestep, &imp, &K, &B);
+    } else {
+      pos = e.con_dist[id]; margin = e.con_incl[id];
+      imp = e.con_imp[id]; K = e.con_K[id]; B = e.con_B[id];
+      const int g1 = e.con_g1[id], g2 = e.con_g2[id];
+      float tran = m.geom_invweight0[2 * g1] + m.geom_invweight0[2 * g2];
+      if (tp == ROW_CON_PYRAMIDAL) diag = tran + e.con_fri[id][0] * e.con_fri[id][0] * tran;
+      else diag = k < 3 ? tran : m.geom_invweight0[2 * g1 + 1] + m.geom_invweight0[2 * g2 + 1];
       const float* Jr = e.J[r - nunit];
       vel = 0;
-      for (int d = 0; d < nv; d++) vel += Jr[d] * e.qvel[d];
+#pragma unroll 4
+      for (int d = 0; d < nv; d++) vel = fmaf(Jr[d], e.qvel[d], vel);
     }
-    e.r_aref[r] = -B * vel - K * imp * (e.r_pos[r] - e.r_margin[r]);
+    float R = fmaxf(LS_MINVAL, (1 - imp) * diag / imp);
+    if (tp == ROW_FRICTION || (tp == ROW_CON_ELLIPTIC && k > 0)) K = 0;
+    e.r_aref[r] = -B * vel - K * imp * (pos - margin);
+    e.r_D[r] = 1.0f / R;
   }
   SYNC();
+  // ---- frictional contacts: regularised cone mu and the D of the friction dimensions ----
   PAR_FOR(ci, ncon) {
     int dim = e.con_dim[ci];
     if (dim == 1) continue;
     int i = nunit + e.con_row[ci];
+    float f0 = e.con_fri[ci][0];
     if (C::CONE == 0) {
-      float mu = e.con_fri[ci][0] * rsqrtf(fmaxf(LS_MINVAL, m.impratio));
+      float mu = f0 * rsqrtf(fmaxf(LS_MINVAL, m.impratio));
       e.con_mu[ci] = mu;
-      float Rpy = 2 * mu * mu * e.r_R[i];
-      NOUNROLL for (int j = 0; j < 2 * (dim - 1); j++) e.r_R[i + j] = Rpy;
+      float Dpy = e.r_D[i] / (2 * mu * mu);
+      NOUNROLL for (int j = 0; j < 2 * (dim - 1); j++) e.r_D[i + j] = Dpy;
     } else {
-      float R0 = e.r_R[i];
-      float R1 = R0 / fmaxf(LS_MINVAL, m.impratio);
-      e.r_R[i + 1] = R1;
-      e.con_mu[ci] = e.con_fri[ci][0] * sqrtf(R1 / R0);
-      NOUNROLL for (int j = 1; j < dim - 1; j++)
-        e.r_R[i + j + 1] = R1 * e.con_fri[ci][0] * e.con_fri[ci][0] / (e.con_fri[ci][j] * e.con_fri[ci][j]);
+      float D0 = e.r_D[i];
+      float ir = fmaxf(LS_MINVAL, m.impratio);
+      float D1 = D0 * ir;                          // R1 = R0 / impratio
+      e.r_D[i + 1] = D1;
+      e.con_mu[ci] = f0 * rsqrtf(ir);              // mu = friction[0] * sqrt(R1 / R0)
+      NOUNROLL for (int j = 1; j < dim - 1; j++) {
+        float fj = e.con_fri[ci][j];
+        e.r_D[i + j + 1] = D1 * fj * fj / (f0 * f0);   // R[j+1] = R1 * f0^2 / fj^2
+      }
     }
   }
-  SYNC();
-  PAR_FOR(r, nefc) e.r_D[r] = 1.0f / e.r_R[r];
   SYNC();
 }
 
@@ -974,9 +1048,9 @@ LS_FN void smooth_forces(const int ms, EnvS<C>& e) {
     e.qfrc_smooth[d] += m.actuator_gear[i] * f;
   }
   SYNC();
-  PAR_FOR(j, nv) e.qacc_smooth[j] = e.qfrc_smooth[j];
+  PAR_FOR(j, EnvS<C>::NV) e.qacc_smooth[j] = j < nv ? e.qfrc_smooth[j] : 0.0f;
   SYNC();
-  chol_solve<EnvS<C>::NVP>(e.L, nv, e.qacc_smooth);
+  chol_solve<EnvS<C>::NV, EnvS<C>::NVP>(e.H, e.qacc_smooth);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -997,7 +1071,7 @@ LS_FN void mulJ(const int ms, const EnvS<C>& e, float* res, const float* v) {
   const DevModel& m = c_models[ms];
   const int nunit = e.nunit, nefc = e.nefc, nv = m.nv;
   PAR_FOR(r, nefc) {
-    if (r < nunit) res[r] = e.r_sign[r] * v[e.r_id[r]];
+    if (r < nunit) { const int ti = e.r_ti[r]; float vv = v[ROW_ID(ti)]; res[r] = ROW_K(ti) == 1 ? -vv : vv; }
     else {
       const float* Jr = e.J[r - nunit];
       float a = 0;
@@ -1014,16 +1088,17 @@ LS_FN float constraint_update(const int ms, EnvS<C>& e) {
   const int nefc = e.nefc, nunit = e.nunit;
   float cost = 0;
   PAR_FOR(r, nefc) {
-    int tp = e.r_type[r];
+    const int ti = e.r_ti[r];
+    const int tp = ROW_TYPE(ti);
     float jar = e.r_jar[r], D = e.r_D[r];
     if (tp == ROW_FRICTION) {
-      float f = e.r_fl[r], Rf = e.r_R[r] * f;
+      float f = m.dof_frictionloss[ROW_ID(ti)], Rf = f / D;
       if (jar <= -Rf) { e.r_state[r] = ST_LINEARNEG; e.r_force[r] = f; cost += -0.5f * Rf * f - f * jar; }
       else if (jar >= Rf) { e.r_state[r] = ST_LINEARPOS; e.r_force[r] = -f; cost += -0.5f * Rf * f + f * jar; }
       else { e.r_state[r] = ST_QUADRATIC; e.r_force[r] = -D * jar; cost += 0.5f * D * jar * jar; }
     } else if (tp == ROW_CON_ELLIPTIC) {
-      if (e.r_sign[r] > 0.5f) continue;   // handled by the contact's first row
-      int ci = e.r_id[r], dim = e.con_dim[ci];
+      if (ROW_K(ti) != 0) continue;   // handled by the contact's first row
+      int ci = ROW_ID(ti), dim = e.con_dim[ci];
       float mu = e.con_mu[ci];
       float U[6];
       U[0] = jar * mu;
@@ -1080,6 +1155,93 @@ LS_FN float update_constraint(const int ms, EnvS<C>& e, float* gauss_out) {
   return cost + g;
 }
 
+#ifndef LS_EMULATE
+// CUDA build: lane i accumulates row i of H = M + J^T diag(w) J (+ cone blocks) in registers, factors it in place
+// (chol_rows) and publishes L (with 1/L_ii on the diagonal) to e.H for the triangular solves.
+template <class C>
+LS_FN void make_hessian(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
+  typedef EnvS<C> E;
+  constexpr int NV = E::NV, JS = E::JS;
+  const int nv = m.nv, nrow = e.nrow, nunit = e.nunit;
+  const int lane = LS_LANE, li = lane < NV ? lane : NV - 1;
+  PAR_FOR(r, e.nefc) e.r_Jv[r] = (e.r_state[r] == ST_QUADRATIC) ? e.r_D[r] : 0.0f;
+  float h[JS];
+#pragma unroll
+  for (int j = 0; j < NV; j++) h[j] = e.M[li][j];
+#pragma unroll
+  for (int j = NV; j < JS; j++) h[j] = 0.0f;
+  __syncwarp();
+  const float* w = e.r_Jv + nunit;
+  NOUNROLL for (int r = 0; r < nrow; r++) {
+    const float wr = w[r];
+    if (wr == 0.0f) continue;                       // warp-uniform: satisfied / linear / cone rows
+    const float t = wr * e.J[r][li];
+    const float4* row = reinterpret_cast<const float4*>(e.J[r]);
+#pragma unroll
+    for (int q = 0; q < JS / 4; q++) {
+      float4 v = row[q];
+      h[4 * q] = fmaf(t, v.x, h[4 * q]); h[4 * q + 1] = fmaf(t, v.y, h[4 * q + 1]);
+      h[4 * q + 2] = fmaf(t, v.z, h[4 * q + 2]); h[4 * q + 3] = fmaf(t, v.w, h[4 * q + 3]);
+    }
+  }
+  // unit rows (frictionloss / joint limits) only touch the diagonal
+  if (lane < nv) {
+    float dsum = 0;
+    int fr = m.dof_frow[lane];
+    if (fr >= 0) dsum += e.r_Jv[fr];
+    int l0 = e.d_lrow[lane][0], l1 = e.d_lrow[lane][1];
+    if (l0 >= 0) dsum += e.r_Jv[l0];
+    if (l1 >= 0) dsum += e.r_Jv[l1];
+#pragma unroll
+    for (int j = 0; j < NV; j++) if (j == lane) h[j] += dsum;
+  }
+  if (C::CONE == 1) {
+    NOUNROLL for (int ci = 0; ci < e.ncon; ci++) {
+      const int r0 = nunit + e.con_row[ci];
+      if (e.r_state[r0] != ST_CONE) continue;
+      const int dim = e.con_dim[ci], jr0 = r0 - nunit;
+      const float mu = e.con_mu[ci];
+      float TT = 0;
+      NOUNROLL for (int j = 1; j < dim; j++) { float u = e.r_jar[r0 + j] * e.con_fri[ci][j - 1]; TT += u * u; }
+      if (lane < dim) {
+        float sc = lane == 0 ? mu : e.con_fri[ci][lane - 1];
+        e.coneS[lane] = sc; e.coneU[lane] = e.r_jar[r0 + lane] * sc;
+      }
+      __syncwarp();
+      const float N = e.r_jar[r0] * mu, T = sqrtf(TT);
+      const float Dm = e.r_D[r0] / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
+      const float invT = 1.0f / T;
+      const float c1 = mu * N * invT * invT * invT, c2 = mu * mu - mu * N * invT;
+      // v_b = sum_a J[a][lane] * Hc[a][b]  (Hc symmetric, in jar space), then H[lane][:] += v_b * J[b][:]
+      NOUNROLL for (int b = 0; b < dim; b++) {
+        float vb = 0;
+        NOUNROLL for (int a = 0; a < dim; a++) {
+          float hc;
+          if (a == 0 && b == 0) hc = 1;
+          else if (a == 0) hc = -mu * e.coneU[b] * invT;
+          else if (b == 0) hc = -mu * e.coneU[a] * invT;
+          else hc = c1 * e.coneU[a] * e.coneU[b] + (a == b ? c2 : 0.0f);
+          vb = fmaf(Dm * hc * e.coneS[a] * e.coneS[b], e.J[jr0 + a][li], vb);
+        }
+        const float4* row = reinterpret_cast<const float4*>(e.J[jr0 + b]);
+#pragma unroll
+        for (int q = 0; q < JS / 4; q++) {
+          float4 v = row[q];
+          h[4 * q] = fmaf(vb, v.x, h[4 * q]); h[4 * q + 1] = fmaf(vb, v.y, h[4 * q + 1]);
+          h[4 * q + 2] = fmaf(vb, v.z, h[4 * q + 2]); h[4 * q + 3] = fmaf(vb, v.w, h[4 * q + 3]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  float a[NV], inv;
+#pragma unroll
+  for (int j = 0; j < NV; j++) a[j] = h[j];
+  chol_rows<NV>(a, inv, lane);
+  store_factor<NV, E::NVP>(e.H, a, inv, lane);
+}
+#else
 template <class C>
 LS_FN void make_hessian(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
@@ -1152,8 +1314,10 @@ LS_FN void make_hessian(const int ms, EnvS<C>& e) {
       SYNC();
     }
   }
-  chol_factor<E::NVP>(e.H, nv);
+  chol_factor<E::NV, E::NVP>(e.H);
 }
+
+#endif
 
 struct LSPoint { float alpha, cost, d1, d2; };
 
@@ -1163,17 +1327,18 @@ LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alp
   const int nefc = e.nefc;
   float c = 0, d1 = 0, d2 = 0;
   PAR_FOR(r, nefc) {
-    int tp = e.r_type[r];
+    const int ti = e.r_ti[r];
+    const int tp = ROW_TYPE(ti);
     float ja = e.r_jar[r], jv = e.r_Jv[r], D = e.r_D[r];
     float x = ja + alpha * jv;
     if (tp == ROW_FRICTION) {
-      float f = e.r_fl[r], Rf = e.r_R[r] * f;
+      float f = m.dof_frictionloss[ROW_ID(ti)], Rf = f / D;
       if (x <= -Rf) { c += f * (-0.5f * Rf - x); d1 += -f * jv; }
       else if (x >= Rf) { c += f * (-0.5f * Rf + x); d1 += f * jv; }
       else { c += 0.5f * D * x * x; d1 += D * x * jv; d2 += D * jv * jv; }
     } else if (tp == ROW_CON_ELLIPTIC) {
-      if (e.r_sign[r] > 0.5f) continue;
-      int ci = e.r_id[r], dim = e.con_dim[ci];
+      if (ROW_K(ti) != 0) continue;
+      int ci = ROW_ID(ti), dim = e.con_dim[ci];
       float mu = e.con_mu[ci];
       float U0 = ja * mu, V0 = jv * mu, UU = 0, UV = 0, VV = 0;
       float qc = 0.5f * D * x * x, q1 = D * x * jv, q2 = D * jv * jv;   // quadratic (bottom zone) pieces
@@ -1269,12 +1434,12 @@ LS_FN float line_search(const int ms, EnvS<C>& e, const SolverOpts so, float gau
 template <class C>
 LS_FN void update_gradient(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
-  PAR_FOR(i, m.nv) {
-    float g = e.Ma[i] - e.qfrc_smooth[i] - e.qfrc_constraint[i];
+  PAR_FOR(i, EnvS<C>::NV) {
+    float g = i < m.nv ? e.Ma[i] - e.qfrc_smooth[i] - e.qfrc_constraint[i] : 0.0f;
     e.grad[i] = g; e.Mgrad[i] = g;
   }
   SYNC();
-  chol_solve<EnvS<C>::NVP>(e.H, m.nv, e.Mgrad);
+  chol_solve<EnvS<C>::NV, EnvS<C>::NVP>(e.H, e.Mgrad);
 }
 
 template <class C>
@@ -1357,9 +1522,9 @@ LS_FN void forward(const int ms, EnvS<C>& e, const SolverOpts so) {
   kinematics(ms, e);
   com_pos(ms, e);
   crb_factor(ms, e);
+  smooth_forces(ms, e);        // last user of the smooth-dynamics scratch that the constraint rows overlay
   collision(ms, e);
   make_constraint(ms, e);
-  smooth_forces(ms, e);
   fwd_constraint(ms, e, so);
 }
 
@@ -1371,12 +1536,15 @@ LS_FN void euler_step(const int ms, EnvS<C>& e) {
   const float h = m.timestep;
   if (m.has_damping) {
     // (M + h*diag(damping)) qacc = qfrc_smooth + qfrc_constraint   (mj_Euler, implicit in joint damping)
-    PAR_FOR(idx, nv * E::NVP) (&e.H[0][0])[idx] = (&e.M[0][0])[idx];
+    PAR_FOR(idx, E::NV * E::NVP) (&e.H[0][0])[idx] = (&e.M[0][0])[idx];
     SYNC();
-    PAR_FOR(i, nv) { e.H[i][i] += h * m.dof_damping[i]; e.Mgrad[i] = e.qfrc_smooth[i] + e.qfrc_constraint[i]; }
+    PAR_FOR(i, E::NV) {
+      if (i < nv) { e.H[i][i] += h * m.dof_damping[i]; e.Mgrad[i] = e.qfrc_smooth[i] + e.qfrc_constraint[i]; }
+      else e.Mgrad[i] = 0.0f;
+    }
     SYNC();
-    chol_factor<E::NVP>(e.H, nv);
-    chol_solve<E::NVP>(e.H, nv, e.Mgrad);
+    chol_factor<E::NV, E::NVP>(e.H);
+    chol_solve<E::NV, E::NVP>(e.H, e.Mgrad);
     PAR_FOR(i, nv) { float v = e.qvel[i] + h * e.Mgrad[i]; e.qvel[i] = v; e.qpos[i] += h * v; }
   } else {
     PAR_FOR(i, nv) { float v = e.qvel[i] + h * e.qacc[i]; e.qvel[i] = v; e.qpos[i] += h * v; }
@@ -1417,7 +1585,7 @@ LS_FN void physics_substeps(const int ms, EnvS<C>& e, const SolverOpts so, int n
   const DevModel& m = c_models[ms];
   for (int k = 0; k < nsub; k++) {
     forward(ms, e, so);
-    if (C::RK4 == 1) rk4_step(ms, e, so); else euler_step(ms, e);
+    if constexpr (C::RK4 == 1) rk4_step(ms, e, so); else euler_step(ms, e);
   }
 }
 
