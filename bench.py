@@ -33,6 +33,7 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-flush", action="store_true", help="diagnostic: do not flush L2 between timed steps")
     p.add_argument("--gather", action="store_true", help="all-gather the rollout buffer across ranks every step")
     return p.parse_args()
 
@@ -169,7 +170,8 @@ def main():
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     launches0 = eng.launches
     for k in range(a.steps):
-        flush.fill_(k & 0xff)
+        if not a.no_flush:
+            flush.fill_(k & 0xff)
         starts[k].record()
         one_step(a.warmup + k)
         stops[k].record()

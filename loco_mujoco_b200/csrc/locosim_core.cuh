@@ -360,103 +360,63 @@ LS_FN void com_pos(const int ms, EnvS<C>& e) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// dense SPD solves, n <= NV (matrices are identity-padded to NV).  Storage: lower triangle in shared memory,
-// row stride NVP.  CUDA build: "row owner" algorithm - lane i keeps row i in registers, columns are exchanged
-// with warp shuffles (no shared-memory round trips, no __syncwarp inside); the factor is written back with
-// 1/L_ii on the diagonal.  Emulation build: plain serial Cholesky (L_ii on the diagonal).
+// dense SPD solves on identity-padded NV x NV matrices in shared memory (lower triangle, row stride NVP).
+// The factor stores 1/L_ii on the diagonal.  All loops are ROLLED on purpose: the first ncu captures showed this
+// kernel limited by instruction fetch, so the hot solver loop has to stay inside the SM's instruction cache.
 // ----------------------------------------------------------------------------------------------------------
-#ifdef LS_EMULATE
 template <int NV, int NVP>
-LS_FN void chol_factor(float (*A)[NVP]) {
-  const int n = NV;
-  for (int j = 0; j < n; j++) {
-    float d = A[j][j];
-    for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
-    if (d < 1e-12f) d = 1e-12f;
-    d = sqrtf(d);
-    A[j][j] = d;
-    for (int i = j + 1; i < n; i++) {
-      float v = A[i][j];
-      for (int k = 0; k < j; k++) v -= A[i][k] * A[j][k];
-      A[i][j] = v / d;
+LS_FN void chol_factor(const int ms, float (*A)[NVP]) {
+  const DevModel& m = c_models[ms];
+  NOUNROLL for (int j = 0; j < NV; j++) {
+    const float inv = rsqrtf(fmaxf(A[j][j], 1e-12f));
+    SYNC();
+    PAR_FOR(ii, NV - j) { A[j + ii][j] = (ii == 0) ? inv : A[j + ii][j] * inv; }
+    SYNC();
+    // trailing update of the lower triangle of rows/cols (j, NV): the first nrem(nrem+1)/2 entries of the
+    // row-major triangular enumeration (m.tri_ij) are exactly the entries (a, b), b <= a < nrem
+    const int nrem = NV - j - 1;
+    PAR_FOR(t, nrem * (nrem + 1) / 2) {
+      const int ab = m.tri_ij[t];
+      const int i = j + 1 + (ab >> 8), k = j + 1 + (ab & 255);
+      A[i][k] = fmaf(-A[i][j], A[k][j], A[i][k]);
     }
+    SYNC();
   }
 }
-template <int NV, int NVP>
-LS_FN void chol_solve(float (*L)[NVP], float* x) {
-  const int n = NV;
-  for (int i = 0; i < n; i++) {
-    float v = x[i];
-    for (int k = 0; k < i; k++) v -= L[i][k] * x[k];
-    x[i] = v / L[i][i];
-  }
-  for (int i = n - 1; i >= 0; i--) {
-    float v = x[i];
-    for (int k = i + 1; k < n; k++) v -= L[k][i] * x[k];
-    x[i] = v / L[i][i];
-  }
-}
-#else
-// in-register right-looking Cholesky of the rows held by the lanes: a[j] = A[lane][j] (j <= lane meaningful).
-// On return a[j] = L[lane][j] for j < lane and `inv` = 1 / L[lane][lane].
-template <int NV>
-LS_DEV void chol_rows(float (&a)[NV], float& inv, const int lane) {
-  inv = 1.0f;
-#pragma unroll
-  for (int j = 0; j < NV; j++) {
-    float djj = fmaxf(__shfl_sync(0xffffffffu, a[j], j), 1e-12f);
-    float r = rsqrtf(djj);
-    if (lane == j) inv = r;
-    a[j] *= r;
-#pragma unroll
-    for (int k = j + 1; k < NV; k++) {
-      float lkj = __shfl_sync(0xffffffffu, a[j], k);
-      a[k] = fmaf(-a[j], lkj, a[k]);
-    }
-  }
-}
-template <int NV, int NVP>
-LS_DEV void store_factor(float (*A)[NVP], const float (&a)[NV], float inv, const int lane) {
-  if (lane < NV) {
-#pragma unroll
-    for (int j = 0; j < NV; j++) A[lane][j] = (j == lane) ? inv : a[j];
-  }
-  __syncwarp();
-}
-template <int NV, int NVP>
-LS_FN void chol_factor(float (*A)[NVP]) {
-  const int lane = LS_LANE, li = lane < NV ? lane : NV - 1;
-  float a[NV], inv;
-#pragma unroll
-  for (int j = 0; j < NV; j++) a[j] = A[li][j];
-  __syncwarp();
-  chol_rows<NV>(a, inv, lane);
-  store_factor<NV, NVP>(A, a, inv, lane);
-}
-// solve L L^T x = b in place (x: shared memory vector, length >= NV, padded entries must be finite)
+// solve L L^T x = b in place (x: shared memory vector of length >= NV, padded entries finite)
 template <int NV, int NVP>
 LS_FN void chol_solve(float (*L)[NVP], float* xs) {
+#ifdef LS_EMULATE
+  for (int i = 0; i < NV; i++) {
+    float v = xs[i];
+    for (int k = 0; k < i; k++) v -= L[i][k] * xs[k];
+    xs[i] = v * L[i][i];
+  }
+  for (int i = NV - 1; i >= 0; i--) {
+    float v = xs[i];
+    for (int k = i + 1; k < NV; k++) v -= L[k][i] * xs[k];
+    xs[i] = v * L[i][i];
+  }
+#else
   const int lane = LS_LANE, li = lane < NV ? lane : NV - 1;
   float x = lane < NV ? xs[lane] : 0.0f;
   const float inv = L[li][li];
-#pragma unroll
-  for (int j = 0; j < NV; j++) {
-    float t = x * inv;
-    float yj = __shfl_sync(0xffffffffu, t, j);
-    float lij = L[li][j];
+  NOUNROLL for (int j = 0; j < NV; j++) {
+    const float t = x * inv;
+    const float yj = __shfl_sync(0xffffffffu, t, j);
+    const float lij = L[li][j];
     x = (lane == j) ? t : ((lane > j) ? fmaf(-lij, yj, x) : x);
   }
-#pragma unroll
-  for (int j = NV - 1; j >= 0; j--) {
-    float t = x * inv;
-    float xj = __shfl_sync(0xffffffffu, t, j);
-    float lji = L[j][li];
+  NOUNROLL for (int j = NV - 1; j >= 0; j--) {
+    const float t = x * inv;
+    const float xj = __shfl_sync(0xffffffffu, t, j);
+    const float lji = L[j][li];
     x = (lane == j) ? t : ((lane < j) ? fmaf(-lji, xj, x) : x);
   }
   if (lane < NV) xs[lane] = x;
   __syncwarp();
-}
 #endif
+}
 
 // ----------------------------------------------------------------------------------------------------------
 // mj_crb + factor: composite inertias up the tree, joint-space inertia M, L = chol(M)
@@ -497,7 +457,7 @@ LS_FN void crb_factor(const int ms, EnvS<C>& e) {
   SYNC();
   PAR_FOR(idx, EnvS<C>::NV * EnvS<C>::NVP) (&e.H[0][0])[idx] = (&e.M[0][0])[idx];
   SYNC();
-  chol_factor<EnvS<C>::NV, EnvS<C>::NVP>(e.H);
+  chol_factor<EnvS<C>::NV, EnvS<C>::NVP>(ms, e.H);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -1235,11 +1195,12 @@ LS_FN void make_hessian(const int ms, EnvS<C>& e) {
       __syncwarp();
     }
   }
-  float a[NV], inv;
+  if (lane < NV) {
 #pragma unroll
-  for (int j = 0; j < NV; j++) a[j] = h[j];
-  chol_rows<NV>(a, inv, lane);
-  store_factor<NV, E::NVP>(e.H, a, inv, lane);
+    for (int j = 0; j < NV; j++) e.H[lane][j] = h[j];
+  }
+  __syncwarp();
+  chol_factor<NV, E::NVP>(ms, e.H);
 }
 #else
 template <class C>
@@ -1314,7 +1275,7 @@ LS_FN void make_hessian(const int ms, EnvS<C>& e) {
       SYNC();
     }
   }
-  chol_factor<E::NV, E::NVP>(e.H);
+  chol_factor<E::NV, E::NVP>(ms, e.H);
 }
 
 #endif
@@ -1543,7 +1504,7 @@ LS_FN void euler_step(const int ms, EnvS<C>& e) {
       else e.Mgrad[i] = 0.0f;
     }
     SYNC();
-    chol_factor<E::NV, E::NVP>(e.H);
+    chol_factor<E::NV, E::NVP>(ms, e.H);
     chol_solve<E::NV, E::NVP>(e.H, e.Mgrad);
     PAR_FOR(i, nv) { float v = e.qvel[i] + h * e.Mgrad[i]; e.qvel[i] = v; e.qpos[i] += h * v; }
   } else {
