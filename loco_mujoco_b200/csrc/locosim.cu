@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -79,15 +80,18 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
 // step kernel: one warp per env, EnvS in dynamic shared memory
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(128) step_kernel(int ms, DevTask t, SolverOpts so, EngineState st,
+__global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts so, EngineState st,
                                                     const float* __restrict__ action, float* __restrict__ obs,
                                                     float* __restrict__ reward, uint8_t* __restrict__ done,
                                                     float* __restrict__ next_obs, int n_envs, int auto_reset,
-                                                    uint64_t seed, int64_t env_off) {
+                                                    uint64_t seed, int64_t env_off, int sync_substeps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (env >= n_envs) return;
+  if (env >= n_envs) {
+    if (sync_substeps) for (int k = 0; k < t.n_substeps; k++) __syncthreads();
+    return;
+  }
   EnvS<C>& e = reinterpret_cast<EnvS<C>*>(smem_raw)[warp];
   const DevModel& m = c_models[ms];
   const int nv = m.nv, nu = m.nu, D = t.obs_dim;
@@ -113,7 +117,12 @@ __global__ void __launch_bounds__(128) step_kernel(int ms, DevTask t, SolverOpts
   } else if (t.reward_type == LS_REWARD_POS) rew = obs_value(t, e, t.ri[0]);
 
   // ---- physics ----
-  physics_substeps(ms, e, so, t.n_substeps);
+  if (sync_substeps) {
+    // keep the warps of a block in the same phase: they then share instruction-cache lines
+    for (int k = 0; k < t.n_substeps; k++) { __syncthreads(); physics_substeps(ms, e, so, 1); }
+  } else {
+    physics_substeps(ms, e, so, t.n_substeps);
+  }
 
   // ---- observation, termination, reward ----
   bool bad = false;
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(128) step_kernel(int ms, DevTask t, SolverOpts
 // handle
 // ----------------------------------------------------------------------------------------------------------
 struct locosim_handle {
-  int device = 0, n_envs = 0, cfg = -1, wpb = 4, smem = 0, slot = -1;
+  int device = 0, n_envs = 0, cfg = -1, wpb = 4, smem = 0, slot = -1, sync_substeps = 0;
   uint64_t seed = 0;
   int64_t env_off = 0;
   HostModel hm;
@@ -200,7 +209,7 @@ static int launch_step(locosim_handle* h, const float* a, float* o, float* r, ui
                        cudaStream_t s) {
   int blocks = (h->n_envs + h->wpb - 1) / h->wpb;
   step_kernel<C><<<blocks, h->wpb * 32, h->smem, s>>>(h->slot, h->dt, h->so, h->st, a, o, r, d, no, h->n_envs, auto_reset,
-                                                      h->seed, h->env_off);
+                                                      h->seed, h->env_off, h->sync_substeps);
   CK(cudaGetLastError());
   return 0;
 }
@@ -211,16 +220,23 @@ static int setup_cfg(locosim_handle* h) {
   CK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
   int sm_total = 0;
   CK(cudaDeviceGetAttribute(&sm_total, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
-  // choose warps/block in {1..4} maximising resident envs per SM (1 KB/block reserved by the driver)
-  int best = 1, best_env = 0;
-  for (int w = 1; w <= 4; w++) {
+  // envs resident per SM for w warps per block (1 KB per block is reserved by the driver)
+  auto envs_per_sm = [&](int w) {
     int sm = w * per_env;
-    if (sm > dev_max) break;
-    int blocks_per_sm = sm_total / (sm + 1024);
-    if (blocks_per_sm > 32) blocks_per_sm = 32;
-    int envs = blocks_per_sm * w;
-    if (envs >= best_env) { best_env = envs; best = w; }
+    if (sm > dev_max) return 0;
+    int b = sm_total / (sm + 1024);
+    return (b > 32 ? 32 : b) * w;
+  };
+  int best = 1, best_env = 0;
+  for (int w = 1; w <= 14; w++) { int ev = envs_per_sm(w); if (ev > best_env) { best_env = ev; best = w; } }
+  // Warps of one block are re-aligned with a block barrier at every sub-step so that they execute the same phase and
+  // share instruction-cache lines (measured +20%): prefer the largest block that still leaves two blocks per SM.
+  h->sync_substeps = 1;
+  for (int w = 14; w >= 1; w--) {
+    if (envs_per_sm(w) == best_env && (sm_total / (w * per_env + 1024)) >= 2) { best = w; break; }
   }
+  if (getenv("LOCOSIM_WPB")) { int w = atoi(getenv("LOCOSIM_WPB")); if (w >= 1 && w <= 14 && w * per_env <= dev_max) best = w; }
+  if (getenv("LOCOSIM_SYNC")) h->sync_substeps = atoi(getenv("LOCOSIM_SYNC"));
   h->wpb = best;
   h->smem = best * per_env;
   CK(cudaFuncSetAttribute(step_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));

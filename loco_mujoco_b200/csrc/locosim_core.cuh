@@ -224,7 +224,7 @@ LS_DEV void get_impedance(const float* solimp_in, float pos, float margin, float
   *imp = s0 + y * (s1 - s0);
 }
 
-LS_DEV void impedance_KB(const float* solref, const float* solimp, float pos, float margin, float timestep, float* imp,
+LS_FN void impedance_KB(const float* solref, const float* solimp, float pos, float margin, float timestep, float* imp,
                          float* K, float* B) {
   float sr0 = solref[0], sr1 = solref[1];
   if (sr0 > 0) sr0 = fmaxf(sr0, 2 * timestep);
@@ -465,7 +465,7 @@ LS_FN void crb_factor(const int ms, EnvS<C>& e) {
 // ----------------------------------------------------------------------------------------------------------
 struct RawCon { float dist, pos[3], frame[6]; };
 
-LS_DEV int plane_sphere(RawCon* c, float margin, const float* pos1, const float* n, const float* pos2, float r) {
+LS_FN int plane_sphere(RawCon* c, float margin, const float* pos1, const float* n, const float* pos2, float r) {
   float tmp[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
   float cdist = dot3(tmp, n);
   if (cdist > margin + r) return 0;
@@ -473,7 +473,7 @@ LS_DEV int plane_sphere(RawCon* c, float margin, const float* pos1, const float*
   for (int k = 0; k < 3; k++) { c->frame[k] = n[k]; c->frame[3 + k] = 0; c->pos[k] = pos2[k] + n[k] * (-c->dist * 0.5f - r); }
   return 1;
 }
-LS_DEV int plane_capsule(RawCon* c, float margin, const float* pos1, const float* n, const float* pos2, const float* mat2,
+LS_FN int plane_capsule(RawCon* c, float margin, const float* pos1, const float* n, const float* pos2, const float* mat2,
                          const float* size2) {
   float axis[3] = {mat2[2], mat2[5], mat2[8]};
   float seg[3] = {axis[0] * size2[1], axis[1] * size2[1], axis[2] * size2[1]};
@@ -485,7 +485,7 @@ LS_DEV int plane_capsule(RawCon* c, float margin, const float* pos1, const float
   if (n2) for (int k = 0; k < 3; k++) c[n1].frame[3 + k] = axis[k];
   return n1 + n2;
 }
-LS_DEV int plane_cylinder(RawCon* c, float margin, const float* pos1, const float* normal, const float* pos2,
+LS_FN int plane_cylinder(RawCon* c, float margin, const float* pos1, const float* normal, const float* pos2,
                           const float* mat2, const float* size2) {
   float axis[3] = {mat2[2], mat2[5], mat2[8]};
   float d[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
@@ -538,7 +538,7 @@ LS_DEV int plane_cylinder(RawCon* c, float margin, const float* pos1, const floa
   }
   return cnt;
 }
-LS_DEV int plane_box(RawCon* c, float margin, const float* pos1, const float* norm, const float* pos2, const float* mat2,
+LS_FN int plane_box(RawCon* c, float margin, const float* pos1, const float* norm, const float* pos2, const float* mat2,
                      const float* size2) {
   float d[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
   float dist = dot3(d, norm);
@@ -558,7 +558,7 @@ LS_DEV int plane_box(RawCon* c, float margin, const float* pos1, const float* no
   }
   return cnt;
 }
-LS_DEV int plane_mesh(RawCon* c, float margin, const float* pos1, const float* norm, const float* pos2, const float* mat2,
+LS_FN int plane_mesh(RawCon* c, float margin, const float* pos1, const float* norm, const float* pos2, const float* mat2,
                       const float* verts, int nvert, float rbound) {
   float nl[3];
   mulmatTvec3(nl, mat2, norm);
@@ -593,7 +593,7 @@ LS_DEV int plane_mesh(RawCon* c, float margin, const float* pos1, const float* n
   }
   return cnt;
 }
-LS_DEV int sphere_sphere_raw(RawCon* c, float margin, const float* pos1, float r1, const float* pos2, float r2) {
+LS_FN int sphere_sphere_raw(RawCon* c, float margin, const float* pos1, float r1, const float* pos2, float r2) {
   float dif[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
   float cdist = sqrtf(dot3(dif, dif));
   if (cdist > margin + r1 + r2) return 0;
@@ -603,7 +603,7 @@ LS_DEV int sphere_sphere_raw(RawCon* c, float margin, const float* pos1, float r
   for (int k = 0; k < 3; k++) { c->frame[3 + k] = 0; c->pos[k] = pos1[k] + c->frame[k] * (r1 + 0.5f * c->dist); }
   return 1;
 }
-LS_DEV int sphere_capsule(RawCon* c, float margin, const float* pos1, float r1, const float* pos2, const float* mat2,
+LS_FN int sphere_capsule(RawCon* c, float margin, const float* pos1, float r1, const float* pos2, const float* mat2,
                           const float* size2) {
   float axis[3] = {mat2[2], mat2[5], mat2[8]};
   float vec[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
@@ -611,7 +611,7 @@ LS_DEV int sphere_capsule(RawCon* c, float margin, const float* pos1, float r1, 
   float p[3] = {pos2[0] + axis[0] * x, pos2[1] + axis[1] * x, pos2[2] + axis[2] * x};
   return sphere_sphere_raw(c, margin, pos1, r1, p, size2[0]);
 }
-LS_DEV int capsule_capsule(RawCon* c, float margin, const float* pos1, const float* mat1, const float* size1,
+LS_FN int capsule_capsule(RawCon* c, float margin, const float* pos1, const float* mat1, const float* size1,
                            const float* pos2, const float* mat2, const float* size2) {
   float a1[3] = {mat1[2], mat1[5], mat1[8]}, a2[3] = {mat2[2], mat2[5], mat2[8]};
   float dif[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
@@ -664,43 +664,20 @@ LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p) {
   return dot3(d, d) <= bound * bound;
 }
 
-// narrow phase of pair p, appending to the env's contact list (executed by a single lane)
+// contact parameters (mj_contactParam), frame completion (mju_makeFrame) and storage of one raw contact
 template <class C>
-LS_FN void pair_narrow(const int ms, EnvS<C>& e, int p) {
+LS_FN void finish_contact(const int ms, EnvS<C>& e, int g1, int g2, float margin, const RawCon* rawk) {
   const DevModel& m = c_models[ms];
-  int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
-  int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-  float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
-  const float *pos1 = e.gxpos[g1], *pos2 = e.gxpos[g2];
-  const float *size1 = m.geom_size + 3 * g1, *size2 = m.geom_size + 3 * g2;
-  float mat1[9], mat2[9];
-  geom_mat(ms, e, g1, mat1);
-  geom_mat(ms, e, g2, mat2);
-  RawCon raw[4];
-  int n = 0;
-  if (t1 == LS_GEOM_PLANE) {
-    float nrm[3] = {mat1[2], mat1[5], mat1[8]};
-    if (t2 == LS_GEOM_SPHERE) n = plane_sphere(raw, margin, pos1, nrm, pos2, size2[0]);
-    else if (t2 == LS_GEOM_CAPSULE) n = plane_capsule(raw, margin, pos1, nrm, pos2, mat2, size2);
-    else if (t2 == LS_GEOM_CYLINDER) n = plane_cylinder(raw, margin, pos1, nrm, pos2, mat2, size2);
-    else if (t2 == LS_GEOM_BOX) n = plane_box(raw, margin, pos1, nrm, pos2, mat2, size2);
-    else if (t2 == LS_GEOM_MESH)
-      n = plane_mesh(raw, margin, pos1, nrm, pos2, mat2, m.mesh_vert + 3 * m.geom_meshadr[g2], m.geom_meshnum[g2],
-                     m.geom_rbound[g2]);
-  } else if (t1 == LS_GEOM_SPHERE && t2 == LS_GEOM_SPHERE) {
-    n = sphere_sphere_raw(raw, margin, pos1, size1[0], pos2, size2[0]);
-  } else if (t1 == LS_GEOM_SPHERE && t2 == LS_GEOM_CAPSULE) {
-    n = sphere_capsule(raw, margin, pos1, size1[0], pos2, mat2, size2);
-  } else if (t1 == LS_GEOM_CAPSULE && t2 == LS_GEOM_CAPSULE) {
-    n = capsule_capsule(raw, margin, pos1, mat1, size1, pos2, mat2, size2);
-  }
+  const RawCon* raw = rawk;
+  const int k = 0;
   int base = e.ncon;
-  NOUNROLL for (int k = 0; k < n && base < EnvS<C>::MAXCON; k++) {
+  if (base >= EnvS<C>::MAXCON) return;
+  do {
     // contact parameters (mj_contactParam)
     int p1 = m.geom_priority[g1], p2 = m.geom_priority[g2];
     float gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
     float incl = margin - gap;
-    if (raw[k].dist >= incl) continue;   // not active: never enters the constraint set
+    if (raw[k].dist >= incl) break;   // not active: never enters the constraint set
     int ci = base++;
     float fri[3], solref[2], solimp[5];
     if (p1 != p2) {
@@ -742,8 +719,41 @@ LS_FN void pair_narrow(const int ms, EnvS<C>& e, int p) {
     normalize3(f + 3);
     cross3(f + 6, f, f + 3);
     for (int c = 0; c < 9; c++) e.con_frame[ci][c] = f[c];
-  }
+  } while (0);
   e.ncon = base;
+}
+
+// narrow phase of pair p, appending to the env's contact list (executed by a single lane)
+template <class C>
+LS_FN void pair_narrow(const int ms, EnvS<C>& e, int p) {
+  const DevModel& m = c_models[ms];
+  int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+  int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+  float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
+  const float *pos1 = e.gxpos[g1], *pos2 = e.gxpos[g2];
+  const float *size1 = m.geom_size + 3 * g1, *size2 = m.geom_size + 3 * g2;
+  float mat1[9], mat2[9];
+  geom_mat(ms, e, g1, mat1);
+  geom_mat(ms, e, g2, mat2);
+  RawCon raw[4];
+  int n = 0;
+  if (t1 == LS_GEOM_PLANE) {
+    float nrm[3] = {mat1[2], mat1[5], mat1[8]};
+    if (t2 == LS_GEOM_SPHERE) n = plane_sphere(raw, margin, pos1, nrm, pos2, size2[0]);
+    else if (t2 == LS_GEOM_CAPSULE) n = plane_capsule(raw, margin, pos1, nrm, pos2, mat2, size2);
+    else if (t2 == LS_GEOM_CYLINDER) n = plane_cylinder(raw, margin, pos1, nrm, pos2, mat2, size2);
+    else if (t2 == LS_GEOM_BOX) n = plane_box(raw, margin, pos1, nrm, pos2, mat2, size2);
+    else if (t2 == LS_GEOM_MESH)
+      n = plane_mesh(raw, margin, pos1, nrm, pos2, mat2, m.mesh_vert + 3 * m.geom_meshadr[g2], m.geom_meshnum[g2],
+                     m.geom_rbound[g2]);
+  } else if (t1 == LS_GEOM_SPHERE && t2 == LS_GEOM_SPHERE) {
+    n = sphere_sphere_raw(raw, margin, pos1, size1[0], pos2, size2[0]);
+  } else if (t1 == LS_GEOM_SPHERE && t2 == LS_GEOM_CAPSULE) {
+    n = sphere_capsule(raw, margin, pos1, size1[0], pos2, mat2, size2);
+  } else if (t1 == LS_GEOM_CAPSULE && t2 == LS_GEOM_CAPSULE) {
+    n = capsule_capsule(raw, margin, pos1, mat1, size1, pos2, mat2, size2);
+  }
+  NOUNROLL for (int k = 0; k < n; k++) finish_contact(ms, e, g1, g2, margin, raw + k);
 }
 
 template <class C>
