@@ -16,6 +16,13 @@ import sys
 import threading
 import time
 
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("LOCO_MUJOCO_B200_FORCE_BUNDLED", "1")     # the GPU box has no reference checkout
@@ -115,7 +122,7 @@ def main():
         if rank != 0:
             return
         env = LocoEnv.make(a.task + ".real", debug=True)
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         per_step = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
         vals = []
         desc = ""
@@ -188,28 +195,21 @@ def main():
     resets = int(counters[:, 1].sum().item())
 
     # ---- end-to-end through the public API with host buffers ----
-    h_act = torch.empty((N, nu), dtype=torch.float32).pin_memory()
-    h_obs = torch.empty((N, D), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty((N,), dtype=torch.float32).pin_memory()
-    h_done = torch.empty((N,), dtype=torch.uint8).pin_memory()
+    # per step: H2D of this step's actions (pinned) -> LocoEnv.step -> one packed D2H of (obs, reward, done) -> sync
+    host_actions = (torch.rand((a.steps, N, nu)) * 2 - 1).pin_memory()
+    h_out = torch.empty((N, D + 2), dtype=torch.float32).pin_memory()
     d_act = torch.empty((N, nu), dtype=torch.float32, device=dev)
-    host_actions = (torch.rand((a.steps, N, nu)) * 2 - 1)
     barrier()
     t0 = time.perf_counter()
     for k in range(a.steps):
-        h_act.copy_(host_actions[k])
-        d_act.copy_(h_act, non_blocking=True)
+        d_act.copy_(host_actions[k], non_blocking=True)
         obs, rew, done, info = env.step(d_act)
-        h_obs.copy_(obs, non_blocking=True)
-        h_rew.copy_(rew, non_blocking=True)
-        h_done.copy_(done.to(torch.uint8), non_blocking=True)
+        h_out.copy_(torch.cat([obs, rew[:, None], done[:, None].to(torch.float32)], dim=1), non_blocking=True)
         torch.cuda.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = world * N * a.steps / float(t.item())
+    from loco_mujoco_b200.parallel import aggregate_throughput
+    e2e, _ = aggregate_throughput(N * a.steps, e2e_s, device=dev)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -222,14 +222,14 @@ def main():
         achieved = bytes_per * N / (launch_ms / 1e3) / 1e9
         cpu = None
         if not a.no_cpu_baseline:
-            v, desc = cpu_rollout(env, a.cpu_seconds, os.cpu_count() or 1)
-            cpu = {"value": v, "unit": "env-steps/s", "cores": os.cpu_count() or 1, "kind": "port", "sample": desc}
+            v, desc = cpu_rollout(env, a.cpu_seconds, host_threads())
+            cpu = {"value": v, "unit": "env-steps/s", "cores": host_threads(), "kind": "port", "sample": desc}
         line = {"metric": "env-steps/sec (batched random-action rollout)", "value": value, "unit": "env-steps/s",
                 "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": launch_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": cfg, "clocks": clocks, "gpu_launches": gpu_launches,
                 "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4,
-                        "d2h_bytes_per_step": N * (D * 4 + 4 + 1)},
+                        "d2h_bytes_per_step": N * (D + 2) * 4},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": None, "peak_source": which, "algorithmic_bytes_per_env_step": bytes_per,
                              "note": "compute/latency-bound by design: state stays in shared memory across the 10 "
