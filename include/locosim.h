@@ -66,7 +66,8 @@ int locosim_get_state(locosim_t* h, float* d_qpos, float* d_qvel, float* d_qacc_
 int locosim_set_state(locosim_t* h, const float* d_qpos, const float* d_qvel, const float* d_qacc_warmstart, void* stream);
 
 /* Diagnostics: per-env counters since create: [0]=env steps, [1]=resets, [2]=solver iterations of the last sub-step,
- * [3]=contacts of the last sub-step.  d_out int32 [n_envs, 4]. */
+ * [3]=contacts of the last sub-step, [4]=terminations caused by a non-finite state, [5..7]=max over control steps of the
+ * last sub-step's solver iterations / contacts / constraint rows.  d_out int32 [n_envs, 8]. */
 int locosim_get_counters(locosim_t* h, int32_t* d_out, void* stream);
 
 /* Launch geometry chosen for this handle: warps(envs) per block, dynamic shared memory bytes per block, blocks. */

@@ -21,7 +21,7 @@
 struct EngineState {
   float *qpos, *qvel, *ws, *goal;   // [N,nv] [N,nv] [N,nv] [N,4]
   int* episode;                     // [N] reset counter (drives the per-env random stream)
-  int* counters;                    // [N,4]
+  int* counters;                    // [N,8]
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
@@ -73,7 +73,7 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
       obs[(size_t)env * t.obs_dim + k] = v;
     }
   }
-  if (lane == 0) { st.episode[env] = ep + 1; st.counters[(size_t)env * 4 + 1] += 1; }
+  if (lane == 0) { st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1; }
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -144,8 +144,10 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
     float r = rew;
     reward[env] = r;
     done[env] = is_done ? 1 : 0;
-    int* cnt = st.counters + (size_t)env * 4;
+    int* cnt = st.counters + (size_t)env * 8;
     cnt[0] += 1; cnt[2] = e.solver_iter; cnt[3] = e.ncon;
+    if (bad) cnt[4] += 1;
+    cnt[5] = max(cnt[5], e.solver_iter); cnt[6] = max(cnt[6], e.ncon); cnt[7] = max(cnt[7], e.nefc);
   }
 
   // ---- auto-reset ----
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
     draw_reset(seed, env_off + env, ep, t.n_traj, t.traj_len, &tr, &sp);
     __syncwarp();
     reset_env(ms, t, e, tr, sp);
-    if (lane == 0) { st.episode[env] = ep + 1; st.counters[(size_t)env * 4 + 1] += 1; }
+    if (lane == 0) { st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1; }
     for (int k = lane; k < t.n_goal; k += 32) st.goal[(size_t)env * 4 + k] = e.goal[k];
   }
   if (next_obs) for (int k = lane; k < D; k += 32) next_obs[(size_t)env * D + k] = obs_value(t, e, k);
@@ -283,10 +285,10 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   size_t N = (size_t)n_envs, nv = (size_t)h->hm.nv;
   ok = ok && cudaMalloc((void**)&h->st.qpos, N * nv * 4) == cudaSuccess && cudaMalloc((void**)&h->st.qvel, N * nv * 4) == cudaSuccess &&
        cudaMalloc((void**)&h->st.ws, N * nv * 4) == cudaSuccess && cudaMalloc((void**)&h->st.goal, N * 4 * 4) == cudaSuccess &&
-       cudaMalloc((void**)&h->st.episode, N * 4) == cudaSuccess && cudaMalloc((void**)&h->st.counters, N * 16) == cudaSuccess;
+       cudaMalloc((void**)&h->st.episode, N * 4) == cudaSuccess && cudaMalloc((void**)&h->st.counters, N * 32) == cudaSuccess;
   if (!ok) { std::string m = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); locosim_destroy(h); g_create_error = m; return 1; }
   cudaMemset(h->st.qpos, 0, N * nv * 4); cudaMemset(h->st.qvel, 0, N * nv * 4); cudaMemset(h->st.ws, 0, N * nv * 4);
-  cudaMemset(h->st.goal, 0, N * 16); cudaMemset(h->st.episode, 0, N * 4); cudaMemset(h->st.counters, 0, N * 16);
+  cudaMemset(h->st.goal, 0, N * 16); cudaMemset(h->st.episode, 0, N * 4); cudaMemset(h->st.counters, 0, N * 32);
   bind_model(h->dm, h->hm, h->d_mints, h->d_mreals);
   for (int k = 0; k < LS_MAX_SLOTS && h->slot < 0; k++) if (!g_slot_used[k]) { h->slot = k; g_slot_used[k] = true; }
   if (h->slot < 0) { locosim_destroy(h); g_create_error = "too many live locosim handles (max 8 per process)"; return 1; }
@@ -364,7 +366,7 @@ int locosim_set_state(locosim_t* h, const float* q, const float* v, const float*
   return 0;
 }
 int locosim_get_counters(locosim_t* h, int32_t* d_out, void* stream) {
-  CK(cudaMemcpyAsync(d_out, h->st.counters, (size_t)h->n_envs * 16, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  CK(cudaMemcpyAsync(d_out, h->st.counters, (size_t)h->n_envs * 32, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 int locosim_launch_info(const locosim_t* h, int* wpb, int* smem, int* blocks) {

@@ -1075,6 +1075,7 @@ LS_FN float constraint_update(const int ms, EnvS<C>& e) {
       float TT = 0;
       NOUNROLL for (int j = 1; j < dim; j++) { U[j] = e.r_jar[r + j] * e.con_fri[ci][j - 1]; TT += U[j] * U[j]; }
       float N = U[0], T = sqrtf(TT);
+      if (T < 1e-12f) T = 0.0f;   // fp32: 1/T^3 in the cone Hessian would overflow
       if (N >= mu * T || (T <= 0 && N >= 0)) {
         NOUNROLL for (int j = 0; j < dim; j++) { e.r_force[r + j] = 0; e.r_state[r + j] = ST_SATISFIED; }
       } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
@@ -1327,7 +1328,8 @@ LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alp
         if (N < 0) { c += qc; d1 += q1; d2 += q2; }
       } else {
         float T = sqrtf(Tsqr);
-        if (N >= mu * T) {
+        if (T < 1e-12f) { if (N < 0) { c += qc; d1 += q1; d2 += q2; } }
+        else if (N >= mu * T) {
         } else if (mu * N + T <= 0) { c += qc; d1 += q1; d2 += q2; }
         else {
           float Dm = D / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
@@ -1419,6 +1421,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
   const int nv = m.nv, nefc = e.nefc;
   if (nefc == 0) {
     PAR_FOR(i, nv) { e.qacc[i] = e.qacc_smooth[i]; e.qacc_ws[i] = e.qacc_smooth[i]; e.qfrc_constraint[i] = 0; }
+    LANE0 { e.solver_iter = 0; }
     SYNC();
     return;
   }

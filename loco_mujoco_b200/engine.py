@@ -151,7 +151,7 @@ class CudaEngine:
 
     def counters(self):
         t = self.torch
-        c = t.empty((self.n_envs, 4), dtype=t.int32, device=self.device)
+        c = t.empty((self.n_envs, 8), dtype=t.int32, device=self.device)
         self._check(self.lib.locosim_get_counters(self.h, _ptr(c), self._stream()))
         return c
 
