@@ -70,6 +70,15 @@ int locosim_set_state(locosim_t* h, const float* d_qpos, const float* d_qvel, co
  * last sub-step's solver iterations / contacts / constraint rows.  d_out int32 [n_envs, 8]. */
 int locosim_get_counters(locosim_t* h, int32_t* d_out, void* stream);
 
+/* Domain randomisation (replaces DomainRandomizationHandler + per-reset MjModel recompilation,
+ * /root/reference/loco_mujoco/utils/domain_randomization.py:191-296, hooked at base.py:183-185): a HOST pool of n_rows
+ * parameter sets (row layout: loco_mujoco_b200/domain_randomization.py POOL_FIELDS, row_len floats as float64) is
+ * uploaded once; every (auto-)reset draws one row per env from the engine's counter-based stream. */
+int locosim_param_pool_row_len(const locosim_t* h);
+int locosim_set_param_pool(locosim_t* h, const double* pool, int n_rows, int row_len);
+/* pool row currently used by each env: d_out int32 [n_envs] */
+int locosim_get_param_rows(locosim_t* h, int32_t* d_out, void* stream);
+
 /* Launch geometry chosen for this handle: warps(envs) per block, dynamic shared memory bytes per block, blocks. */
 int locosim_launch_info(const locosim_t* h, int* warps_per_block, int* smem_bytes, int* n_blocks);
 

@@ -22,6 +22,9 @@ struct EngineState {
   float *qpos, *qvel, *ws, *goal;   // [N,nv] [N,nv] [N,nv] [N,4]
   int* episode;                     // [N] reset counter (drives the per-env random stream)
   int* counters;                    // [N,8]
+  int* dr_row;                      // [N] row of the parameter pool used by the env's current episode
+  const float* pool;                // [K, P] parameter pool (domain randomisation); K = 1: the model's own values
+  int pool_K;
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
@@ -36,6 +39,12 @@ __device__ __forceinline__ void draw_reset(uint64_t seed, int64_t genv, int epis
   uint64_t r = mix64(seed ^ mix64((uint64_t)genv * 0x100000001B3ULL + (uint64_t)(uint32_t)episode));
   *traj = (int)((r & 0xffffffffULL) % (uint64_t)n_traj);
   *step = (int)((r >> 32) % (uint64_t)traj_len);
+}
+
+__device__ __forceinline__ int draw_pool_row(uint64_t seed, int64_t genv, int episode, int K) {
+  if (K <= 1) return 0;
+  uint64_t r = mix64((seed + 0x5DEECE66DULL) ^ mix64((uint64_t)genv * 0x100000001B3ULL + (uint64_t)(uint32_t)episode));
+  return (int)(r % (uint64_t)K);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -73,7 +82,10 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
       obs[(size_t)env * t.obs_dim + k] = v;
     }
   }
-  if (lane == 0) { st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1; }
+  if (lane == 0) {
+    st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1;
+    st.dr_row[env] = draw_pool_row(seed, env_off + env, ep, st.pool_K);
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -95,6 +107,7 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
   EnvS<C>& e = reinterpret_cast<EnvS<C>*>(smem_raw)[warp];
   const DevModel& m = c_models[ms];
   const int nv = m.nv, nu = m.nu, D = t.obs_dim;
+  if (lane == 0) e.prm = st.pool + (size_t)st.dr_row[env] * m.pool_P;
 
   // ---- load state ----
   for (int i = lane; i < nv; i += 32) {
@@ -157,7 +170,10 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
     draw_reset(seed, env_off + env, ep, t.n_traj, t.traj_len, &tr, &sp);
     __syncwarp();
     reset_env(ms, t, e, tr, sp);
-    if (lane == 0) { st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1; }
+    if (lane == 0) {
+      st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1;
+      st.dr_row[env] = draw_pool_row(seed, env_off + env, ep, st.pool_K);
+    }
     for (int k = lane; k < t.n_goal; k += 32) st.goal[(size_t)env * 4 + k] = e.goal[k];
   }
   if (next_obs) for (int k = lane; k < D; k += 32) next_obs[(size_t)env * D + k] = obs_value(t, e, k);
@@ -184,6 +200,7 @@ struct locosim_handle {
   SolverOpts so;
   EngineState st;
   int* d_mints = nullptr; float* d_mreals = nullptr; int* d_tints = nullptr; float* d_treals = nullptr;
+  float* d_pool = nullptr;
   std::string err;
 };
 static std::string g_create_error;
@@ -285,10 +302,14 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   size_t N = (size_t)n_envs, nv = (size_t)h->hm.nv;
   ok = ok && cudaMalloc((void**)&h->st.qpos, N * nv * 4) == cudaSuccess && cudaMalloc((void**)&h->st.qvel, N * nv * 4) == cudaSuccess &&
        cudaMalloc((void**)&h->st.ws, N * nv * 4) == cudaSuccess && cudaMalloc((void**)&h->st.goal, N * 4 * 4) == cudaSuccess &&
-       cudaMalloc((void**)&h->st.episode, N * 4) == cudaSuccess && cudaMalloc((void**)&h->st.counters, N * 32) == cudaSuccess;
+       cudaMalloc((void**)&h->st.episode, N * 4) == cudaSuccess && cudaMalloc((void**)&h->st.counters, N * 32) == cudaSuccess &&
+       cudaMalloc((void**)&h->st.dr_row, N * 4) == cudaSuccess &&
+       up((void**)&h->d_pool, h->hm.default_row.data(), h->hm.default_row.size() * 4);
   if (!ok) { std::string m = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); locosim_destroy(h); g_create_error = m; return 1; }
   cudaMemset(h->st.qpos, 0, N * nv * 4); cudaMemset(h->st.qvel, 0, N * nv * 4); cudaMemset(h->st.ws, 0, N * nv * 4);
   cudaMemset(h->st.goal, 0, N * 16); cudaMemset(h->st.episode, 0, N * 4); cudaMemset(h->st.counters, 0, N * 32);
+  cudaMemset(h->st.dr_row, 0, N * 4);
+  h->st.pool = h->d_pool; h->st.pool_K = 1;
   bind_model(h->dm, h->hm, h->d_mints, h->d_mreals);
   for (int k = 0; k < LS_MAX_SLOTS && h->slot < 0; k++) if (!g_slot_used[k]) { h->slot = k; g_slot_used[k] = true; }
   if (h->slot < 0) { locosim_destroy(h); g_create_error = "too many live locosim handles (max 8 per process)"; return 1; }
@@ -312,7 +333,7 @@ void locosim_destroy(locosim_t* h) {
   if (h->slot >= 0) g_slot_used[h->slot] = false;
   cudaFree(h->d_mints); cudaFree(h->d_mreals); cudaFree(h->d_tints); cudaFree(h->d_treals);
   cudaFree(h->st.qpos); cudaFree(h->st.qvel); cudaFree(h->st.ws); cudaFree(h->st.goal); cudaFree(h->st.episode);
-  cudaFree(h->st.counters);
+  cudaFree(h->st.counters); cudaFree(h->st.dr_row); cudaFree(h->d_pool);
   delete h;
 }
 
@@ -369,6 +390,38 @@ int locosim_get_counters(locosim_t* h, int32_t* d_out, void* stream) {
   CK(cudaMemcpyAsync(d_out, h->st.counters, (size_t)h->n_envs * 32, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
+int locosim_param_pool_row_len(const locosim_t* h) { return h->hm.pool_P; }
+
+int locosim_get_param_rows(locosim_t* h, int32_t* d_out, void* stream) {
+  CK(cudaMemcpyAsync(d_out, h->st.dr_row, (size_t)h->n_envs * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int locosim_set_param_pool(locosim_t* h, const double* pool, int n_rows, int row_len) {
+  if (!pool || n_rows < 1 || row_len != h->hm.pool_P) { h->err = "bad parameter pool (row_len must equal locosim_param_pool_row_len)"; return 1; }
+  CK(cudaSetDevice(h->device));
+  std::vector<float> f((size_t)n_rows * row_len);
+  bool damp = false;
+  for (size_t i = 0; i < f.size(); i++) {
+    f[i] = (float)pool[i];
+    if (!(f[i] == f[i]) || f[i] > 1e30f || f[i] < -1e30f) { h->err = "non-finite value in parameter pool"; return 1; }
+  }
+  for (int r = 0; r < n_rows; r++)
+    for (int d = 0; d < h->hm.nv; d++) if (f[(size_t)r * row_len + h->hm.po[0] + d] > 0) damp = true;
+  float* d_new = nullptr;
+  CK(cudaMalloc((void**)&d_new, f.size() * 4));
+  CK(cudaMemcpy(d_new, f.data(), f.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());
+  cudaFree(h->d_pool);
+  h->d_pool = d_new; h->st.pool = d_new; h->st.pool_K = n_rows;
+  if (damp && !h->dm.has_damping) {
+    h->dm.has_damping = 1;
+    CK(cudaMemcpyToSymbol(c_models, &h->dm, sizeof(DevModel), sizeof(DevModel) * h->slot));
+  }
+  CK(cudaMemset(h->st.dr_row, 0, (size_t)h->n_envs * 4));
+  return 0;
+}
+
 int locosim_launch_info(const locosim_t* h, int* wpb, int* smem, int* blocks) {
   if (wpb) *wpb = h->wpb;
   if (smem) *smem = h->smem;

@@ -71,6 +71,9 @@ struct DevModel {
   const int* body_dofmask;   // [nb] bit d set if dof d is on the path root..body
   const int* dof_frow;       // [nv] index of the frictionloss row of dof d, or -1
   const int* tri_ij;         // [nv(nv+1)/2] packed (i << 8) | j of the lower triangle, row major
+  // per-env parameter pool (domain randomisation): float offsets of each field inside one pool row
+  int po_dof_damping, po_dof_frictionloss, po_dof_armature, po_jnt_stiffness, po_dof_invweight0, po_body_mass,
+      po_body_inertia, po_body_ipos, po_body_iquat, po_geom_friction, po_geom_invweight0, po_meaninertia, pool_P;
 };
 
 struct DevTask {
@@ -141,7 +144,9 @@ struct alignas(16) EnvS {
   float coneU[8], coneS[8];
   // task
   float goal[4];
+  const float* prm;        // this env's row of the parameter pool
 };
+#define PRM(field) (e.prm + m.po_##field)
 #define ROW_TYPE(ti) ((ti) & 255)
 #define ROW_ID(ti) (((ti) >> 8) & 0xffff)
 #define ROW_K(ti) ((ti) >> 24)
@@ -284,10 +289,10 @@ LS_FN void kinematics(const int ms, EnvS<C>& e) {
       for (int c = 0; c < 3; c++) e.xpos[b][c] = pos[c];
       for (int c = 0; c < 4; c++) e.xquat[b][c] = quat[c];
       for (int c = 0; c < 9; c++) e.xmat[b][c] = mat[c];
-      mulmatvec3(tmp, mat, m.body_ipos + 3 * b);
+      mulmatvec3(tmp, mat, PRM(body_ipos) + 3 * b);
       for (int c = 0; c < 3; c++) e.xipos[b][c] = pos[c] + tmp[c];
       float iq[4], im[9];
-      mulquat(iq, quat, m.body_iquat + 4 * b);
+      mulquat(iq, quat, PRM(body_iquat) + 4 * b);
       quat2mat(im, iq);
       for (int c = 0; c < 9; c++) e.ximat[b][c] = im[c];
     }
@@ -318,7 +323,7 @@ LS_FN void com_pos(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
   float sx = 0, sy = 0, sz = 0, sm = 0;
   PAR_FOR(b, m.nb) {
-    float ms = m.body_mass[b];
+    float ms = PRM(body_mass)[b];
     sx += ms * e.xipos[b][0]; sy += ms * e.xipos[b][1]; sz += ms * e.xipos[b][2]; sm += ms;
   }
   sx = WARP_SUM(sx); sy = WARP_SUM(sy); sz = WARP_SUM(sz); sm = WARP_SUM(sm);
@@ -330,8 +335,8 @@ LS_FN void com_pos(const int ms, EnvS<C>& e) {
     if (b == 0) { for (int k = 0; k < 10; k++) ci[k] = 0; continue; }
     float dif[3] = {e.xipos[b][0] - com[0], e.xipos[b][1] - com[1], e.xipos[b][2] - com[2]};
     const float* R = e.ximat[b];
-    const float* I = m.body_inertia + 3 * b;
-    float mass = m.body_mass[b];
+    const float* I = PRM(body_inertia) + 3 * b;
+    float mass = PRM(body_mass)[b];
     float t[9];
     for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) t[3 * r + c] = R[3 * r + c] * I[c];
     float r00 = t[0] * R[0] + t[1] * R[1] + t[2] * R[2], r11 = t[3] * R[3] + t[4] * R[4] + t[5] * R[5],
@@ -449,7 +454,7 @@ LS_FN void crb_factor(const int ms, EnvS<C>& e) {
     NOUNROLL for (int j = i; j >= 0; j = m.dof_parentid[j]) {
       float v = 0;
       for (int k = 0; k < 6; k++) v += e.cdof[j][k] * buf[k];
-      if (j == i) v += m.dof_armature[i];
+      if (j == i) v += PRM(dof_armature)[i];
       e.M[i][j] = v;
       e.M[j][i] = v;
     }
@@ -685,7 +690,7 @@ LS_FN void finish_contact(const int ms, EnvS<C>& e, int g1, int g2, float margin
       e.con_dim[ci] = m.geom_condim[g];
       for (int c = 0; c < 2; c++) solref[c] = m.geom_solref[2 * g + c];
       for (int c = 0; c < 5; c++) solimp[c] = m.geom_solimp[5 * g + c];
-      for (int c = 0; c < 3; c++) fri[c] = m.geom_friction[3 * g + c];
+      for (int c = 0; c < 3; c++) fri[c] = PRM(geom_friction)[3 * g + c];
     } else {
       e.con_dim[ci] = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
       float s1 = m.geom_solmix[g1], s2 = m.geom_solmix[g2], mix;
@@ -697,7 +702,7 @@ LS_FN void finish_contact(const int ms, EnvS<C>& e, int g1, int g2, float margin
       if (r1[0] > 0 && r2[0] > 0) for (int c = 0; c < 2; c++) solref[c] = mix * r1[c] + (1 - mix) * r2[c];
       else for (int c = 0; c < 2; c++) solref[c] = fminf(r1[c], r2[c]);
       for (int c = 0; c < 5; c++) solimp[c] = mix * m.geom_solimp[5 * g1 + c] + (1 - mix) * m.geom_solimp[5 * g2 + c];
-      for (int c = 0; c < 3; c++) fri[c] = fmaxf(m.geom_friction[3 * g1 + c], m.geom_friction[3 * g2 + c]);
+      for (int c = 0; c < 3; c++) fri[c] = fmaxf(PRM(geom_friction)[3 * g1 + c], PRM(geom_friction)[3 * g2 + c]);
     }
     impedance_KB(solref, solimp, raw[k].dist, incl, m.timestep, &e.con_imp[ci], &e.con_K[ci], &e.con_B[ci]);
     e.con_fri[ci][0] = fri[0]; e.con_fri[ci][1] = fri[0]; e.con_fri[ci][2] = fri[1]; e.con_fri[ci][3] = fri[2];
@@ -895,19 +900,19 @@ LS_FN void make_constraint(const int ms, EnvS<C>& e) {
     const int tp = ROW_TYPE(ti), id = ROW_ID(ti), k = ROW_K(ti);
     float pos, margin, diag, vel, imp, K, B;
     if (tp == ROW_FRICTION) {
-      pos = 0; margin = 0; diag = m.dof_invweight0[id]; vel = e.qvel[id];
+      pos = 0; margin = 0; diag = PRM(dof_invweight0)[id]; vel = e.qvel[id];
       impedance_KB(m.dof_solref + 2 * id, m.dof_solimp + 5 * id, pos, margin, m.timestep, &imp, &K, &B);
     } else if (tp == ROW_LIMIT) {
       pos = k == 0 ? e.qpos[id] - m.jnt_range[2 * id] : m.jnt_range[2 * id + 1] - e.qpos[id];
-      margin = m.jnt_margin[id]; diag = m.dof_invweight0[id]; vel = k == 0 ? e.qvel[id] : -e.qvel[id];
+      margin = m.jnt_margin[id]; diag = PRM(dof_invweight0)[id]; vel = k == 0 ? e.qvel[id] : -e.qvel[id];
       impedance_KB(m.jnt_solref + 2 * id, m.jnt_solimp + 5 * id, pos, margin, m.timestep, &imp, &K, &B);
     } else {
       pos = e.con_dist[id]; margin = e.con_incl[id];
       imp = e.con_imp[id]; K = e.con_K[id]; B = e.con_B[id];
       const int g1 = e.con_g1[id], g2 = e.con_g2[id];
-      float tran = m.geom_invweight0[2 * g1] + m.geom_invweight0[2 * g2];
+      float tran = PRM(geom_invweight0)[2 * g1] + PRM(geom_invweight0)[2 * g2];
       if (tp == ROW_CON_PYRAMIDAL) diag = tran + e.con_fri[id][0] * e.con_fri[id][0] * tran;
-      else diag = k < 3 ? tran : m.geom_invweight0[2 * g1 + 1] + m.geom_invweight0[2 * g2 + 1];
+      else diag = k < 3 ? tran : PRM(geom_invweight0)[2 * g1 + 1] + PRM(geom_invweight0)[2 * g2 + 1];
       const float* Jr = e.J[r - nunit];
       vel = 0;
 #pragma unroll 4
@@ -1003,7 +1008,7 @@ LS_FN void smooth_forces(const int ms, EnvS<C>& e) {
     const float* f = e.crb[m.jnt_bodyid[j]];
     float bias = 0;
     for (int c = 0; c < 6; c++) bias += e.cdof[j][c] * f[c];
-    float passive = -m.jnt_stiffness[j] * (e.qpos[j] - m.qpos_spring[j]) - m.dof_damping[j] * e.qvel[j];
+    float passive = -PRM(jnt_stiffness)[j] * (e.qpos[j] - m.qpos_spring[j]) - PRM(dof_damping)[j] * e.qvel[j];
     e.qfrc_smooth[j] = passive - bias;
   }
   SYNC();
@@ -1062,7 +1067,7 @@ LS_FN float constraint_update(const int ms, EnvS<C>& e) {
     const int tp = ROW_TYPE(ti);
     float jar = e.r_jar[r], D = e.r_D[r];
     if (tp == ROW_FRICTION) {
-      float f = m.dof_frictionloss[ROW_ID(ti)], Rf = f / D;
+      float f = PRM(dof_frictionloss)[ROW_ID(ti)], Rf = f / D;
       if (jar <= -Rf) { e.r_state[r] = ST_LINEARNEG; e.r_force[r] = f; cost += -0.5f * Rf * f - f * jar; }
       else if (jar >= Rf) { e.r_state[r] = ST_LINEARPOS; e.r_force[r] = -f; cost += -0.5f * Rf * f + f * jar; }
       else { e.r_state[r] = ST_QUADRATIC; e.r_force[r] = -D * jar; cost += 0.5f * D * jar * jar; }
@@ -1304,7 +1309,7 @@ LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alp
     float ja = e.r_jar[r], jv = e.r_Jv[r], D = e.r_D[r];
     float x = ja + alpha * jv;
     if (tp == ROW_FRICTION) {
-      float f = m.dof_frictionloss[ROW_ID(ti)], Rf = f / D;
+      float f = PRM(dof_frictionloss)[ROW_ID(ti)], Rf = f / D;
       if (x <= -Rf) { c += f * (-0.5f * Rf - x); d1 += -f * jv; }
       else if (x >= Rf) { c += f * (-0.5f * Rf + x); d1 += f * jv; }
       else { c += 0.5f * D * x * x; d1 += D * x * jv; d2 += D * jv * jv; }
@@ -1453,7 +1458,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
   }
   SYNC();
   // ---- Newton iterations ----
-  float scale = 1.0f / (m.meaninertia * (nv > 1 ? nv : 1));
+  float scale = 1.0f / (PRM(meaninertia)[0] * (nv > 1 ? nv : 1));
   float gauss;
   float cost = update_constraint(ms, e, &gauss);
   make_hessian(ms, e);
@@ -1513,7 +1518,7 @@ LS_FN void euler_step(const int ms, EnvS<C>& e) {
     PAR_FOR(idx, E::NV * E::NVP) (&e.H[0][0])[idx] = (&e.M[0][0])[idx];
     SYNC();
     PAR_FOR(i, E::NV) {
-      if (i < nv) { e.H[i][i] += h * m.dof_damping[i]; e.Mgrad[i] = e.qfrc_smooth[i] + e.qfrc_constraint[i]; }
+      if (i < nv) { e.H[i][i] += h * PRM(dof_damping)[i]; e.Mgrad[i] = e.qfrc_smooth[i] + e.qfrc_constraint[i]; }
       else e.Mgrad[i] = 0.0f;
     }
     SYNC();

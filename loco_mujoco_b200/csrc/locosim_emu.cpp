@@ -19,6 +19,7 @@ struct EmuBase {
   virtual void get(double* q, double* v, double* qacc, double* ws) = 0;
   virtual void set_ws(const double* w) = 0;
   virtual int info(int k) = 0;
+  virtual void bind_prm() = 0;
 };
 template <class C>
 struct EmuT : EmuBase {
@@ -47,6 +48,7 @@ struct EmuT : EmuBase {
   }
   void set_ws(const double* w) override { for (int i = 0; i < m.nv; i++) e.qacc_ws[i] = (float)w[i]; }
   int info(int k) override { return k == 0 ? e.ncon : (k == 1 ? e.nefc : e.solver_iter); }
+  void bind_prm() override { e.prm = hm.default_row.data(); }
 };
 
 extern "C" {
@@ -61,6 +63,7 @@ EmuBase* emu_create(const int* ints, int n_ints, const double* reals, int n_real
   else { fprintf(stderr, "emu: no config\n"); return nullptr; }
   s->hm = hm;
   bind_model(s->m, s->hm, s->hm.ints.data(), s->hm.reals.data());
+  s->bind_prm();
   s->so.tolerance = 1e-5f; s->so.ls_tolerance = 0.01f; s->so.max_iter = 20; s->so.ls_iter = 16;
   return s;
 }

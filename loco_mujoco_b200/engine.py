@@ -48,6 +48,12 @@ def load_library():
     lib.locosim_set_state.argtypes = [vp, vp, vp, vp, vp]
     lib.locosim_get_counters.restype = ip
     lib.locosim_get_counters.argtypes = [vp, vp, vp]
+    lib.locosim_param_pool_row_len.restype = ip
+    lib.locosim_param_pool_row_len.argtypes = [vp]
+    lib.locosim_set_param_pool.restype = ip
+    lib.locosim_set_param_pool.argtypes = [vp, vp, ip, ip]
+    lib.locosim_get_param_rows.restype = ip
+    lib.locosim_get_param_rows.argtypes = [vp, vp, vp]
     lib.locosim_launch_info.restype = ip
     lib.locosim_launch_info.argtypes = [vp, ctypes.POINTER(ip), ctypes.POINTER(ip), ctypes.POINTER(ip)]
     _LIB = lib
@@ -56,7 +62,8 @@ def load_library():
 
 EXPORTED_SYMBOLS = ["locosim_create", "locosim_destroy", "locosim_last_error", "locosim_num_envs", "locosim_obs_dim",
                     "locosim_action_dim", "locosim_nq", "locosim_set_solver", "locosim_reset", "locosim_step",
-                    "locosim_get_state", "locosim_set_state", "locosim_get_counters", "locosim_launch_info"]
+                    "locosim_get_state", "locosim_set_state", "locosim_get_counters", "locosim_launch_info",
+                    "locosim_param_pool_row_len", "locosim_set_param_pool", "locosim_get_param_rows"]
 
 
 def _ptr(t):
@@ -148,6 +155,19 @@ class CudaEngine:
             if x is not None and (x.dtype != self.torch.float32 or not x.is_contiguous()):
                 raise ValueError("state tensors must be contiguous float32")
         self._check(self.lib.locosim_set_state(self.h, _ptr(qpos), _ptr(qvel), _ptr(qacc_warmstart), self._stream()))
+
+    def set_param_pool(self, pool):
+        """pool: float64 [n_rows, row_len] (domain_randomization.pool_row layout)."""
+        pool = np.ascontiguousarray(pool, dtype=np.float64)
+        if pool.ndim != 2 or pool.shape[1] != self.lib.locosim_param_pool_row_len(self.h):
+            raise ValueError("pool row length %s != %d" % (pool.shape, self.lib.locosim_param_pool_row_len(self.h)))
+        self._check(self.lib.locosim_set_param_pool(self.h, pool.ctypes.data, pool.shape[0], pool.shape[1]))
+
+    def param_rows(self):
+        t = self.torch
+        r = t.empty((self.n_envs,), dtype=t.int32, device=self.device)
+        self._check(self.lib.locosim_get_param_rows(self.h, _ptr(r), self._stream()))
+        return r
 
     def counters(self):
         t = self.torch

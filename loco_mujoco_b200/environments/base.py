@@ -144,8 +144,9 @@ class LocoEnv:
             raise NotImplementedError("multi-model environments (carry tasks with several weights) are not built yet")
         if use_foot_forces:
             raise NotImplementedError("use_foot_forces=True is not built yet (SURVEY.md 8(f) item 2)")
-        if domain_randomization_config is not None:
-            raise NotImplementedError("domain randomisation is not built yet (SURVEY.md 8(a) row a10)")
+        self._domain_rand_config = domain_randomization_config
+        self._domain_rand_pool_size = viewer_params.pop("domain_randomization_pool_size", 64)
+        self._domain_rand = None
         self._timestep = timestep
         self._n_substeps = n_substeps
         self._n_intermediate_steps = 1
@@ -296,6 +297,17 @@ class LocoEnv:
                         self._n_substeps, self._reset_table(), self._n_goal(), recenter, self._use_absorbing_states,
                         act_idx=self._action_indices)
 
+    def domain_randomization_pool(self):
+        """[K, P] parameter pool: K consecutive randomised recompilations of the model (see domain_randomization.py)."""
+        if self._domain_rand is None:
+            from ..domain_randomization import DomainRandomizationHandler
+            if self._xml_handles[0] is None:
+                raise ValueError("domain randomisation needs the MJCF source (a loco_mujoco checkout), not bundled assets")
+            self._domain_rand = DomainRandomizationHandler([self._xml_handles[0].copy()], self._domain_rand_config,
+                                                           timestep=self._timestep)
+            self._dr_pool = self._domain_rand.build_pool(self._domain_rand_pool_size)
+        return self._dr_pool
+
     def _get_engine(self):
         if self._engine is None:
             from ..engine import CudaEngine
@@ -303,6 +315,8 @@ class LocoEnv:
             dev = torch.device(self._device)
             self._engine = CudaEngine(modelpack.pack(self._model), self.task_spec().pack(), self.num_envs,
                                       device=dev.index or 0, seed=self._seed, env_id_offset=self._env_id_offset)
+            if self._domain_rand_config is not None:
+                self._engine.set_param_pool(self.domain_randomization_pool())
         return self._engine
 
     # ---------------------------------------------------------------------------------------------------
