@@ -13,7 +13,7 @@ needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="needs the referen
 CONF = {"Default": {"exclude": ["pelvis_tx", "pelvis_tz", "pelvis_ty", "pelvis_tilt", "pelvis_list", "pelvis_rotation"],
                     "Joints": {"damping": {"sigma": 0.0}}},
         "Joints": {"hip_flexion_r": {"damping": {"uniform_range": [1.0, 3.0]}, "armature": {"sigma": 0.002}},
-                   "knee_angle_l": {"frictionloss": {"uniform_range_delta": 0.05}}},
+                   "knee_angle_l": {"damping": {"sigma": 0.1}, "frictionloss": {"sigma": 0.05}}},
         "Inertial": {"l_uleg": {"mass": {"sigma": 0.5}}, "r_foot": {"diaginertia": {"uniform_range_delta": 0.0005}}}}
 
 
@@ -24,7 +24,6 @@ def test_apply_domain_randomization_semantics():
     h = mjcf.XmlHandle(os.path.join(REF, "environments/data/atlas/atlas.xml"))
     np.random.seed(0)
     conf = copy.deepcopy(CONF)
-    conf["Joints"]["knee_angle_l"] = {"damping": {"sigma": 0.1}}
     apply_domain_randomization(h, conf)
     j = h.find("joint", "hip_flexion_r")
     assert 1.0 <= float(j.get("damping")) <= 3.0 and float(j.get("armature")) >= 0.0
