@@ -27,7 +27,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("LOCO_MUJOCO_B200_FORCE_BUNDLED", "1")     # the GPU box has no reference checkout
 
-ALGO_BYTES = {"UnitreeA1": 633}       # fp32 state in/out + action + obs + reward + done, per env-step
+ALGO_BYTES = {"UnitreeA1": 633, "HumanoidTorque": 657, "Atlas": 549, "Talos": 621}
+# DRAM bytes per launch of step_kernel from the last committed `ncu --set full` capture (profiles/README.md), 4096 envs
+NCU_TRAFFIC_BYTES = {"UnitreeA1": 3.83e6}       # fp32 state in/out + action + obs + reward + done, per env-step
 
 
 def parse():
@@ -231,7 +233,7 @@ def main():
                 "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4,
                         "d2h_bytes_per_step": N * (D + 2) * 4},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": which, "algorithmic_bytes_per_env_step": bytes_per,
+                             "traffic": (NCU_TRAFFIC_BYTES.get(robot) if N == 4096 else None), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)", "peak_source": which, "algorithmic_bytes_per_env_step": bytes_per,
                              "note": "compute/latency-bound by design: state stays in shared memory across the 10 "
                                      "sub-steps (DESIGN.md)"},
                 "cpu_baseline": cpu, "resets_in_run": resets, "launch_info": eng.launch_info(),

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * (blockDim.x >> 5) + warp;
   if (env >= n_envs) {
-    if (sync_substeps) for (int k = 0; k < t.n_substeps; k++) __syncthreads();
+    if (sync_substeps) for (int k = 0; k < t.n_substeps; k++) if (k % sync_substeps == 0) __syncthreads();
     return;
   }
   EnvS<C>& e = reinterpret_cast<EnvS<C>*>(smem_raw)[warp];
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
   // ---- physics ----
   if (sync_substeps) {
     // keep the warps of a block in the same phase: they then share instruction-cache lines
-    for (int k = 0; k < t.n_substeps; k++) { __syncthreads(); physics_substeps(ms, e, so, 1); }
+    for (int k = 0; k < t.n_substeps; k++) { if (k % sync_substeps == 0) __syncthreads(); physics_substeps(ms, e, so, 1); }
   } else {
     physics_substeps(ms, e, so, t.n_substeps);
   }
