@@ -414,10 +414,19 @@ int locosim_set_param_pool(locosim_t* h, const double* pool, int n_rows, int row
   CK(cudaDeviceSynchronize());
   cudaFree(h->d_pool);
   h->d_pool = d_new; h->st.pool = d_new; h->st.pool_K = n_rows;
-  if (damp && !h->dm.has_damping) {
-    h->dm.has_damping = 1;
-    CK(cudaMemcpyToSymbol(c_models, &h->dm, sizeof(DevModel), sizeof(DevModel) * h->slot));
+  // a dof gets a (static) frictionloss row as soon as ANY pool row gives it a positive frictionloss; in rows where
+  // its value is 0 the constraint row is inert (force interval [-0, 0])
+  std::vector<int> frow(h->hm.nv, -1);
+  int nfric = 0;
+  for (int d = 0; d < h->hm.nv; d++) {
+    bool any = h->hm.default_row[h->hm.po[1] + d] > 0;
+    for (int r = 0; r < n_rows && !any; r++) any = f[(size_t)r * row_len + h->hm.po[1] + d] > 0;
+    if (any) frow[d] = nfric++;
   }
+  CK(cudaMemcpy((void*)h->dm.dof_frow, frow.data(), frow.size() * 4, cudaMemcpyHostToDevice));
+  h->dm.nfric = nfric;
+  if (damp) h->dm.has_damping = 1;
+  CK(cudaMemcpyToSymbol(c_models, &h->dm, sizeof(DevModel), sizeof(DevModel) * h->slot));
   CK(cudaMemset(h->st.dr_row, 0, (size_t)h->n_envs * 4));
   return 0;
 }

@@ -36,3 +36,24 @@ def reference_draws(env, seed=0):
     traj_no = np.random.randint(0, env.trajectories.number_of_trajectories)
     step_no = np.random.randint(0, env.trajectories.trajectory_length)
     return traj_no, step_no
+
+
+def oracle_step_sensitivity(oracle, model_blobs, task_blobs, traj_no, step_no, qpos, qvel, action, ref_obs,
+                            eps=1e-6, n_probe=4, seed=0):
+    """How far the ORACLE's own one-step result moves when its start state is perturbed by `eps` (fp32 resolution).
+
+    A control step is discontinuous where a contact or a joint limit switches on (trajectory samples clipped onto a
+    joint limit sit exactly on such a switch); there an fp32 engine and an fp64 oracle may legitimately take different
+    branches. Tests use this to tell such a state from a real mismatch: the fp32 error must not exceed what a
+    1e-6 perturbation does to the fp64 result.
+    """
+    rng = np.random.RandomState(seed)
+    gap = 0.0
+    for _ in range(n_probe):
+        oe = oracle.env(model_blobs, task_blobs)
+        oe.reset_to(int(traj_no), int(step_no))
+        oe.set_state(qpos + eps * rng.randn(len(qpos)), qvel + eps * rng.randn(len(qvel)))
+        o, _, _ = oe.step(np.asarray(action, dtype=np.float64))
+        gap = max(gap, float(np.abs(o - ref_obs).max()))
+        oe.close()
+    return gap
