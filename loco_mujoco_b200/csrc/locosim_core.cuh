@@ -371,24 +371,43 @@ LS_FN void com_pos(const int ms, EnvS<C>& e) {
 // ----------------------------------------------------------------------------------------------------------
 template <int NV, int NVP>
 LS_FN void chol_factor(const int ms, float (*A)[NVP]) {
+#ifdef LS_EMULATE
   const DevModel& m = c_models[ms];
-  NOUNROLL for (int j = 0; j < NV; j++) {
+  for (int j = 0; j < NV; j++) {
     const float inv = rsqrtf(fmaxf(A[j][j], 1e-12f));
-    SYNC();
-    PAR_FOR(ii, NV - j) { A[j + ii][j] = (ii == 0) ? inv : A[j + ii][j] * inv; }
-    SYNC();
-    // trailing update of the lower triangle of rows/cols (j, NV): the first nrem(nrem+1)/2 entries of the
-    // row-major triangular enumeration (m.tri_ij) are exactly the entries (a, b), b <= a < nrem
-    const int nrem = NV - j - 1;
-    PAR_FOR(t, nrem * (nrem + 1) / 2) {
-      const int ab = m.tri_ij[t];
-      const int i = j + 1 + (ab >> 8), k = j + 1 + (ab & 255);
-      A[i][k] = fmaf(-A[i][j], A[k][j], A[i][k]);
-    }
-    SYNC();
+    for (int ii = 0; ii < NV - j; ii++) A[j + ii][j] = (ii == 0) ? inv : A[j + ii][j] * inv;
+    for (int i = j + 1; i < NV; i++)
+      for (int k = j + 1; k <= i; k++) A[i][k] = fmaf(-A[i][j], A[k][j], A[i][k]);
   }
+  (void)m;
+#else
+  // Lane i keeps row i in registers; column j of the factor is broadcast lane-to-lane with shuffles
+  // (right-looking, ~2 instructions per updated entry, no shared-memory round trips inside the loop).
+  // One __noinline__ copy per NV serves M, the Newton Hessian and the implicit-damping matrix.
+  const int lane = LS_LANE, li = lane < NV ? lane : NV - 1;
+  float a[NV], inv = 1.0f;
+#pragma unroll
+  for (int j = 0; j < NV; j++) a[j] = A[li][j];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    const float r = rsqrtf(fmaxf(__shfl_sync(0xffffffffu, a[j], j), 1e-12f));
+    if (lane == j) inv = r;
+    a[j] *= r;
+#pragma unroll
+    for (int k = j + 1; k < NV; k++) a[k] = fmaf(-a[j], __shfl_sync(0xffffffffu, a[j], k), a[k]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < NV; j++)
+    if (j <= lane && lane < NV) A[lane][j] = (j == lane) ? inv : a[j];
+  __syncwarp();
+  (void)ms;
+#endif
 }
 // solve L L^T x = b in place (x: shared memory vector of length >= NV, padded entries finite)
+#ifndef LS_SOLVE_UNROLL
+#define LS_SOLVE_UNROLL _Pragma("unroll")
+#endif
 template <int NV, int NVP>
 LS_FN void chol_solve(float (*L)[NVP], float* xs) {
 #ifdef LS_EMULATE
@@ -406,13 +425,13 @@ LS_FN void chol_solve(float (*L)[NVP], float* xs) {
   const int lane = LS_LANE, li = lane < NV ? lane : NV - 1;
   float x = lane < NV ? xs[lane] : 0.0f;
   const float inv = L[li][li];
-  NOUNROLL for (int j = 0; j < NV; j++) {
+  LS_SOLVE_UNROLL for (int j = 0; j < NV; j++) {
     const float t = x * inv;
     const float yj = __shfl_sync(0xffffffffu, t, j);
     const float lij = L[li][j];
     x = (lane == j) ? t : ((lane > j) ? fmaf(-lij, yj, x) : x);
   }
-  NOUNROLL for (int j = NV - 1; j >= 0; j--) {
+  LS_SOLVE_UNROLL for (int j = NV - 1; j >= 0; j--) {
     const float t = x * inv;
     const float xj = __shfl_sync(0xffffffffu, t, j);
     const float lji = L[j][li];
@@ -1409,15 +1428,19 @@ LS_FN float line_search(const int ms, EnvS<C>& e, const SolverOpts so, float gau
   return best.alpha;
 }
 
+// gradient of the cost at qacc (mj_solNewton: grad = M qacc - qfrc_smooth - J^T force); returns |grad|^2
 template <class C>
-LS_FN void update_gradient(const int ms, EnvS<C>& e) {
+LS_FN float update_gradient(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
+  float gn = 0;
   PAR_FOR(i, EnvS<C>::NV) {
     float g = i < m.nv ? e.Ma[i] - e.qfrc_smooth[i] - e.qfrc_constraint[i] : 0.0f;
     e.grad[i] = g; e.Mgrad[i] = g;
+    gn += g * g;
   }
+  gn = WARP_SUM(gn);
   SYNC();
-  chol_solve<EnvS<C>::NV, EnvS<C>::NVP>(e.H, e.Mgrad);
+  return gn;
 }
 
 template <class C>
@@ -1458,34 +1481,34 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
   }
   SYNC();
   // ---- Newton iterations ----
-  float scale = 1.0f / (PRM(meaninertia)[0] * (nv > 1 ? nv : 1));
+  // Order differs from mj_solNewton in one respect: the convergence test comes BEFORE the Hessian of the new point is
+  // assembled and factored, so the last iteration's factorisation (never used) is not computed.
+  // fp32 termination: scaled gradient below tolerance, or a Newton step with exact line search that did not lower the
+  // cost any more (the cost value has reached its fp32 resolution; further iterations only move noise).
+  const float scale = 1.0f / (PRM(meaninertia)[0] * (nv > 1 ? nv : 1));
   float gauss;
   float cost = update_constraint(ms, e, &gauss);
-  make_hessian(ms, e);
-  update_gradient(ms, e);
-  PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
-  SYNC();
+  float gn = update_gradient(ms, e);
   int iter = 0;
-  while (iter < so.max_iter) {
+  while (iter < so.max_iter && scale * sqrtf(gn) >= so.tolerance) {
+    make_hessian(ms, e);
+    chol_solve<EnvS<C>::NV, EnvS<C>::NVP>(e.H, e.Mgrad);
+    PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
+    SYNC();
     float alpha = line_search(ms, e, so, gauss, scale);
     if (alpha == 0) break;
     PAR_FOR(i, nv) { e.qacc[i] += alpha * e.search[i]; e.Ma[i] += alpha * e.Mv[i]; }
     PAR_FOR(r, nefc) e.r_jar[r] += alpha * e.r_Jv[r];
     SYNC();
-    float oldcost = cost;
+    const float oldcost = cost;
     cost = update_constraint(ms, e, &gauss);
-    make_hessian(ms, e);
-    update_gradient(ms, e);
-    float gn = 0;
-    PAR_FOR(i, nv) gn += e.grad[i] * e.grad[i];
-    gn = WARP_SUM(gn);
-    float improvement = scale * (oldcost - cost);
-    float gradient = scale * sqrtf(gn);
+    gn = update_gradient(ms, e);
     iter++;
-    (void)improvement;
-    if (gradient < so.tolerance) break;
-    PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
-    SYNC();
+#if defined(LS_EMULATE) && defined(LS_TRACE)
+    printf("  it %2d alpha %.3e cost %.9e impr %.3e grad %.3e nefc %d\n", iter, alpha, cost, scale * (oldcost - cost),
+           scale * sqrtf(gn), nefc);
+#endif
+    if (!(cost < oldcost)) break;
   }
   LANE0 { e.solver_iter = iter; }
   PAR_FOR(i, nv) e.qacc_ws[i] = e.qacc[i];

@@ -3,4 +3,4 @@
 set -e
 cd "$(dirname "$0")/.."
 mkdir -p scratch
-g++ -O2 -fPIC -shared -std=c++17 -Wall -Wno-unused-function -Wno-unused-variable -o scratch/liblocosim_emu.so loco_mujoco_b200/csrc/locosim_emu.cpp -lm
+g++ -O2 -fPIC -shared -std=c++17 -Wall -Wno-unused-function -Wno-unused-variable -Wno-unknown-pragmas -o scratch/liblocosim_emu.so loco_mujoco_b200/csrc/locosim_emu.cpp -lm
