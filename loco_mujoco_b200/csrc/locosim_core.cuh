@@ -29,6 +29,7 @@
 #define WARP_MIN(x) (x)
 #define LANE0
 #define LS_LANE 0
+#define BLOCK_ANY(flag, pred) (pred)
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #else
 #define LS_DEV __device__ __forceinline__
@@ -38,6 +39,8 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define WARP_SUM(x) warp_sum(x)
 #define LANE0 if ((threadIdx.x & 31) == 0)
 #define LS_LANE ((int)(threadIdx.x & 31))
+// block-wide OR that doubles as a barrier: keeps the warps of a block in the same solver iteration (flag = 0: plain predicate)
+#define BLOCK_ANY(flag, pred) ((flag) ? (__syncthreads_or((pred) ? 1 : 0) != 0) : (pred))
 LS_DEV float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -97,6 +100,7 @@ struct SolverOpts {
   float ls_tolerance;  // relative line-search gradient tolerance
   int max_iter;        // Newton iterations cap
   int ls_iter;         // line-search evaluations cap
+  int sync_iters;      // 1: the warps of a block run the Newton iterations in lock-step (instruction-cache sharing)
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -1447,56 +1451,57 @@ template <class C>
 LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
   const DevModel& m = c_models[ms];
   const int nv = m.nv, nefc = e.nefc;
+  const float scale = 1.0f / (PRM(meaninertia)[0] * (nv > 1 ? nv : 1));
+  float gauss = 0, cost = 0, gn = 0;
+  int iter = 0;
   if (nefc == 0) {
-    PAR_FOR(i, nv) { e.qacc[i] = e.qacc_smooth[i]; e.qacc_ws[i] = e.qacc_smooth[i]; e.qfrc_constraint[i] = 0; }
-    LANE0 { e.solver_iter = 0; }
+    PAR_FOR(i, nv) { e.qacc[i] = e.qacc_smooth[i]; e.qfrc_constraint[i] = 0; }
     SYNC();
-    return;
-  }
-  // ---- warmstart choice ----
-  PAR_FOR(i, nv) e.qacc[i] = e.qacc_ws[i];
-  SYNC();
-  mulM(ms, e, e.Ma, e.qacc);
-  mulJ(ms, e, e.r_jar, e.qacc);
-  SYNC();
-  PAR_FOR(r, nefc) e.r_jar[r] -= e.r_aref[r];
-  SYNC();
-  float cw = constraint_update(ms, e);
-  float g = 0;
-  PAR_FOR(i, nv) g += 0.5f * (e.Ma[i] - e.qfrc_smooth[i]) * (e.qacc[i] - e.qacc_smooth[i]);
-  cw += WARP_SUM(g);
-  SYNC();
-  mulJ(ms, e, e.r_Jv, e.qacc_smooth);   // r_Jv used as scratch for J*qacc_smooth
-  SYNC();
-  // cost at qacc_smooth: swap in jar = J qacc_smooth - aref
-  PAR_FOR(r, nefc) { float t = e.r_jar[r]; e.r_jar[r] = e.r_Jv[r] - e.r_aref[r]; e.r_Jv[r] = t; }
-  SYNC();
-  float cs = constraint_update(ms, e);
-  if (cw > cs) {
-    PAR_FOR(i, nv) e.qacc[i] = e.qacc_smooth[i];
+  } else {
+    // ---- warmstart choice ----
+    PAR_FOR(i, nv) e.qacc[i] = e.qacc_ws[i];
     SYNC();
     mulM(ms, e, e.Ma, e.qacc);
-  } else {
-    PAR_FOR(r, nefc) e.r_jar[r] = e.r_Jv[r];
+    mulJ(ms, e, e.r_jar, e.qacc);
+    SYNC();
+    PAR_FOR(r, nefc) e.r_jar[r] -= e.r_aref[r];
+    SYNC();
+    float cw = constraint_update(ms, e);
+    float g = 0;
+    PAR_FOR(i, nv) g += 0.5f * (e.Ma[i] - e.qfrc_smooth[i]) * (e.qacc[i] - e.qacc_smooth[i]);
+    cw += WARP_SUM(g);
+    SYNC();
+    mulJ(ms, e, e.r_Jv, e.qacc_smooth);   // r_Jv used as scratch for J*qacc_smooth
+    SYNC();
+    // cost at qacc_smooth: swap in jar = J qacc_smooth - aref
+    PAR_FOR(r, nefc) { float t = e.r_jar[r]; e.r_jar[r] = e.r_Jv[r] - e.r_aref[r]; e.r_Jv[r] = t; }
+    SYNC();
+    float cs = constraint_update(ms, e);
+    if (cw > cs) {
+      PAR_FOR(i, nv) e.qacc[i] = e.qacc_smooth[i];
+      SYNC();
+      mulM(ms, e, e.Ma, e.qacc);
+    } else {
+      PAR_FOR(r, nefc) e.r_jar[r] = e.r_Jv[r];
+    }
+    SYNC();
+    cost = update_constraint(ms, e, &gauss);
+    gn = update_gradient(ms, e);
   }
-  SYNC();
   // ---- Newton iterations ----
   // Order differs from mj_solNewton in one respect: the convergence test comes BEFORE the Hessian of the new point is
   // assembled and factored, so the last iteration's factorisation (never used) is not computed.
   // fp32 termination: scaled gradient below tolerance, or a Newton step with exact line search that did not lower the
   // cost any more (the cost value has reached its fp32 resolution; further iterations only move noise).
-  const float scale = 1.0f / (PRM(meaninertia)[0] * (nv > 1 ? nv : 1));
-  float gauss;
-  float cost = update_constraint(ms, e, &gauss);
-  float gn = update_gradient(ms, e);
-  int iter = 0;
-  while (iter < so.max_iter && scale * sqrtf(gn) >= so.tolerance) {
+  bool active = nefc > 0 && so.max_iter > 0 && scale * sqrtf(gn) >= so.tolerance;
+  while (BLOCK_ANY(so.sync_iters, active)) {
+    if (!active) continue;
     make_hessian(ms, e);
     chol_solve<EnvS<C>::NV, EnvS<C>::NVP>(e.H, e.Mgrad);
     PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
     SYNC();
-    float alpha = line_search(ms, e, so, gauss, scale);
-    if (alpha == 0) break;
+    const float alpha = line_search(ms, e, so, gauss, scale);
+    if (alpha == 0) { active = false; continue; }
     PAR_FOR(i, nv) { e.qacc[i] += alpha * e.search[i]; e.Ma[i] += alpha * e.Mv[i]; }
     PAR_FOR(r, nefc) e.r_jar[r] += alpha * e.r_Jv[r];
     SYNC();
@@ -1508,7 +1513,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
     printf("  it %2d alpha %.3e cost %.9e impr %.3e grad %.3e nefc %d\n", iter, alpha, cost, scale * (oldcost - cost),
            scale * sqrtf(gn), nefc);
 #endif
-    if (!(cost < oldcost)) break;
+    active = iter < so.max_iter && scale * sqrtf(gn) >= so.tolerance && cost < oldcost;
   }
   LANE0 { e.solver_iter = iter; }
   PAR_FOR(i, nv) e.qacc_ws[i] = e.qacc[i];
