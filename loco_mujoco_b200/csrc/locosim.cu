@@ -261,6 +261,9 @@ static int setup_cfg(locosim_handle* h) {
   if (getenv("LOCOSIM_SYNC")) h->sync_substeps = atoi(getenv("LOCOSIM_SYNC"));
   h->so.sync_iters = 1;
   if (getenv("LOCOSIM_SYNC_ITERS")) h->so.sync_iters = atoi(getenv("LOCOSIM_SYNC_ITERS"));
+  h->so.sync_phases = 32;   // one more barrier where the warps enter the solver (measured +2%)
+  if (getenv("LOCOSIM_SYNC_PHASES")) h->so.sync_phases = atoi(getenv("LOCOSIM_SYNC_PHASES"));
+  if (!h->so.sync_iters) h->so.sync_phases &= 63;   // barriers inside the Newton loop need lock-step iterations
   h->wpb = best;
   h->smem = best * per_env;
   CK(cudaFuncSetAttribute(step_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));

@@ -30,6 +30,7 @@
 #define LANE0
 #define LS_LANE 0
 #define BLOCK_ANY(flag, pred) (pred)
+#define BLOCK_SYNC(flag) ((void)0)
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #else
 #define LS_DEV __device__ __forceinline__
@@ -41,6 +42,7 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define LS_LANE ((int)(threadIdx.x & 31))
 // block-wide OR that doubles as a barrier: keeps the warps of a block in the same solver iteration (flag = 0: plain predicate)
 #define BLOCK_ANY(flag, pred) ((flag) ? (__syncthreads_or((pred) ? 1 : 0) != 0) : (pred))
+#define BLOCK_SYNC(flag) do { if (flag) __syncthreads(); } while (0)
 LS_DEV float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -101,6 +103,7 @@ struct SolverOpts {
   int max_iter;        // Newton iterations cap
   int ls_iter;         // line-search evaluations cap
   int sync_iters;      // 1: the warps of a block run the Newton iterations in lock-step (instruction-cache sharing)
+  int sync_phases;     // bit mask of extra block barriers at phase boundaries of forward()
 };
 
 // ----------------------------------------------------------------------------------------------------------
@@ -1321,6 +1324,32 @@ LS_FN void make_hessian(const int ms, EnvS<C>& e) {
 
 struct LSPoint { float alpha, cost, d1, d2; };
 
+// Per line search: for every elliptic contact the alpha-independent sums of the cone coordinates
+// (UU, UV, VV -> r_aref[r..r+2]) and the coefficients of its bottom-zone quadratic qc(alpha) = c0 + c1 alpha + c2 alpha^2
+// (-> r_force[r..r+2]).  r_aref is dead once jar has been formed and r_force is rewritten by the update_constraint that
+// follows every line search (elliptic contacts have dim >= 3 rows, so the three slots per array exist).
+template <class C>
+LS_FN void ls_prepare(const int ms, EnvS<C>& e) {
+  const int nefc = e.nefc;
+  PAR_FOR(r, nefc) {
+    const int ti = e.r_ti[r];
+    if (ROW_TYPE(ti) != ROW_CON_ELLIPTIC || ROW_K(ti) != 0) continue;
+    const int ci = ROW_ID(ti), dim = e.con_dim[ci];
+    float ja = e.r_jar[r], jv = e.r_Jv[r], D = e.r_D[r];
+    float UU = 0, UV = 0, VV = 0, c0 = 0.5f * D * ja * ja, c1 = D * ja * jv, c2 = 0.5f * D * jv * jv;
+    NOUNROLL for (int j = 1; j < dim; j++) {
+      const float fr = e.con_fri[ci][j - 1];
+      const float aj = e.r_jar[r + j], vj = e.r_Jv[r + j], Dj = e.r_D[r + j];
+      const float u = aj * fr, v = vj * fr;
+      UU += u * u; UV += u * v; VV += v * v;
+      c0 += 0.5f * Dj * aj * aj; c1 += Dj * aj * vj; c2 += 0.5f * Dj * vj * vj;
+    }
+    e.r_aref[r] = UU; e.r_aref[r + 1] = UV; e.r_aref[r + 2] = VV;
+    e.r_force[r] = c0; e.r_force[r + 1] = c1; e.r_force[r + 2] = c2;
+  }
+  SYNC();
+}
+
 template <class C>
 LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alpha) {
   const DevModel& m = c_models[ms];
@@ -1338,18 +1367,12 @@ LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alp
       else { c += 0.5f * D * x * x; d1 += D * x * jv; d2 += D * jv * jv; }
     } else if (tp == ROW_CON_ELLIPTIC) {
       if (ROW_K(ti) != 0) continue;
-      int ci = ROW_ID(ti), dim = e.con_dim[ci];
-      float mu = e.con_mu[ci];
-      float U0 = ja * mu, V0 = jv * mu, UU = 0, UV = 0, VV = 0;
-      float qc = 0.5f * D * x * x, q1 = D * x * jv, q2 = D * jv * jv;   // quadratic (bottom zone) pieces
-      NOUNROLL for (int j = 1; j < dim; j++) {
-        float fr = e.con_fri[ci][j - 1];
-        float aj = e.r_jar[r + j], vj = e.r_Jv[r + j], Dj = e.r_D[r + j];
-        float u = aj * fr, v = vj * fr;
-        UU += u * u; UV += u * v; VV += v * v;
-        float xj = aj + alpha * vj;
-        qc += 0.5f * Dj * xj * xj; q1 += Dj * xj * vj; q2 += Dj * vj * vj;
-      }
+      // alpha-independent sums over the contact's rows were prepared once per line search (ls_prepare)
+      const int ci = ROW_ID(ti);
+      const float mu = e.con_mu[ci];
+      const float U0 = ja * mu, V0 = jv * mu, UU = e.r_aref[r], UV = e.r_aref[r + 1], VV = e.r_aref[r + 2];
+      const float c1 = e.r_force[r + 1], c2 = e.r_force[r + 2];
+      const float qc = e.r_force[r] + alpha * (c1 + alpha * c2), q1 = c1 + 2 * alpha * c2, q2 = 2 * c2;
       float N = U0 + alpha * V0;
       float Tsqr = UU + alpha * (2 * UV + alpha * VV);
       if (Tsqr <= 0) {
@@ -1400,6 +1423,7 @@ LS_FN float line_search(const int ms, EnvS<C>& e, const SolverOpts so, float gau
   if (snorm < LS_MINVAL) return 0;
   float gtol = so.tolerance * so.ls_tolerance * snorm / scale;
   float qg[3] = {gauss, q1, q2};
+  if (C::CONE == 1) ls_prepare(ms, e);
   LSPoint p0 = ls_eval(ms, e, qg, 0.0f);
   LSPoint p1 = ls_eval(ms, e, qg, p0.alpha - p0.d1 / p0.d2);
   if (p0.cost < p1.cost) p1 = p0;
@@ -1495,25 +1519,32 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
   // cost any more (the cost value has reached its fp32 resolution; further iterations only move noise).
   bool active = nefc > 0 && so.max_iter > 0 && scale * sqrtf(gn) >= so.tolerance;
   while (BLOCK_ANY(so.sync_iters, active)) {
-    if (!active) continue;
-    make_hessian(ms, e);
-    chol_solve<EnvS<C>::NV, EnvS<C>::NVP>(e.H, e.Mgrad);
-    PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
-    SYNC();
-    const float alpha = line_search(ms, e, so, gauss, scale);
-    if (alpha == 0) { active = false; continue; }
-    PAR_FOR(i, nv) { e.qacc[i] += alpha * e.search[i]; e.Ma[i] += alpha * e.Mv[i]; }
-    PAR_FOR(r, nefc) e.r_jar[r] += alpha * e.r_Jv[r];
-    SYNC();
-    const float oldcost = cost;
-    cost = update_constraint(ms, e, &gauss);
-    gn = update_gradient(ms, e);
-    iter++;
+    // (warps whose env has converged keep passing the same barriers until the whole block is done)
+    if (active) make_hessian(ms, e);
+    BLOCK_SYNC(so.sync_phases & 64);
+    float alpha = 0;
+    if (active) {
+      chol_solve<EnvS<C>::NV, EnvS<C>::NVP>(e.H, e.Mgrad);
+      PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
+      SYNC();
+      alpha = line_search(ms, e, so, gauss, scale);
+      if (alpha == 0) active = false;
+    }
+    BLOCK_SYNC(so.sync_phases & 128);
+    if (active) {
+      PAR_FOR(i, nv) { e.qacc[i] += alpha * e.search[i]; e.Ma[i] += alpha * e.Mv[i]; }
+      PAR_FOR(r, nefc) e.r_jar[r] += alpha * e.r_Jv[r];
+      SYNC();
+      const float oldcost = cost;
+      cost = update_constraint(ms, e, &gauss);
+      gn = update_gradient(ms, e);
+      iter++;
 #if defined(LS_EMULATE) && defined(LS_TRACE)
-    printf("  it %2d alpha %.3e cost %.9e impr %.3e grad %.3e nefc %d\n", iter, alpha, cost, scale * (oldcost - cost),
-           scale * sqrtf(gn), nefc);
+      printf("  it %2d alpha %.3e cost %.9e impr %.3e grad %.3e nefc %d\n", iter, alpha, cost, scale * (oldcost - cost),
+             scale * sqrtf(gn), nefc);
 #endif
-    active = iter < so.max_iter && scale * sqrtf(gn) >= so.tolerance && cost < oldcost;
+      active = iter < so.max_iter && scale * sqrtf(gn) >= so.tolerance && cost < oldcost;
+    }
   }
   LANE0 { e.solver_iter = iter; }
   PAR_FOR(i, nv) e.qacc_ws[i] = e.qacc[i];
@@ -1526,12 +1557,18 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
 template <class C>
 LS_FN void forward(const int ms, EnvS<C>& e, const SolverOpts so) {
   const DevModel& m = c_models[ms];
+  BLOCK_SYNC(so.sync_phases & 1);
   kinematics(ms, e);
+  BLOCK_SYNC(so.sync_phases & 2);
   com_pos(ms, e);
   crb_factor(ms, e);
+  BLOCK_SYNC(so.sync_phases & 4);
   smooth_forces(ms, e);        // last user of the smooth-dynamics scratch that the constraint rows overlay
+  BLOCK_SYNC(so.sync_phases & 8);
   collision(ms, e);
+  BLOCK_SYNC(so.sync_phases & 16);
   make_constraint(ms, e);
+  BLOCK_SYNC(so.sync_phases & 32);
   fwd_constraint(ms, e, so);
 }
 

@@ -2,10 +2,11 @@ from .base import LocoEnv, ValidTaskConf, ObservationType
 from .unitree_a1 import UnitreeA1
 
 UnitreeA1.register()
-from .robot_humanoids import Atlas, Talos
+from .robot_humanoids import Atlas, Talos, UnitreeH1
 
 Atlas.register()
 Talos.register()
+UnitreeH1.register()
 from .humanoids import HumanoidTorque
 
 HumanoidTorque.register()

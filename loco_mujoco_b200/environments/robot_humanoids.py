@@ -1,8 +1,8 @@
 """
-Atlas and Talos (walk task, real dataset) on the batched CUDA engine.
+Atlas, Talos (walk) and UnitreeH1 (walk, run), real datasets, on the batched CUDA engine.
 Mirrors /root/reference/loco_mujoco/environments/humanoids/base_robot_humanoid.py:12-260 (generate, dataset keys),
-atlas.py:275-453,485-598 and talos.py:266-466,523-640 (joint/motor removal, observation/action specification,
-_has_fallen windows).
+atlas.py:275-453,485-598, talos.py:266-466,523-640 and unitreeH1.py:235-296,319-384,447-553 (joint/motor removal,
+observation/action specification, _has_fallen windows).
 """
 import os
 import warnings
@@ -62,10 +62,10 @@ class BaseRobotHumanoid(LocoEnv):
         check_validity_task_mode_dataset(cls.__name__, task, None, dataset_type, *cls.valid_task_confs.get_all())
         if dataset_type != "real":
             raise NotImplementedError("perfect datasets are not shipped (network download in the reference)")
-        if task != "walk":
+        if task not in ("walk", "run"):
             raise NotImplementedError("task %r is not built yet" % task)
         reward_type = kwargs.pop("reward_type", "target_velocity")
-        reward_params = kwargs.pop("reward_params", dict(target_velocity=1.25))
+        reward_params = kwargs.pop("reward_params", dict(target_velocity=2.5 if task == "run" else 1.25))
         root = reference_data_root()
         if root is not None:
             mdp = cls(reward_type=reward_type, reward_params=reward_params, **kwargs)
@@ -172,3 +172,54 @@ class Talos(BaseRobotHumanoid):
 
 
 _TALOS_ARM_QUATS = {"arm_right_4_link": [1.0, 0.0, -0.25, 0.0], "arm_left_4_link": [1.0, 0.0, -0.25, 0.0]}
+
+
+_H1_ARMS = ["l_arm_shy", "l_arm_shx", "l_arm_shz", "left_elbow", "r_arm_shy", "r_arm_shx", "r_arm_shz", "right_elbow"]
+_H1_ARM_QUATS = {"left_shoulder_pitch_link": [1.0, 0.25, 0.1, 0.0], "right_elbow_link": [1.0, 0.0, 0.25, 0.0],
+                 "right_shoulder_pitch_link": [1.0, -0.25, 0.1, 0.0], "left_elbow_link": [1.0, 0.0, 0.25, 0.0]}
+
+
+class UnitreeH1(BaseRobotHumanoid):
+    """Unitree H1 (unitreeH1.py). Default: arms fixed in a reoriented pose, back joint active: 17 dofs, 11 motors."""
+    valid_task_confs = ValidTaskConf(tasks=["walk", "run", "carry"], data_types=["real", "perfect"])
+    _xml_rel = ("unitree_h1", "h1.xml")
+
+    def __init__(self, disable_arms=True, disable_back_joint=False, hold_weight=False, weight_mass=None, **kwargs):
+        super().__init__(disable_arms=disable_arms, disable_back_joint=disable_back_joint, hold_weight=hold_weight,
+                         weight_mass=weight_mass, **kwargs)
+
+    def _modify_xml(self, xml_handle):
+        if self._disable_arms:
+            for name, quat in _H1_ARM_QUATS.items():       # unitreeH1.py:447-468
+                xml_handle.find("body", name).set("quat", " ".join(repr(float(x)) for x in quat))
+        return xml_handle
+
+    def _get_xml_modifications(self):
+        joints, motors = [], []
+        if self._disable_arms:
+            joints += _H1_ARMS
+            motors += [j + "_actuator" for j in _H1_ARMS]
+        if self._disable_back_joint:
+            joints += ["back_bkz"]
+            motors += ["back_bkz_actuator"]
+        return joints, motors, []
+
+    def _has_fallen_terms(self):
+        # unitreeH1.py:362-370: the rotation window is +-pi/8 (Atlas/Talos use +-pi/10)
+        return [("q_pelvis_ty", -0.3, 0.1), ("q_pelvis_tilt", -np.pi / 4.5, np.pi / 12),
+                ("q_pelvis_list", -np.pi / 12, np.pi / 8), ("q_pelvis_rotation", -np.pi / 8, np.pi / 8)]
+
+    @staticmethod
+    def _get_observation_specification():
+        joints = _PELVIS + ["back_bkz"] + _H1_ARMS + _LEGS
+        return [("q_" + j, j, ObservationType.JOINT_POS) for j in joints] + \
+               [("dq_" + j, j, ObservationType.JOINT_VEL) for j in joints]
+
+    @staticmethod
+    def _get_action_specification():
+        return ["back_bkz_actuator"] + [j + "_actuator" for j in _H1_ARMS] + [j + "_actuator" for j in _LEGS]
+
+    @staticmethod
+    def generate(task="walk", dataset_type="real", **kwargs):
+        stub = "05-run_UnitreeH1.npz" if task == "run" else "02-constspeed_UnitreeH1.npz"
+        return UnitreeH1._generate(stub, task, dataset_type, clip_trajectory_to_joint_ranges=True, **kwargs)

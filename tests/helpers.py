@@ -5,13 +5,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-GOLDEN_TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "HumanoidTorque.walk", "Atlas.walk", "Talos.walk"]
+GOLDEN_TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "HumanoidTorque.walk", "Atlas.walk", "Talos.walk",
+                "UnitreeH1.run"]
 
 
 # HumanoidTorque.walk: from row 20 on the reference rollout contains a convex mesh-mesh self-contact (fixed arm/hand
 # bones against the leg, mjc_Convex / libccd MPR in MuJoCo) that the engines do not implement yet (DESIGN.md "gaps");
 # rows 0..19 (190 RK4 steps = 760 dynamics evaluations) are pinned.
-PINNED_ROWS = {"HumanoidTorque.walk": 20}
+# UnitreeH1: the feet are convex MESHES; MuJoCo's plane-mesh routine picks its (up to 3) contact vertices by walking the
+# qhull vertex graph of the mesh from the support vertex, an order that cannot be reproduced without MuJoCo's own qhull
+# run (the sole has ~30 exactly coplanar hull vertices). The engines use the deepest-vertices rule instead, so only the
+# rows before the first foot strike of the golden (10 rows = 90 steps of free flight incl. joint limits) are pinned.
+PINNED_ROWS = {"HumanoidTorque.walk": 20, "UnitreeH1.run": 10}
 
 
 def golden(task):
