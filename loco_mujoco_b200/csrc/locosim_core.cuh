@@ -372,21 +372,22 @@ LS_FN void com_pos(const int ms, EnvS<C>& e) {
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// dense SPD solves on identity-padded NV x NV matrices in shared memory (lower triangle, row stride NVP).
-// The factor stores 1/L_ii on the diagonal.  All loops are ROLLED on purpose: the first ncu captures showed this
-// kernel limited by instruction fetch, so the hot solver loop has to stay inside the SM's instruction cache.
+// dense SPD solves on identity-padded NV x NV matrices in shared memory (row stride NVP = NV + 1).
+// Factor layout (chosen so that the triangular solves need no lane predicates): A[i][j] = L_ij for j < i,
+// A[i][j] = 0 for NV > j >= i, and the padding column holds the inverse diagonal, A[i][NV] = 1 / L_ii.
 // ----------------------------------------------------------------------------------------------------------
 template <int NV, int NVP>
 LS_FN void chol_factor(const int ms, float (*A)[NVP]) {
 #ifdef LS_EMULATE
-  const DevModel& m = c_models[ms];
   for (int j = 0; j < NV; j++) {
     const float inv = rsqrtf(fmaxf(A[j][j], 1e-12f));
-    for (int ii = 0; ii < NV - j; ii++) A[j + ii][j] = (ii == 0) ? inv : A[j + ii][j] * inv;
+    A[j][NV] = inv;
+    for (int i = j + 1; i < NV; i++) A[i][j] *= inv;
     for (int i = j + 1; i < NV; i++)
       for (int k = j + 1; k <= i; k++) A[i][k] = fmaf(-A[i][j], A[k][j], A[i][k]);
   }
-  (void)m;
+  for (int i = 0; i < NV; i++) for (int j = i; j < NV; j++) A[i][j] = 0.0f;
+  (void)ms;
 #else
   // Lane i keeps row i in registers; column j of the factor is broadcast lane-to-lane with shuffles
   // (right-looking, ~2 instructions per updated entry, no shared-memory round trips inside the loop).
@@ -404,46 +405,40 @@ LS_FN void chol_factor(const int ms, float (*A)[NVP]) {
     for (int k = j + 1; k < NV; k++) a[k] = fmaf(-a[j], __shfl_sync(0xffffffffu, a[j], k), a[k]);
   }
   __syncwarp();
+  if (lane < NV) {
 #pragma unroll
-  for (int j = 0; j < NV; j++)
-    if (j <= lane && lane < NV) A[lane][j] = (j == lane) ? inv : a[j];
+    for (int j = 0; j < NV; j++) A[lane][j] = (j < lane) ? a[j] : 0.0f;
+    A[lane][NV] = inv;
+  }
   __syncwarp();
   (void)ms;
 #endif
 }
 // solve L L^T x = b in place (x: shared memory vector of length >= NV, padded entries finite)
-#ifndef LS_SOLVE_UNROLL
-#define LS_SOLVE_UNROLL _Pragma("unroll")
-#endif
 template <int NV, int NVP>
 LS_FN void chol_solve(float (*L)[NVP], float* xs) {
 #ifdef LS_EMULATE
   for (int i = 0; i < NV; i++) {
     float v = xs[i];
     for (int k = 0; k < i; k++) v -= L[i][k] * xs[k];
-    xs[i] = v * L[i][i];
+    xs[i] = v * L[i][NV];
   }
   for (int i = NV - 1; i >= 0; i--) {
     float v = xs[i];
     for (int k = i + 1; k < NV; k++) v -= L[k][i] * xs[k];
-    xs[i] = v * L[i][i];
+    xs[i] = v * L[i][NV];
   }
 #else
+  // lane i carries x_i; thanks to the zeros on and above the diagonal every lane executes the same FFMA
   const int lane = LS_LANE, li = lane < NV ? lane : NV - 1;
   float x = lane < NV ? xs[lane] : 0.0f;
-  const float inv = L[li][li];
-  LS_SOLVE_UNROLL for (int j = 0; j < NV; j++) {
-    const float t = x * inv;
-    const float yj = __shfl_sync(0xffffffffu, t, j);
-    const float lij = L[li][j];
-    x = (lane == j) ? t : ((lane > j) ? fmaf(-lij, yj, x) : x);
-  }
-  LS_SOLVE_UNROLL for (int j = NV - 1; j >= 0; j--) {
-    const float t = x * inv;
-    const float xj = __shfl_sync(0xffffffffu, t, j);
-    const float lji = L[j][li];
-    x = (lane == j) ? t : ((lane < j) ? fmaf(-lji, xj, x) : x);
-  }
+  const float inv = L[li][NV];
+#pragma unroll
+  for (int j = 0; j < NV - 1; j++) x = fmaf(-L[li][j], __shfl_sync(0xffffffffu, x * inv, j), x);   // y_j = x_j / L_jj
+  x *= inv;                                                                                          // x = y (L y = b)
+#pragma unroll
+  for (int j = NV - 1; j > 0; j--) x = fmaf(-L[j][li], __shfl_sync(0xffffffffu, x * inv, j), x);    // z_j = x_j / L_jj
+  x *= inv;
   if (lane < NV) xs[lane] = x;
   __syncwarp();
 #endif
@@ -1215,17 +1210,16 @@ LS_FN void make_hessian(const int ms, EnvS<C>& e) {
       const float Dm = e.r_D[r0] / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
       const float invT = 1.0f / T;
       const float c1 = mu * N * invT * invT * invT, c2 = mu * mu - mu * N * invT;
-      // v_b = sum_a J[a][lane] * Hc[a][b]  (Hc symmetric, in jar space), then H[lane][:] += v_b * J[b][:]
+      // Hc (jar space) = Dm S [ e0 e0^T - (mu/T)(e0 U^T + U e0^T) + c1 U U^T + c2 I_t ] S  with U, I_t tangential only.
+      // v = Hc p for this lane's column p_a = J[a][lane] in O(dim), then H[lane][:] += sum_b v_b J[b][:]
+      float p0 = e.coneS[0] * e.J[jr0][li], pU = 0;
+      NOUNROLL for (int a = 1; a < dim; a++) pU = fmaf(e.coneU[a], e.coneS[a] * e.J[jr0 + a][li], pU);
+      const float muT = mu * invT;
       NOUNROLL for (int b = 0; b < dim; b++) {
-        float vb = 0;
-        NOUNROLL for (int a = 0; a < dim; a++) {
-          float hc;
-          if (a == 0 && b == 0) hc = 1;
-          else if (a == 0) hc = -mu * e.coneU[b] * invT;
-          else if (b == 0) hc = -mu * e.coneU[a] * invT;
-          else hc = c1 * e.coneU[a] * e.coneU[b] + (a == b ? c2 : 0.0f);
-          vb = fmaf(Dm * hc * e.coneS[a] * e.coneS[b], e.J[jr0 + a][li], vb);
-        }
+        float vb;
+        if (b == 0) vb = p0 - muT * pU;
+        else vb = e.coneU[b] * (c1 * pU - muT * p0) + c2 * e.coneS[b] * e.J[jr0 + b][li];
+        vb *= Dm * e.coneS[b];
         const float4* row = reinterpret_cast<const float4*>(e.J[jr0 + b]);
 #pragma unroll
         for (int q = 0; q < JS / 4; q++) {
