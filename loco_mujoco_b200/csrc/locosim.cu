@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
   for (int i = lane; i < nu; i += 32) e.ctrl[t.act_idx[i]] = action[(size_t)env * nu + i] * t.act_delta[i] + t.act_mean[i];
   if (lane < 4) e.goal[lane] = st.goal[(size_t)env * 4 + lane];
   __syncwarp();
+  init_workspace(ms, e);
   // reward depends on the *previous* observation only (utils/reward.py via base.py:170-176): evaluate it now
   float rew = 0;
   if (t.reward_type == LS_REWARD_TARGET_VELOCITY) { float d = obs_value(t, e, t.ri[0]) - t.rp[0]; rew = expf(-d * d); }

@@ -29,6 +29,8 @@
 #define WARP_MIN(x) (x)
 #define LANE0
 #define LS_LANE 0
+#define LS_FFS(x) __builtin_ffs((int)(x))
+#define LS_CLZ(x) __builtin_clz((unsigned)(x))
 #define BLOCK_ANY(flag, pred) (pred)
 #define BLOCK_SYNC(flag) ((void)0)
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
@@ -40,6 +42,8 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define WARP_SUM(x) warp_sum(x)
 #define LANE0 if ((threadIdx.x & 31) == 0)
 #define LS_LANE ((int)(threadIdx.x & 31))
+#define LS_FFS(x) __ffs((int)(x))
+#define LS_CLZ(x) __clz((int)(x))
 // block-wide OR that doubles as a barrier: keeps the warps of a block in the same solver iteration (flag = 0: plain predicate)
 #define BLOCK_ANY(flag, pred) ((flag) ? (__syncthreads_or((pred) ? 1 : 0) != 0) : (pred))
 #define BLOCK_SYNC(flag) do { if (flag) __syncthreads(); } while (0)
@@ -249,62 +253,90 @@ LS_FN void impedance_KB(const float* solref, const float* solimp, float pos, flo
 // ----------------------------------------------------------------------------------------------------------
 // kinematics (mj_kinematics): level-synchronous over the tree, then geom centres
 // ----------------------------------------------------------------------------------------------------------
+// once per kernel (and per emulated env): the parts of the workspace that no phase rewrites
+template <class C>
+LS_FN void init_workspace(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
+  PAR_FOR(idx, EnvS<C>::NV * EnvS<C>::NVP) {
+    int i = idx / EnvS<C>::NVP, j = idx - i * EnvS<C>::NVP;
+    (&e.M[0][0])[idx] = (i == j && i >= m.nv) ? 1.0f : 0.0f;
+  }
+  SYNC();
+}
+
+// v rotated by the unit quaternion q:  v + 2 w (u x v) + 2 u x (u x v)
+LS_DEV void rotvec(float* r, const float* q, const float* v) {
+  float t[3] = {q[2] * v[2] - q[3] * v[1], q[3] * v[0] - q[1] * v[2], q[1] * v[1] - q[2] * v[0]};
+  t[0] += t[0]; t[1] += t[1]; t[2] += t[2];
+  float x = v[0] + q[0] * t[0] + (q[2] * t[2] - q[3] * t[1]), y = v[1] + q[0] * t[1] + (q[3] * t[0] - q[1] * t[2]),
+        z = v[2] + q[0] * t[2] + (q[1] * t[1] - q[2] * t[0]);
+  r[0] = x; r[1] = y; r[2] = z;
+}
+
+// mj_kinematics in three phases: (1) all joints in parallel: the joint's own quaternion / translation;
+// (2) the kinematic chain, level by level, in quaternion algebra only (the only serial part: per joint one vector
+// rotation and one quaternion product when the joint anchor is the body origin, which it is for almost every joint of
+// the in-scope robots); (3) all bodies in parallel: rotation matrices, inertial frames; then geoms.
 template <class C>
 LS_FN void kinematics(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
   LANE0 {
     e.xpos[0][0] = e.xpos[0][1] = e.xpos[0][2] = 0;
     e.xquat[0][0] = 1; e.xquat[0][1] = e.xquat[0][2] = e.xquat[0][3] = 0;
-    for (int k = 0; k < 9; k++) e.xmat[0][k] = (k % 4 == 0) ? 1.0f : 0.0f;
-    e.xipos[0][0] = e.xipos[0][1] = e.xipos[0][2] = 0;
+  }
+  PAR_FOR(j, m.nv) {          // joint-local motion -> cdof_dot[j][0..3] (scratch until smooth_forces)
+    const float q = e.qpos[j] - m.qpos0[j];
+    float* o = e.cdof_dot[j];
+    if (m.jnt_type[j] == LS_JNT_SLIDE) { o[0] = q; }
+    else {
+      float sn, cs;
+      sincosf(0.5f * q, &sn, &cs);
+      o[0] = cs; o[1] = m.jnt_axis[3 * j] * sn; o[2] = m.jnt_axis[3 * j + 1] * sn; o[3] = m.jnt_axis[3 * j + 2] * sn;
+    }
   }
   SYNC();
   for (int lev = 1; lev < m.nlevel; lev++) {
     PAR_FOR(b, m.nb) {
       if (m.body_level[b] != lev) continue;
-      int p = m.body_parentid[b];
-      float pos[3], quat[4], tmp[3], mat[9];
-      mulmatvec3(tmp, e.xmat[p], m.body_pos + 3 * b);
+      const int p = m.body_parentid[b];
+      float pos[3], quat[4], tmp[3];
+      rotvec(tmp, e.xquat[p], m.body_pos + 3 * b);
       for (int k = 0; k < 3; k++) pos[k] = e.xpos[p][k] + tmp[k];
       mulquat(quat, e.xquat[p], m.body_quat + 4 * b);
-      int jn = m.body_jntnum[b], ja = m.body_jntadr[b];
-      quat2mat(mat, quat);
+      const int jn = m.body_jntnum[b], ja = m.body_jntadr[b];
       NOUNROLL for (int k = 0; k < jn; k++) {
-        int j = ja + k;
-        mulmatvec3(tmp, mat, m.jnt_pos + 3 * j);
-        float anchor[3] = {pos[0] + tmp[0], pos[1] + tmp[1], pos[2] + tmp[2]};
-        float axis[3];
-        mulmatvec3(axis, mat, m.jnt_axis + 3 * j);
+        const int j = ja + k;
+        const float* jp = m.jnt_pos + 3 * j;
+        const bool at_origin = (jp[0] == 0.0f) & (jp[1] == 0.0f) & (jp[2] == 0.0f);
+        float anchor[3] = {pos[0], pos[1], pos[2]}, axis[3];
+        if (!at_origin) { rotvec(tmp, quat, jp); anchor[0] += tmp[0]; anchor[1] += tmp[1]; anchor[2] += tmp[2]; }
+        rotvec(axis, quat, m.jnt_axis + 3 * j);
         for (int c = 0; c < 3; c++) { e.xanchor[j][c] = anchor[c]; e.xaxis[j][c] = axis[c]; }
-        float q = e.qpos[j] - m.qpos0[j];
+        const float* o = e.cdof_dot[j];
         if (m.jnt_type[j] == LS_JNT_SLIDE) {
-          for (int c = 0; c < 3; c++) pos[c] += axis[c] * q;
+          for (int c = 0; c < 3; c++) pos[c] += axis[c] * o[0];
         } else {
-          float sn, cs;
-          sincosf(0.5f * q, &sn, &cs);
-          float ql[4] = {cs, m.jnt_axis[3 * j] * sn, m.jnt_axis[3 * j + 1] * sn, m.jnt_axis[3 * j + 2] * sn};
-          mulquat(quat, quat, ql);
-          quat2mat(mat, quat);
-          mulmatvec3(tmp, mat, m.jnt_pos + 3 * j);
-          for (int c = 0; c < 3; c++) pos[c] = anchor[c] - tmp[c];
+          mulquat(quat, quat, o);
+          if (!at_origin) { rotvec(tmp, quat, jp); for (int c = 0; c < 3; c++) pos[c] = anchor[c] - tmp[c]; }
         }
       }
-      float n = sqrtf(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
-      float inv = 1.0f / n;
-      for (int c = 0; c < 4; c++) quat[c] *= inv;
-      quat2mat(mat, quat);
+      const float inv = rsqrtf(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
       for (int c = 0; c < 3; c++) e.xpos[b][c] = pos[c];
-      for (int c = 0; c < 4; c++) e.xquat[b][c] = quat[c];
-      for (int c = 0; c < 9; c++) e.xmat[b][c] = mat[c];
-      mulmatvec3(tmp, mat, PRM(body_ipos) + 3 * b);
-      for (int c = 0; c < 3; c++) e.xipos[b][c] = pos[c] + tmp[c];
-      float iq[4], im[9];
-      mulquat(iq, quat, PRM(body_iquat) + 4 * b);
-      quat2mat(im, iq);
-      for (int c = 0; c < 9; c++) e.ximat[b][c] = im[c];
+      for (int c = 0; c < 4; c++) e.xquat[b][c] = quat[c] * inv;
     }
     SYNC();
   }
+  PAR_FOR(b, m.nb) {
+    float mat[9], tmp[3], iq[4];
+    quat2mat(mat, e.xquat[b]);
+    for (int c = 0; c < 9; c++) e.xmat[b][c] = mat[c];
+    mulmatvec3(tmp, mat, PRM(body_ipos) + 3 * b);
+    for (int c = 0; c < 3; c++) e.xipos[b][c] = e.xpos[b][c] + tmp[c];
+    mulquat(iq, e.xquat[b], PRM(body_iquat) + 4 * b);
+    quat2mat(mat, iq);
+    for (int c = 0; c < 9; c++) e.ximat[b][c] = mat[c];
+  }
+  SYNC();
   PAR_FOR(g, m.ng) {
     int b = m.geom_bodyid[g];
     float tmp[3];
@@ -450,25 +482,22 @@ LS_FN void chol_solve(float (*L)[NVP], float* xs) {
 template <class C>
 LS_FN void crb_factor(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
-  PAR_FOR(b, m.nb) for (int k = 0; k < 10; k++) e.crb[b][k] = e.cinert[b][k];
-  SYNC();
-  for (int lev = m.nlevel - 2; lev >= 1; lev--) {
-    // bodies at level `lev` gather their children (level lev+1)
-    PAR_FOR(b, m.nb) {
-      if (m.body_level[b] != lev) continue;
-      float acc[10];
-      for (int k = 0; k < 10; k++) acc[k] = e.crb[b][k];
-      NOUNROLL for (int c = b + 1; c < m.nb; c++)
-        if (m.body_parentid[c] == b) for (int k = 0; k < 10; k++) acc[k] += e.crb[c][k];
-      for (int k = 0; k < 10; k++) e.crb[b][k] = acc[k];
+  // composite inertia of body b = sum of cinert over its subtree = the bodies whose dof chain contains b's last dof
+  // (all in one frame, so a plain sum; no level recursion)
+  PAR_FOR(b, m.nb) {
+    float acc[10];
+    for (int k = 0; k < 10; k++) acc[k] = e.cinert[b][k];
+    if (b > 0) {
+      const int ld = 31 - LS_CLZ(m.body_dofmask[b]);
+      NOUNROLL for (int c = b + 1; c < m.nb; c++) {
+        if (!((m.body_dofmask[c] >> ld) & 1)) continue;
+        for (int k = 0; k < 10; k++) acc[k] += e.cinert[c][k];
+      }
     }
-    SYNC();
-  }
-  PAR_FOR(idx, EnvS<C>::NV * EnvS<C>::NVP) {
-    int i = idx / EnvS<C>::NVP, j = idx - i * EnvS<C>::NVP;
-    (&e.M[0][0])[idx] = (i == j && i >= m.nv) ? 1.0f : 0.0f;
+    for (int k = 0; k < 10; k++) e.crb[b][k] = acc[k];
   }
   SYNC();
+  // (entries of M outside the dof chains stay 0 and the identity padding stays 1: init_workspace)
   PAR_FOR(i, m.nv) {
     float buf[6];
     mulInertVec(buf, e.crb[m.jnt_bodyid[i]], e.cdof[i]);
@@ -974,61 +1003,57 @@ LS_FN void make_constraint(const int ms, EnvS<C>& e) {
 // ----------------------------------------------------------------------------------------------------------
 // velocity-dependent smooth terms: comVel, RNE bias, passive, actuation -> qfrc_smooth, qacc_smooth
 // ----------------------------------------------------------------------------------------------------------
+// mj_comVel + mj_rne (bias forces) without tree recursion: all spatial vectors live in one frame (world-aligned, at the
+// CoM), so the velocity / bias acceleration of a body is a plain SUM over the dofs of its chain (bit mask
+// body_dofmask) and the force a dof feels is a plain sum over the bodies of its subtree. Three fully parallel passes.
 template <class C>
 LS_FN void smooth_forces(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
   const int nv = m.nv;
-  // comVel + cacc + per-body force, level by level (cvel/cacc of parent needed)
-  LANE0 {
-    for (int k = 0; k < 6; k++) { e.cvel[0][k] = 0; e.cacc[0][k] = 0; }
-    e.cacc[0][3] = -m.gravity[0]; e.cacc[0][4] = -m.gravity[1]; e.cacc[0][5] = -m.gravity[2];
+  // (A) cdof_dot_j = cvel(just above dof j) x cdof_j
+  PAR_FOR(j, nv) {
+    unsigned mask = (unsigned)m.body_dofmask[m.jnt_bodyid[j]] & ((1u << j) - 1u);
+    float v[6] = {0, 0, 0, 0, 0, 0};
+    while (mask) {
+      const int i = LS_FFS(mask) - 1;
+      mask &= mask - 1;
+      const float qv = e.qvel[i];
+      for (int c = 0; c < 6; c++) v[c] = fmaf(e.cdof[i][c], qv, v[c]);
+    }
+    float cdd[6];
+    crossMotion(cdd, v, e.cdof[j]);
+    for (int c = 0; c < 6; c++) e.cdof_dot[j][c] = cdd[c];
   }
   SYNC();
-  for (int lev = 1; lev < m.nlevel; lev++) {
-    PAR_FOR(b, m.nb) {
-      if (m.body_level[b] != lev) continue;
-      int p = m.body_parentid[b];
-      float cvel[6], cacc[6];
-      for (int k = 0; k < 6; k++) { cvel[k] = e.cvel[p][k]; cacc[k] = e.cacc[p][k]; }
-      int jn = m.body_jntnum[b], ja = m.body_jntadr[b];
-      NOUNROLL for (int k = 0; k < jn; k++) {
-        int j = ja + k;
-        float cdd[6];
-        crossMotion(cdd, cvel, e.cdof[j]);
-        float qv = e.qvel[j];
-        for (int c = 0; c < 6; c++) { e.cdof_dot[j][c] = cdd[c]; cvel[c] += e.cdof[j][c] * qv; cacc[c] += cdd[c] * qv; }
-      }
-      for (int k = 0; k < 6; k++) { e.cvel[b][k] = cvel[k]; e.cacc[b][k] = cacc[k]; }
-    }
-    SYNC();
-  }
-  // body forces -> reuse crb[b][0..5] as cfrc storage (crb no longer needed after M)
+  // (B) per body: cvel, cacc (gravity enters as the world's upward acceleration), f = I cacc + cvel x* (I cvel)
+  //     -> crb[b][0..5] (the composite inertias are dead once M is assembled)
   PAR_FOR(b, m.nb) {
     float* f = e.crb[b];
     if (b == 0) { for (int k = 0; k < 6; k++) f[k] = 0; continue; }
+    unsigned mask = (unsigned)m.body_dofmask[b];
+    float cvel[6] = {0, 0, 0, 0, 0, 0}, cacc[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
+    while (mask) {
+      const int i = LS_FFS(mask) - 1;
+      mask &= mask - 1;
+      const float qv = e.qvel[i];
+      for (int c = 0; c < 6; c++) { cvel[c] = fmaf(e.cdof[i][c], qv, cvel[c]); cacc[c] = fmaf(e.cdof_dot[i][c], qv, cacc[c]); }
+    }
     float t1[6], t2[6], t3[6];
-    mulInertVec(t1, e.cinert[b], e.cacc[b]);
-    mulInertVec(t2, e.cinert[b], e.cvel[b]);
-    crossForce(t3, e.cvel[b], t2);
+    mulInertVec(t1, e.cinert[b], cacc);
+    mulInertVec(t2, e.cinert[b], cvel);
+    crossForce(t3, cvel, t2);
     for (int k = 0; k < 6; k++) f[k] = t1[k] + t3[k];
   }
   SYNC();
-  for (int lev = m.nlevel - 2; lev >= 1; lev--) {
-    PAR_FOR(b, m.nb) {
-      if (m.body_level[b] != lev) continue;
-      float acc[6];
-      for (int k = 0; k < 6; k++) acc[k] = e.crb[b][k];
-      NOUNROLL for (int c = b + 1; c < m.nb; c++)
-        if (m.body_parentid[c] == b) for (int k = 0; k < 6; k++) acc[k] += e.crb[c][k];
-      for (int k = 0; k < 6; k++) e.crb[b][k] = acc[k];
-    }
-    SYNC();
-  }
-  // qfrc_smooth = passive - bias + actuator
+  // (C) bias force of dof j = cdof_j . (sum of f over the bodies below j);  qfrc_smooth = passive - bias + actuator
   PAR_FOR(j, nv) {
-    const float* f = e.crb[m.jnt_bodyid[j]];
+    float F[6] = {0, 0, 0, 0, 0, 0};
+    NOUNROLL for (int b = 1; b < m.nb; b++) {
+      if (!((m.body_dofmask[b] >> j) & 1)) continue;
+      for (int c = 0; c < 6; c++) F[c] += e.crb[b][c];
+    }
     float bias = 0;
-    for (int c = 0; c < 6; c++) bias += e.cdof[j][c] * f[c];
+    for (int c = 0; c < 6; c++) bias += e.cdof[j][c] * F[c];
     float passive = -PRM(jnt_stiffness)[j] * (e.qpos[j] - m.qpos_spring[j]) - PRM(dof_damping)[j] * e.qvel[j];
     e.qfrc_smooth[j] = passive - bias;
   }

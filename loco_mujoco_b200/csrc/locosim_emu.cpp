@@ -48,7 +48,7 @@ struct EmuT : EmuBase {
   }
   void set_ws(const double* w) override { for (int i = 0; i < m.nv; i++) e.qacc_ws[i] = (float)w[i]; }
   int info(int k) override { return k == 0 ? e.ncon : (k == 1 ? e.nefc : e.solver_iter); }
-  void bind_prm() override { e.prm = hm.default_row.data(); }
+  void bind_prm() override { e.prm = hm.default_row.data(); c_models[0] = m; init_workspace(0, e); }
 };
 
 extern "C" {
