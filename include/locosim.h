@@ -65,9 +65,9 @@ int locosim_step(locosim_t* h, const float* d_action, float* d_obs, float* d_rew
 int locosim_get_state(locosim_t* h, float* d_qpos, float* d_qvel, float* d_qacc_warmstart, void* stream);
 int locosim_set_state(locosim_t* h, const float* d_qpos, const float* d_qvel, const float* d_qacc_warmstart, void* stream);
 
-/* Diagnostics: per-env counters since create: [0]=env steps, [1]=resets, [2]=solver iterations of the last sub-step,
- * [3]=contacts of the last sub-step, [4]=terminations caused by a non-finite state, [5..7]=max over control steps of the
- * last sub-step's solver iterations / contacts / constraint rows.  d_out int32 [n_envs, 8]. */
+/* Diagnostics: per-env counters since create: [0]=env steps, [1]=resets, [2]=Newton iterations of the last control
+ * step (summed over its sub-steps; also the regrouping key), [3]=contacts of the last sub-step, [4]=terminations caused by
+ * a non-finite state, [5..7]=max over control steps of [2] / the last sub-step's contacts / constraint rows.  d_out int32 [n_envs, 8]. */
 int locosim_get_counters(locosim_t* h, int32_t* d_out, void* stream);
 
 /* Domain randomisation (replaces DomainRandomizationHandler + per-reset MjModel recompilation,
@@ -78,6 +78,10 @@ int locosim_param_pool_row_len(const locosim_t* h);
 int locosim_set_param_pool(locosim_t* h, const double* pool, int n_rows, int row_len);
 /* pool row currently used by each env: d_out int32 [n_envs] */
 int locosim_get_param_rows(locosim_t* h, int32_t* d_out, void* stream);
+
+/* Kernels enqueued by one locosim_step: the fused step kernel, preceded (default) by the one-block regrouping kernel that
+ * buckets the envs by the solver effort of their previous step (scheduling only; results do not depend on it). */
+int locosim_kernels_per_step(const locosim_t* h);
 
 /* Launch geometry chosen for this handle: warps(envs) per block, dynamic shared memory bytes per block, blocks. */
 int locosim_launch_info(const locosim_t* h, int* warps_per_block, int* smem_bytes, int* n_blocks);

@@ -23,6 +23,7 @@ struct EngineState {
   int* episode;                     // [N] reset counter (drives the per-env random stream)
   int* counters;                    // [N,8]
   int* dr_row;                      // [N] row of the parameter pool used by the env's current episode
+  int* perm;                        // [N] env handled by warp slot i (regrouped every step by solver effort)
   const float* pool;                // [K, P] parameter pool (domain randomisation); K = 1: the model's own values
   int pool_K;
 };
@@ -101,9 +102,9 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // warps past the last env shadow it (same barriers, no stores): the block-wide barriers inside the solver have
   // data-dependent counts, so every warp of a block has to run the physics
-  const int env_raw = blockIdx.x * (blockDim.x >> 5) + warp;
-  const bool ghost = env_raw >= n_envs;
-  const int env = ghost ? n_envs - 1 : env_raw;
+  const int slot_raw = blockIdx.x * (blockDim.x >> 5) + warp;
+  const bool ghost = slot_raw >= n_envs;
+  const int env = st.perm[ghost ? n_envs - 1 : slot_raw];
   EnvS<C>& e = reinterpret_cast<EnvS<C>*>(smem_raw)[warp];
   const DevModel& m = c_models[ms];
   const int nv = m.nv, nu = m.nu, D = t.obs_dim;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
   if (lane < 4) e.goal[lane] = st.goal[(size_t)env * 4 + lane];
   __syncwarp();
   init_workspace(ms, e);
+  if (lane == 0) e.iter_sum = 0;
   // reward depends on the *previous* observation only (utils/reward.py via base.py:170-176): evaluate it now
   float rew = 0;
   if (t.reward_type == LS_REWARD_TARGET_VELOCITY) { float d = obs_value(t, e, t.ri[0]) - t.rp[0]; rew = expf(-d * d); }
@@ -161,9 +163,9 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
     reward[env] = r;
     done[env] = is_done ? 1 : 0;
     int* cnt = st.counters + (size_t)env * 8;
-    cnt[0] += 1; cnt[2] = e.solver_iter; cnt[3] = e.ncon;
+    cnt[0] += 1; cnt[2] = e.iter_sum; cnt[3] = e.ncon;
     if (bad) cnt[4] += 1;
-    cnt[5] = max(cnt[5], e.solver_iter); cnt[6] = max(cnt[6], e.ncon); cnt[7] = max(cnt[7], e.nefc);
+    cnt[5] = max(cnt[5], e.iter_sum); cnt[6] = max(cnt[6], e.ncon); cnt[7] = max(cnt[7], e.nefc);
   }
 
   // ---- auto-reset ----
@@ -190,10 +192,40 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// Regrouping: the warps of a block run the solver in lock-step, so a block is as slow as its hardest env. Solver effort
+// is strongly correlated from one control step to the next (lag-1 correlation of the per-step Newton iteration count
+// ~0.6), so before every step the envs are bucketed by the iteration count of their previous step (counting sort,
+// one block) and envs of similar effort share a block. Pure scheduling: results do not depend on the mapping.
+// ----------------------------------------------------------------------------------------------------------
+#define LS_RANK_BUCKETS 128
+__global__ void __launch_bounds__(1024) rank_kernel(const int* __restrict__ counters, int* __restrict__ perm, int n_envs,
+                                                    int key_shift) {
+  __shared__ int hist[LS_RANK_BUCKETS];
+  __shared__ int base[LS_RANK_BUCKETS];
+  for (int i = threadIdx.x; i < LS_RANK_BUCKETS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_envs; i += blockDim.x) {
+    int k = counters[(size_t)i * 8 + 2] >> key_shift;
+    atomicAdd(&hist[k < LS_RANK_BUCKETS - 1 ? k : LS_RANK_BUCKETS - 1], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < LS_RANK_BUCKETS; i++) { base[i] = acc; acc += hist[i]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_envs; i += blockDim.x) {
+    int k = counters[(size_t)i * 8 + 2] >> key_shift;
+    int pos = atomicAdd(&base[k < LS_RANK_BUCKETS - 1 ? k : LS_RANK_BUCKETS - 1], 1);
+    perm[n_envs - 1 - pos] = i;     // hardest first: the long blocks start early, the short ones fill the tail
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // handle
 // ----------------------------------------------------------------------------------------------------------
 struct locosim_handle {
-  int device = 0, n_envs = 0, cfg = -1, wpb = 4, smem = 0, slot = -1, sync_substeps = 0;
+  int device = 0, n_envs = 0, cfg = -1, wpb = 4, smem = 0, slot = -1, sync_substeps = 0, regroup = 1, key_shift = 0;
   uint64_t seed = 0;
   int64_t env_off = 0;
   HostModel hm;
@@ -230,6 +262,7 @@ template <class C>
 static int launch_step(locosim_handle* h, const float* a, float* o, float* r, uint8_t* d, float* no, int auto_reset,
                        cudaStream_t s) {
   int blocks = (h->n_envs + h->wpb - 1) / h->wpb;
+  if (h->regroup) rank_kernel<<<1, 1024, 0, s>>>(h->st.counters, h->st.perm, h->n_envs, h->key_shift);
   step_kernel<C><<<blocks, h->wpb * 32, h->smem, s>>>(h->slot, h->dt, h->so, h->st, a, o, r, d, no, h->n_envs, auto_reset,
                                                       h->seed, h->env_off, h->sync_substeps);
   CK(cudaGetLastError());
@@ -261,6 +294,10 @@ static int setup_cfg(locosim_handle* h) {
   if (getenv("LOCOSIM_WPB")) { int w = atoi(getenv("LOCOSIM_WPB")); if (w >= 1 && w <= 14 && w * per_env <= dev_max) best = w; }
   if (getenv("LOCOSIM_SYNC")) h->sync_substeps = atoi(getenv("LOCOSIM_SYNC"));
   h->so.sync_iters = 1;
+  h->regroup = 1;
+  if (getenv("LOCOSIM_REGROUP")) h->regroup = atoi(getenv("LOCOSIM_REGROUP"));
+  h->key_shift = C::RK4 ? 2 : 0;   // RK4: four solves per sub-step
+  if (getenv("LOCOSIM_KEY_SHIFT")) h->key_shift = atoi(getenv("LOCOSIM_KEY_SHIFT"));
   if (getenv("LOCOSIM_SYNC_ITERS")) h->so.sync_iters = atoi(getenv("LOCOSIM_SYNC_ITERS"));
   h->so.sync_phases = 32;   // one more barrier where the warps enter the solver (measured +2%)
   if (getenv("LOCOSIM_SYNC_PHASES")) h->so.sync_phases = atoi(getenv("LOCOSIM_SYNC_PHASES"));
@@ -312,12 +349,13 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   ok = ok && cudaMalloc((void**)&h->st.qpos, N * nv * 4) == cudaSuccess && cudaMalloc((void**)&h->st.qvel, N * nv * 4) == cudaSuccess &&
        cudaMalloc((void**)&h->st.ws, N * nv * 4) == cudaSuccess && cudaMalloc((void**)&h->st.goal, N * 4 * 4) == cudaSuccess &&
        cudaMalloc((void**)&h->st.episode, N * 4) == cudaSuccess && cudaMalloc((void**)&h->st.counters, N * 32) == cudaSuccess &&
-       cudaMalloc((void**)&h->st.dr_row, N * 4) == cudaSuccess &&
+       cudaMalloc((void**)&h->st.dr_row, N * 4) == cudaSuccess && cudaMalloc((void**)&h->st.perm, N * 4) == cudaSuccess &&
        up((void**)&h->d_pool, h->hm.default_row.data(), h->hm.default_row.size() * 4);
   if (!ok) { std::string m = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); locosim_destroy(h); g_create_error = m; return 1; }
   cudaMemset(h->st.qpos, 0, N * nv * 4); cudaMemset(h->st.qvel, 0, N * nv * 4); cudaMemset(h->st.ws, 0, N * nv * 4);
   cudaMemset(h->st.goal, 0, N * 16); cudaMemset(h->st.episode, 0, N * 4); cudaMemset(h->st.counters, 0, N * 32);
   cudaMemset(h->st.dr_row, 0, N * 4);
+  { std::vector<int> id(N); for (size_t i = 0; i < N; i++) id[i] = (int)i; cudaMemcpy(h->st.perm, id.data(), N * 4, cudaMemcpyHostToDevice); }
   h->st.pool = h->d_pool; h->st.pool_K = 1;
   bind_model(h->dm, h->hm, h->d_mints, h->d_mreals);
   for (int k = 0; k < LS_MAX_SLOTS && h->slot < 0; k++) if (!g_slot_used[k]) { h->slot = k; g_slot_used[k] = true; }
@@ -342,7 +380,7 @@ void locosim_destroy(locosim_t* h) {
   if (h->slot >= 0) g_slot_used[h->slot] = false;
   cudaFree(h->d_mints); cudaFree(h->d_mreals); cudaFree(h->d_tints); cudaFree(h->d_treals);
   cudaFree(h->st.qpos); cudaFree(h->st.qvel); cudaFree(h->st.ws); cudaFree(h->st.goal); cudaFree(h->st.episode);
-  cudaFree(h->st.counters); cudaFree(h->st.dr_row); cudaFree(h->d_pool);
+  cudaFree(h->st.counters); cudaFree(h->st.dr_row); cudaFree(h->st.perm); cudaFree(h->d_pool);
   delete h;
 }
 
@@ -439,6 +477,8 @@ int locosim_set_param_pool(locosim_t* h, const double* pool, int n_rows, int row
   CK(cudaMemset(h->st.dr_row, 0, (size_t)h->n_envs * 4));
   return 0;
 }
+
+int locosim_kernels_per_step(const locosim_t* h) { return h->regroup ? 2 : 1; }
 
 int locosim_launch_info(const locosim_t* h, int* wpb, int* smem, int* blocks) {
   if (wpb) *wpb = h->wpb;

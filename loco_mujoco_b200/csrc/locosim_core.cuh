@@ -128,7 +128,7 @@ struct alignas(16) EnvS {
   float cdof[NV][6];
   float M[NV][NVP], H[NV][NVP];                              // H: chol(M) during smooth_forces, then the Newton Hessian factor
   // contacts
-  int ncon, nunit, nrow, nefc, solver_iter, pad0, pad1, pad2;
+  int ncon, nunit, nrow, nefc, solver_iter, iter_sum, pad1, pad2;   // iter_sum: Newton iterations of this control step
   float con_dist[MAXCON], con_pos[MAXCON][3], con_frame[MAXCON][9], con_fri[MAXCON][5], con_imp[MAXCON], con_K[MAXCON],
       con_B[MAXCON], con_incl[MAXCON], con_mu[MAXCON];
   int con_dim[MAXCON], con_g1[MAXCON], con_g2[MAXCON], con_row[MAXCON];
@@ -1565,7 +1565,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
       active = iter < so.max_iter && scale * sqrtf(gn) >= so.tolerance && cost < oldcost;
     }
   }
-  LANE0 { e.solver_iter = iter; }
+  LANE0 { e.solver_iter = iter; e.iter_sum += iter; }
   PAR_FOR(i, nv) e.qacc_ws[i] = e.qacc[i];
   SYNC();
 }

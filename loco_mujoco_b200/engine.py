@@ -54,6 +54,8 @@ def load_library():
     lib.locosim_set_param_pool.argtypes = [vp, vp, ip, ip]
     lib.locosim_get_param_rows.restype = ip
     lib.locosim_get_param_rows.argtypes = [vp, vp, vp]
+    lib.locosim_kernels_per_step.restype = ip
+    lib.locosim_kernels_per_step.argtypes = [vp]
     lib.locosim_launch_info.restype = ip
     lib.locosim_launch_info.argtypes = [vp, ctypes.POINTER(ip), ctypes.POINTER(ip), ctypes.POINTER(ip)]
     _LIB = lib
@@ -63,7 +65,8 @@ def load_library():
 EXPORTED_SYMBOLS = ["locosim_create", "locosim_destroy", "locosim_last_error", "locosim_num_envs", "locosim_obs_dim",
                     "locosim_action_dim", "locosim_nq", "locosim_set_solver", "locosim_reset", "locosim_step",
                     "locosim_get_state", "locosim_set_state", "locosim_get_counters", "locosim_launch_info",
-                    "locosim_param_pool_row_len", "locosim_set_param_pool", "locosim_get_param_rows"]
+                    "locosim_param_pool_row_len", "locosim_set_param_pool", "locosim_get_param_rows",
+                    "locosim_kernels_per_step"]
 
 
 def _ptr(t):
@@ -102,6 +105,7 @@ class CudaEngine:
         self.reward = torch.zeros((n_envs,), dtype=torch.float32, device=self.device)
         self.done = torch.zeros((n_envs,), dtype=torch.uint8, device=self.device)
         self.launches = 0
+        self.kernels_per_step = self.lib.locosim_kernels_per_step(h)
 
     def _check(self, rc):
         if rc != 0:
@@ -139,7 +143,7 @@ class CudaEngine:
         self._check(self.lib.locosim_step(self.h, _ptr(action), _ptr(self.obs), _ptr(self.reward), _ptr(self.done),
                                           _ptr(self.next_obs) if want_next_obs else None, int(bool(auto_reset)),
                                           self._stream()))
-        self.launches += 1
+        self.launches += self.kernels_per_step
         return self.obs, self.reward, self.done, self.next_obs
 
     def get_state(self):
