@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
                                                     const float* __restrict__ action, float* __restrict__ obs,
                                                     float* __restrict__ reward, uint8_t* __restrict__ done,
                                                     float* __restrict__ next_obs, int n_envs, int auto_reset,
-                                                    uint64_t seed, int64_t env_off, int sync_substeps) {
+                                                    uint64_t seed, int64_t env_off, int sync_substeps, int key_mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // warps past the last env shadow it (same barriers, no stores): the block-wide barriers inside the solver have
@@ -165,7 +165,17 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
     int* cnt = st.counters + (size_t)env * 8;
     cnt[0] += 1; cnt[2] = e.iter_sum; cnt[3] = e.ncon;
     if (bad) cnt[4] += 1;
-    cnt[5] = max(cnt[5], e.iter_sum); cnt[6] = max(cnt[6], e.ncon); cnt[7] = max(cnt[7], e.nefc);
+    {
+      int key = e.iter_sum;
+      if (key_mode == 1) key = (cnt[5] + e.iter_sum + 1) >> 1;
+      else if (key_mode == 2) key = e.solver_iter * 8;
+      else if (key_mode == 3) key = e.iter_sum + (e.nefc >> 1);
+      else if (key_mode == 4) key = (3 * cnt[5] + e.iter_sum + 2) >> 2;
+      else if (key_mode == 5) key = e.iter_sum + 4 * e.solver_iter;
+      else if (key_mode == 6) key = e.iter_sum + e.nefc;
+      else if (key_mode == 7) key = e.iter_sum + 4 * e.solver_iter + (e.nefc >> 1);
+      cnt[5] = key;
+    } cnt[6] = max(cnt[6], e.ncon); cnt[7] = max(cnt[7], e.nefc);
   }
 
   // ---- auto-reset ----
@@ -205,7 +215,7 @@ __global__ void __launch_bounds__(1024) rank_kernel(const int* __restrict__ coun
   for (int i = threadIdx.x; i < LS_RANK_BUCKETS; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < n_envs; i += blockDim.x) {
-    int k = counters[(size_t)i * 8 + 2] >> key_shift;
+    int k = counters[(size_t)i * 8 + 5] >> key_shift;
     atomicAdd(&hist[k < LS_RANK_BUCKETS - 1 ? k : LS_RANK_BUCKETS - 1], 1);
   }
   __syncthreads();
@@ -215,7 +225,7 @@ __global__ void __launch_bounds__(1024) rank_kernel(const int* __restrict__ coun
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n_envs; i += blockDim.x) {
-    int k = counters[(size_t)i * 8 + 2] >> key_shift;
+    int k = counters[(size_t)i * 8 + 5] >> key_shift;
     int pos = atomicAdd(&base[k < LS_RANK_BUCKETS - 1 ? k : LS_RANK_BUCKETS - 1], 1);
     perm[n_envs - 1 - pos] = i;     // hardest first: the long blocks start early, the short ones fill the tail
   }
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(1024) rank_kernel(const int* __restrict__ coun
 // handle
 // ----------------------------------------------------------------------------------------------------------
 struct locosim_handle {
-  int device = 0, n_envs = 0, cfg = -1, wpb = 4, smem = 0, slot = -1, sync_substeps = 0, regroup = 1, key_shift = 0;
+  int device = 0, n_envs = 0, cfg = -1, wpb = 4, smem = 0, slot = -1, sync_substeps = 0, regroup = 1, key_shift = 0, key_mode = 3;
   uint64_t seed = 0;
   int64_t env_off = 0;
   HostModel hm;
@@ -264,7 +274,7 @@ static int launch_step(locosim_handle* h, const float* a, float* o, float* r, ui
   int blocks = (h->n_envs + h->wpb - 1) / h->wpb;
   if (h->regroup) rank_kernel<<<1, 1024, 0, s>>>(h->st.counters, h->st.perm, h->n_envs, h->key_shift);
   step_kernel<C><<<blocks, h->wpb * 32, h->smem, s>>>(h->slot, h->dt, h->so, h->st, a, o, r, d, no, h->n_envs, auto_reset,
-                                                      h->seed, h->env_off, h->sync_substeps);
+                                                      h->seed, h->env_off, h->sync_substeps, h->key_mode);
   CK(cudaGetLastError());
   return 0;
 }
@@ -298,6 +308,7 @@ static int setup_cfg(locosim_handle* h) {
   if (getenv("LOCOSIM_REGROUP")) h->regroup = atoi(getenv("LOCOSIM_REGROUP"));
   h->key_shift = C::RK4 ? 2 : 0;   // RK4: four solves per sub-step
   if (getenv("LOCOSIM_KEY_SHIFT")) h->key_shift = atoi(getenv("LOCOSIM_KEY_SHIFT"));
+  if (getenv("LOCOSIM_KEY_MODE")) h->key_mode = atoi(getenv("LOCOSIM_KEY_MODE"));
   if (getenv("LOCOSIM_SYNC_ITERS")) h->so.sync_iters = atoi(getenv("LOCOSIM_SYNC_ITERS"));
   h->so.sync_phases = 32;   // one more barrier where the warps enter the solver (measured +2%)
   if (getenv("LOCOSIM_SYNC_PHASES")) h->so.sync_phases = atoi(getenv("LOCOSIM_SYNC_PHASES"));

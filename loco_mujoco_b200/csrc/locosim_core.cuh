@@ -21,6 +21,7 @@
 #include "../../include/locosim_task.h"
 
 #ifdef LS_EMULATE
+struct alignas(16) float4 { float x, y, z, w; };
 #define LS_DEV static inline
 #define LS_FN static
 #define PAR_FOR(i, n) for (int i = 0; i < (n); i++)
@@ -260,6 +261,13 @@ LS_FN void init_workspace(const int ms, EnvS<C>& e) {
   PAR_FOR(idx, EnvS<C>::NV * EnvS<C>::NVP) {
     int i = idx / EnvS<C>::NVP, j = idx - i * EnvS<C>::NVP;
     (&e.M[0][0])[idx] = (i == j && i >= m.nv) ? 1.0f : 0.0f;
+  }
+  // entries [nv, NV) of the solver vectors are never written by the phases (they loop to nv): keep them 0
+  PAR_FOR(i, EnvS<C>::NV) {
+    if (i >= m.nv) {
+      e.qacc[i] = 0; e.qacc_ws[i] = 0; e.qacc_smooth[i] = 0; e.search[i] = 0; e.Mgrad[i] = 0; e.grad[i] = 0;
+      e.Ma[i] = 0; e.Mv[i] = 0; e.qfrc_smooth[i] = 0; e.qfrc_constraint[i] = 0; e.qvel[i] = 0; e.qpos[i] = 0;
+    }
   }
   SYNC();
 }
@@ -1094,9 +1102,17 @@ LS_FN void mulJ(const int ms, const EnvS<C>& e, float* res, const float* v) {
   PAR_FOR(r, nefc) {
     if (r < nunit) { const int ti = e.r_ti[r]; float vv = v[ROW_ID(ti)]; res[r] = ROW_K(ti) == 1 ? -vv : vv; }
     else {
-      const float* Jr = e.J[r - nunit];
+      // v is one of the NV-long solver vectors (entries >= nv are kept at 0, init_workspace), J rows are zero padded
+      const float4* Jr = reinterpret_cast<const float4*>(e.J[r - nunit]);
       float a = 0;
-      for (int d = 0; d < nv; d++) a += Jr[d] * v[d];
+#pragma unroll
+      for (int q = 0; q < EnvS<C>::JS / 4; q++) {
+        const float4 j4 = Jr[q];
+        a = fmaf(j4.x, v[4 * q], a);
+        if (4 * q + 1 < EnvS<C>::NV) a = fmaf(j4.y, v[4 * q + 1], a);
+        if (4 * q + 2 < EnvS<C>::NV) a = fmaf(j4.z, v[4 * q + 2], a);
+        if (4 * q + 3 < EnvS<C>::NV) a = fmaf(j4.w, v[4 * q + 3], a);
+      }
       res[r] = a;
     }
   }
@@ -1167,7 +1183,8 @@ LS_FN float update_constraint(const int ms, EnvS<C>& e, float* gauss_out) {
     int l0 = e.d_lrow[d][0], l1 = e.d_lrow[d][1];
     if (l0 >= 0) a += e.r_force[l0];
     if (l1 >= 0) a -= e.r_force[l1];
-    for (int r = 0; r < nrow; r++) a += e.J[r][d] * e.r_force[nunit + r];
+#pragma unroll 4
+    for (int r = 0; r < nrow; r++) a = fmaf(e.J[r][d], e.r_force[nunit + r], a);
     e.qfrc_constraint[d] = a;
     g += 0.5f * (e.Ma[d] - e.qfrc_smooth[d]) * (e.qacc[d] - e.qacc_smooth[d]);
   }
