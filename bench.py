@@ -29,7 +29,10 @@ os.environ.setdefault("LOCO_MUJOCO_B200_FORCE_BUNDLED", "1")     # the GPU box h
 
 ALGO_BYTES = {"UnitreeA1": 633, "HumanoidTorque": 657, "Atlas": 549, "Talos": 621}
 # DRAM bytes per launch of step_kernel from the last committed `ncu --set full` capture (profiles/README.md), 4096 envs
-NCU_TRAFFIC_BYTES = {"UnitreeA1": 3.83e6}       # fp32 state in/out + action + obs + reward + done, per env-step
+NCU_TRAFFIC_BYTES = {"UnitreeA1": 10.9e6, "HumanoidTorque": 15.2e6}
+# FP32 flops per env-step (2*FFMA + FMUL + FADD thread instructions of one launch / 4096 envs, same ncu captures)
+NCU_FLOPS_PER_ENV_STEP = {"UnitreeA1": 1.70e6, "HumanoidTorque": 2.50e6}
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz (non-tensor)
 
 
 def parse():
@@ -235,7 +238,13 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (NCU_TRAFFIC_BYTES.get(robot) if N == 4096 else None), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)", "peak_source": which, "algorithmic_bytes_per_env_step": bytes_per,
                              "note": "compute/latency-bound by design: state stays in shared memory across the 10 "
-                                     "sub-steps (DESIGN.md)"},
+                                     "sub-steps (DESIGN.md); measured traffic > algorithmic = instruction fetch + "
+                                     "local-memory lines re-read after the L2 flush between timed steps",
+                             "fp32": ({"achieved_tflops": NCU_FLOPS_PER_ENV_STEP[robot] * value / world / 1e12,
+                                       "peak_tflops": FP32_PEAK_TFLOPS,
+                                       "frac": NCU_FLOPS_PER_ENV_STEP[robot] * value / world / 1e12 / FP32_PEAK_TFLOPS,
+                                       "flops_per_env_step": NCU_FLOPS_PER_ENV_STEP[robot]}
+                                      if robot in NCU_FLOPS_PER_ENV_STEP else None)},
                 "cpu_baseline": cpu, "resets_in_run": resets, "launch_info": eng.launch_info(),
                 "physics_substeps_per_s": value * 10}
         print(json.dumps(line))
