@@ -9,6 +9,8 @@
  *                        base_humanoid.py:129-180; atlas.py:366-418; talos.py:356-405)
  *   reward               utils/reward.py:34-117 via LocoEnv.reward (base.py:170-176)
  *   action scaling       LocoEnv._preprocess_action (base.py:606-621, 121-126)
+ *   foot forces          LocoEnv._simulation_post_step / _get_ground_forces / _create_observation with use_foot_forces
+ *                        (base.py:94-98,584-604,623-631,656-679)
  *   reset                LocoEnv.reset/setup/set_sim_state + Trajectory.reset_trajectory
  *                        (base.py:178-241,478-497; utils/trajectory.py:236-273)
  *
@@ -18,24 +20,34 @@
 #define LOCOSIM_TASK_H
 
 #define LOCOSIM_TASK_MAGIC 0x5441534B
-#define LOCOSIM_TASK_VERSION 2
+#define LOCOSIM_TASK_VERSION 3
 
 enum {
   TKI_MAGIC = 0, TKI_VERSION, TKI_OBS_DIM, TKI_N_DONE, TKI_REWARD_TYPE, TKI_N_SUBSTEPS, TKI_N_TRAJ, TKI_TRAJ_LEN,
   TKI_N_GOAL, TKI_RECENTER0, TKI_RECENTER1, TKI_REWARD_I0, TKI_REWARD_I1, TKI_REWARD_I2, TKI_REWARD_I3,
   TKI_USE_ABSORBING,
-  TKI_HEADER_LEN = 16
+  TKI_N_GRF,      /* number of foot-force groups (0: use_foot_forces off) */
+  TKI_N_GRF_GEOM, /* length of the grf_group array (= ngeom of the compiled model, 0 if n_grf == 0) */
+  TKI_RESERVED0, TKI_RESERVED1,
+  TKI_HEADER_LEN = 20
 };
 /* int arrays after the header: obs_src_type[obs_dim], obs_src_idx[obs_dim], done_obs_idx[n_done],
  *                                  act_idx[nu]  (data.ctrl[act_idx[k]] = action[k]*act_delta[k] + act_mean[k]; mushroom's
- *                                  `self._data.ctrl[self._action_indices] = action`)                                  */
+ *                                  `self._data.ctrl[self._action_indices] = action`),
+ *                                  grf_group[n_grf_geom]: per geom -1 = none, k < n_grf = member of foot group k,
+ *                                  LS_GRF_FLOOR = floor (collision_groups of the env; base.py:667-679, unitreeA1.py:223-227,551-562) */
 
 enum { TKR_REWARD_P0 = 0, TKR_REWARD_P1, TKR_HEADER_LEN = 8 };
 /* real arrays after the header: act_mean[nu], act_delta[nu], done_lo[n_done], done_hi[n_done],
  *                               traj_table[n_traj][traj_len][nq + nv + n_goal]                      */
 
 /* obs_src_type */
-enum { LS_OBS_QPOS = 0, LS_OBS_QVEL = 1, LS_OBS_GOAL = 2 };
+enum { LS_OBS_QPOS = 0, LS_OBS_QVEL = 1, LS_OBS_GOAL = 2,
+       LS_OBS_GRF = 3 /* idx = 3*group + component: mean over the sub-steps of the control step of the contact-frame force
+                         (normal, tangent1, tangent2: mj_contactForce) of the FIRST floor contact of the group, / 1000
+                         (base.py:94-98,596-599,623-631; 0 in the reset observation) */ };
+#define LS_GRF_FLOOR 127
+#define LS_MAX_GRF 4
 /* reward types (utils/reward.py) */
 enum {
   LS_REWARD_NONE = 0,            /* NoReward :34 */

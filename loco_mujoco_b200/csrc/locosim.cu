@@ -79,6 +79,7 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
       float v;
       if (ty == LS_OBS_QPOS) v = (idx == t.recenter0 || idx == t.recenter1) ? 0.0f : row[idx];
       else if (ty == LS_OBS_QVEL) v = row[nv + idx];
+      else if (ty == LS_OBS_GRF) v = 0.0f;           // the running mean of the foot forces is reset with the episode
       else v = row[2 * nv + idx];
       obs[(size_t)env * t.obs_dim + k] = v;
     }
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
   __syncwarp();
   init_workspace(ms, e);
   if (lane == 0) e.iter_sum = 0;
+  if (lane < 3 * LS_MAX_GRF) e.grf[lane] = 0;
   // reward depends on the *previous* observation only (utils/reward.py via base.py:170-176): evaluate it now
   float rew = 0;
   if (t.reward_type == LS_REWARD_TARGET_VELOCITY) { float d = obs_value(t, e, t.ri[0]) - t.rp[0]; rew = expf(-d * d); }
@@ -135,9 +137,9 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
   // ---- physics ----
   if (sync_substeps) {
     // keep the warps of a block in the same phase: they then share instruction-cache lines
-    for (int k = 0; k < t.n_substeps; k++) { if (k % sync_substeps == 0) __syncthreads(); physics_substeps(ms, e, so, 1); }
+    for (int k = 0; k < t.n_substeps; k++) { if (k % sync_substeps == 0) __syncthreads(); physics_substeps(ms, e, so, 1, t.grf_group, t.n_grf); }
   } else {
-    physics_substeps(ms, e, so, t.n_substeps);
+    physics_substeps(ms, e, so, t.n_substeps, t.grf_group, t.n_grf);
   }
 
   if (ghost) return;
@@ -331,7 +333,7 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   if (n_envs <= 0) return fail("n_envs must be positive");
   std::string err = parse_model(h->hm, mi, nmi, mr, nmr);
   if (!err.empty()) return fail(err);
-  err = parse_task(h->ht, h->hm.nu, h->hm.nv, ti, nti, tr, ntr);
+  err = parse_task(h->ht, h->hm.nu, h->hm.nv, h->hm.ng, ti, nti, tr, ntr);
   if (!err.empty()) return fail(err);
   if (h->hm.nu > h->hm.nv) return fail("nu > nv");
   h->device = device; h->n_envs = n_envs; h->seed = seed; h->env_off = env_off;

@@ -2,6 +2,6 @@
 // NV / NB / NG / MAXOBS are capacities (model sizes must be <=), MAXCON / MAXROW bound the active contact set.
 // CONE: 0 pyramidal, 1 elliptic (mjModel.opt.cone); RK4: 0 Euler, 1 RK4 (mjModel.opt.integrator).
 #pragma once
-struct CfgEllEuler { enum { NV = 18, NB = 14, NG = 40,  MAXCON = 16, MAXROW = 64, MAXOBS = 40, CONE = 1, RK4 = 0 }; };  // UnitreeA1
-struct CfgPyrEuler { enum { NV = 18, NB = 14, NG = 56,  MAXCON = 16, MAXROW = 64, MAXOBS = 40, CONE = 0, RK4 = 0 }; };  // Talos
-struct CfgPyrRK4   { enum { NV = 19, NB = 14, NG = 104, MAXCON = 16, MAXROW = 64, MAXOBS = 40, CONE = 0, RK4 = 1 }; };  // Atlas, HumanoidTorque
+struct CfgEllEuler { enum { NV = 18, NB = 14, NG = 40,  MAXCON = 16, MAXROW = 64, MAXOBS = 64, CONE = 1, RK4 = 0 }; };  // UnitreeA1
+struct CfgPyrEuler { enum { NV = 18, NB = 14, NG = 56,  MAXCON = 16, MAXROW = 64, MAXOBS = 64, CONE = 0, RK4 = 0 }; };  // Talos
+struct CfgPyrRK4   { enum { NV = 19, NB = 14, NG = 104, MAXCON = 16, MAXROW = 64, MAXOBS = 64, CONE = 0, RK4 = 1 }; };  // Atlas, HumanoidTorque

@@ -88,8 +88,9 @@ struct DevModel {
 
 struct DevTask {
   int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter0, recenter1, ri[4], use_absorbing;
+  int n_grf;                      // foot-force groups (use_foot_forces), 0 = off
   float rp[2];
-  const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx;
+  const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx, *grf_group;
   const float *act_mean, *act_delta, *done_lo, *done_hi, *table;
 };
 
@@ -156,6 +157,7 @@ struct alignas(16) EnvS {
   float coneU[8], coneS[8];
   // task
   float goal[4];
+  float grf[3 * LS_MAX_GRF];   // use_foot_forces: per foot group, contact-frame force summed over the sub-steps
   const float* prm;        // this env's row of the parameter pool
 };
 #define PRM(field) (e.prm + m.po_##field)
@@ -1554,6 +1556,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
   // fp32 termination: scaled gradient below tolerance, or a Newton step with exact line search that did not lower the
   // cost any more (the cost value has reached its fp32 resolution; further iterations only move noise).
   bool active = nefc > 0 && so.max_iter > 0 && scale * sqrtf(gn) >= so.tolerance;
+  bool force_dirty = false;   // ls_prepare borrows r_force / r_aref of the elliptic rows
   while (BLOCK_ANY(so.sync_iters, active)) {
     // (warps whose env has converged keep passing the same barriers until the whole block is done)
     if (active) make_hessian(ms, e);
@@ -1564,7 +1567,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
       PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
       SYNC();
       alpha = line_search(ms, e, so, gauss, scale);
-      if (alpha == 0) active = false;
+      if (alpha == 0) { active = false; force_dirty = (C::CONE == 1); }
     }
     BLOCK_SYNC(so.sync_phases & 128);
     if (active) {
@@ -1582,6 +1585,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
       active = iter < so.max_iter && scale * sqrtf(gn) >= so.tolerance && cost < oldcost;
     }
   }
+  if (force_dirty) cost = update_constraint(ms, e, &gauss);   // rare: restore efc_force for contact_forces()
   LANE0 { e.solver_iter = iter; e.iter_sum += iter; }
   PAR_FOR(i, nv) e.qacc_ws[i] = e.qacc[i];
   SYNC();
@@ -1660,12 +1664,63 @@ LS_FN void rk4_step(const int ms, EnvS<C>& e, const SolverOpts so) {
   SYNC();
 }
 
+// use_foot_forces (base.py:623-631,656-679 -> mushroom _get_collision_force -> mj_contactForce): per foot group the
+// contact-frame force (normal, tangent 1, tangent 2) of the FIRST contact between the floor and a geom of the group, in
+// contact-list order, from the constraint forces of the sub-step's (last) forward evaluation; summed over sub-steps.
 template <class C>
-LS_FN void physics_substeps(const int ms, EnvS<C>& e, const SolverOpts so, int nsub) {
+LS_FN void contact_forces(const int ms, EnvS<C>& e, const int* grf_group, int n_grf) {
+  const int nunit = e.nunit, ncon = e.ncon;
+  // lane ci looks at contact ci (ncon <= MAXCON <= 32); the first match of every group is a warp-wide minimum.
+  // (A scalar "scan the list until the first match" loop was miscompiled by nvcc 12.9 for the pyramidal
+  //  instantiations: the membership test read contact ci+1 while the forces were taken from contact ci.)
+  int ga = -1, gb = -1;
+  const int lane = LS_LANE;
+#ifdef LS_EMULATE
+  for (int k = 0; k < n_grf; k++) {
+    int first = ncon;
+    for (int ci = ncon - 1; ci >= 0; ci--) {
+      ga = grf_group[e.con_g1[ci]]; gb = grf_group[e.con_g2[ci]];
+      if ((ga == LS_GRF_FLOOR && gb == k) || (gb == LS_GRF_FLOOR && ga == k)) first = ci;
+    }
+#else
+  if (lane < ncon) { ga = grf_group[e.con_g1[lane]]; gb = grf_group[e.con_g2[lane]]; }
+  for (int k = 0; k < n_grf; k++) {
+    const bool hit = (ga == LS_GRF_FLOOR && gb == k) || (gb == LS_GRF_FLOOR && ga == k);
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    const int first = mask ? __ffs(mask) - 1 : ncon;
+#endif
+    if (first >= ncon) continue;
+    LANE0 {
+      const int ci = first, r0 = nunit + e.con_row[ci], dim = e.con_dim[ci];
+      float f0 = 0, f1 = 0, f2 = 0;
+      if (dim == 1) f0 = e.r_force[r0];
+      else if (C::CONE == 1) {
+        f0 = e.r_force[r0]; f1 = e.r_force[r0 + 1]; f2 = e.r_force[r0 + 2];
+      } else {
+        // mju_decodePyramid: normal = sum of the edge forces, tangent_i = (f_2i - f_2i+1) * mu_i
+        const int ne = 2 * (dim - 1);
+        NOUNROLL for (int j = 0; j < ne; j++) f0 += e.r_force[r0 + j];
+        f1 = (e.r_force[r0] - e.r_force[r0 + 1]) * e.con_fri[ci][0];
+        if (dim > 2) f2 = (e.r_force[r0 + 2] - e.r_force[r0 + 3]) * e.con_fri[ci][1];
+      }
+#if !defined(LS_EMULATE) && defined(LS_DEBUG_GRF)
+      if ((int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) == LS_DEBUG_GRF)
+        printf("grf k %d ci %d of %d g %d-%d dim %d r0 %d -> %.3f %.3f %.3f\n", k, ci, ncon, e.con_g1[ci], e.con_g2[ci], dim, r0,
+               f0, f1, f2);
+#endif
+      e.grf[3 * k] += f0; e.grf[3 * k + 1] += f1; e.grf[3 * k + 2] += f2;
+    }
+  }
+  SYNC();
+}
+
+template <class C>
+LS_FN void physics_substeps(const int ms, EnvS<C>& e, const SolverOpts so, int nsub, const int* grf_group, int n_grf) {
   const DevModel& m = c_models[ms];
   for (int k = 0; k < nsub; k++) {
     forward(ms, e, so);
     if constexpr (C::RK4 == 1) rk4_step(ms, e, so); else euler_step(ms, e);
+    if (n_grf > 0) contact_forces(ms, e, grf_group, n_grf);
   }
 }
 
@@ -1676,6 +1731,7 @@ template <class C>
 LS_DEV float obs_value(const DevTask& t, const EnvS<C>& e, int k) {
   int idx = t.obs_src_idx[k];
   int ty = t.obs_src_type[k];
+  if (ty == LS_OBS_GRF) return e.grf[idx] * (1.0f / (1000.0f * (float)t.n_substeps));
   return ty == LS_OBS_QPOS ? e.qpos[idx] : (ty == LS_OBS_QVEL ? e.qvel[idx] : e.goal[idx]);
 }
 
@@ -1690,5 +1746,6 @@ LS_FN void reset_env(const int ms, const DevTask& t, EnvS<C>& e, int traj_no, in
     e.qpos[i] = q; e.qvel[i] = row[nv + i]; e.qacc_ws[i] = 0; e.qacc[i] = 0;
   }
   PAR_FOR(k, t.n_goal) e.goal[k] = row[2 * nv + k];
+  PAR_FOR(k, 3 * LS_MAX_GRF) e.grf[k] = 0;     // mean_grf is reset with the episode (reset observation: zeros)
   SYNC();
 }

@@ -12,6 +12,7 @@ struct EmuBase {
   HostModel hm;
   DevModel m;
   SolverOpts so;
+  std::vector<int> grf_group; int n_grf = 0;
   virtual ~EmuBase() {}
   virtual void reset(const double* q, const double* v) = 0;
   virtual void step(const double* ctrl, int nsub) = 0;
@@ -20,6 +21,8 @@ struct EmuBase {
   virtual void set_ws(const double* w) = 0;
   virtual int info(int k) = 0;
   virtual void bind_prm() = 0;
+  virtual void contact(int k, double* o) = 0;
+  virtual void grf(double* o, int clear) = 0;
 };
 template <class C>
 struct EmuT : EmuBase {
@@ -31,7 +34,7 @@ struct EmuT : EmuBase {
   void step(const double* ctrl, int nsub) override {
     for (int i = 0; i < m.nu; i++) e.ctrl[i] = (float)ctrl[i];
     c_models[0] = m;
-    physics_substeps(0, e, so, nsub);
+    physics_substeps(0, e, so, nsub, grf_group.data(), n_grf);
   }
   void fwd(const double* ctrl) override {
     for (int i = 0; i < m.nu; i++) e.ctrl[i] = (float)ctrl[i];
@@ -48,6 +51,12 @@ struct EmuT : EmuBase {
   }
   void set_ws(const double* w) override { for (int i = 0; i < m.nv; i++) e.qacc_ws[i] = (float)w[i]; }
   int info(int k) override { return k == 0 ? e.ncon : (k == 1 ? e.nefc : e.solver_iter); }
+  void contact(int k, double* o) override {
+    o[0] = e.con_g1[k]; o[1] = e.con_g2[k]; o[2] = e.con_dim[k]; o[3] = e.con_dist[k];
+    int r0 = e.nunit + e.con_row[k], dim = e.con_dim[k];
+    for (int j = 0; j < 8; j++) o[4 + j] = (j < (C::CONE == 1 || dim == 1 ? dim : 2 * (dim - 1))) ? e.r_force[r0 + j] : 0.0;
+  }
+  void grf(double* o, int clear) override { for (int k = 0; k < 3 * LS_MAX_GRF; k++) { o[k] = e.grf[k]; if (clear) e.grf[k] = 0; } }
   void bind_prm() override { e.prm = hm.default_row.data(); c_models[0] = m; init_workspace(0, e); }
 };
 
@@ -79,6 +88,9 @@ void emu_get_qacc(EmuBase* s, double* qacc) { s->get(nullptr, nullptr, qacc, nul
 void emu_get_ws(EmuBase* s, double* w) { s->get(nullptr, nullptr, nullptr, w); }
 void emu_set_ws(EmuBase* s, const double* w) { s->set_ws(w); }
 int emu_ncon(EmuBase* s) { return s->info(0); }
+void emu_contact(EmuBase* s, int k, double* o) { s->contact(k, o); }
+void emu_set_grf(EmuBase* s, const int* group, int ng, int n_grf) { s->grf_group.assign(group, group + ng); s->n_grf = n_grf; }
+void emu_get_grf(EmuBase* s, double* o, int clear) { s->grf(o, clear); }
 int emu_nefc(EmuBase* s) { return s->info(1); }
 int emu_iter(EmuBase* s) { return s->info(2); }
 int emu_sizeof_env(int which) {

@@ -133,10 +133,11 @@ struct HostTask {
   std::vector<int> ints;
   std::vector<float> reals;
   int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter0, recenter1, ri[4], use_absorbing;
+  int n_grf = 0, n_grf_geom = 0;
   float rp[2];
 };
 
-static inline std::string parse_task(HostTask& t, int nu, int nv, const int* ti, int nti, const double* tr, int ntr) {
+static inline std::string parse_task(HostTask& t, int nu, int nv, int ng, const int* ti, int nti, const double* tr, int ntr) {
   if (nti < TKI_HEADER_LEN || ti[TKI_MAGIC] != LOCOSIM_TASK_MAGIC) return "bad TaskSpec magic";
   if (ti[TKI_VERSION] != LOCOSIM_TASK_VERSION) return "TaskSpec version mismatch";
   t.obs_dim = ti[TKI_OBS_DIM]; t.n_done = ti[TKI_N_DONE]; t.reward_type = ti[TKI_REWARD_TYPE];
@@ -144,11 +145,14 @@ static inline std::string parse_task(HostTask& t, int nu, int nv, const int* ti,
   t.recenter0 = ti[TKI_RECENTER0]; t.recenter1 = ti[TKI_RECENTER1];
   for (int k = 0; k < 4; k++) t.ri[k] = ti[TKI_REWARD_I0 + k];
   t.use_absorbing = ti[TKI_USE_ABSORBING];
+  t.n_grf = ti[TKI_N_GRF]; t.n_grf_geom = ti[TKI_N_GRF_GEOM];
+  if (t.n_grf < 0 || t.n_grf > LS_MAX_GRF) return "n_grf out of range";
   t.rp[0] = (float)tr[TKR_REWARD_P0]; t.rp[1] = (float)tr[TKR_REWARD_P1];
-  size_t ni = 2 * (size_t)t.obs_dim + t.n_done + (size_t)nu;
+  size_t ni = 2 * (size_t)t.obs_dim + t.n_done + (size_t)nu + (size_t)t.n_grf_geom;
   size_t nr = 2 * (size_t)nu + 2 * (size_t)t.n_done + (size_t)t.n_traj * t.traj_len * (2 * nv + t.n_goal);
   if ((size_t)nti != TKI_HEADER_LEN + ni || (size_t)ntr != TKR_HEADER_LEN + nr) return "TaskSpec size mismatch";
   if (t.n_goal > 4) return "n_goal > 4";
+  if (t.n_grf > 0 && t.n_grf_geom != ng) return "grf_group length != ngeom";
   t.ints.assign(ti + TKI_HEADER_LEN, ti + nti);
   t.reals.resize(nr);
   for (size_t i = 0; i < nr; i++) t.reals[i] = (float)tr[TKR_HEADER_LEN + i];
@@ -159,9 +163,10 @@ static inline void bind_task(DevTask& d, const HostTask& t, int nu, const int* i
   d.obs_dim = t.obs_dim; d.n_done = t.n_done; d.reward_type = t.reward_type; d.n_substeps = t.n_substeps;
   d.n_traj = t.n_traj; d.traj_len = t.traj_len; d.n_goal = t.n_goal; d.recenter0 = t.recenter0; d.recenter1 = t.recenter1;
   for (int k = 0; k < 4; k++) d.ri[k] = t.ri[k];
-  d.use_absorbing = t.use_absorbing; d.rp[0] = t.rp[0]; d.rp[1] = t.rp[1];
+  d.use_absorbing = t.use_absorbing; d.rp[0] = t.rp[0]; d.rp[1] = t.rp[1]; d.n_grf = t.n_grf;
   const int* ip = ibase;
-  d.obs_src_type = ip; ip += t.obs_dim; d.obs_src_idx = ip; ip += t.obs_dim; d.done_obs_idx = ip; ip += t.n_done; d.act_idx = ip;
+  d.obs_src_type = ip; ip += t.obs_dim; d.obs_src_idx = ip; ip += t.obs_dim; d.done_obs_idx = ip; ip += t.n_done; d.act_idx = ip; ip += nu;
+  d.grf_group = ip;
   const float* rp = rbase;
   d.act_mean = rp; rp += nu; d.act_delta = rp; rp += nu; d.done_lo = rp; rp += t.n_done; d.done_hi = rp; rp += t.n_done;
   d.table = rp;

@@ -23,7 +23,8 @@ from itertools import product
 import numpy as np
 
 from .. import mjcf, modelpack
-from ..task import (TaskSpec, OBS_QPOS, OBS_QVEL, OBS_GOAL, REWARD_NONE, REWARD_TARGET_VELOCITY, REWARD_POS)
+from ..task import (TaskSpec, OBS_QPOS, OBS_QVEL, OBS_GOAL, OBS_GRF, GRF_FLOOR, REWARD_NONE, REWARD_TARGET_VELOCITY,
+                    REWARD_POS)
 from ..trajectory import Trajectory
 from ..utils.reward import NoReward, CustomReward, TargetVelocityReward, PosReward
 
@@ -142,8 +143,9 @@ class LocoEnv:
         self._xml_handles = xml_handles
         if len(xml_handles) != 1:
             raise NotImplementedError("multi-model environments (carry tasks with several weights) are not built yet")
-        if use_foot_forces:
-            raise NotImplementedError("use_foot_forces=True is not built yet (SURVEY.md 8(f) item 2)")
+        # use_foot_forces (base.py:93-98 of the reference): n_intermediate_steps x mj_step(1) with a contact-force hook
+        # after each one. The engine always runs n_substeps physics steps per control step; dt is unchanged.
+        self._collision_groups = list(collision_groups) if collision_groups else []
         self._domain_rand_config = domain_randomization_config
         self._domain_rand_pool_size = viewer_params.pop("domain_randomization_pool_size", 64)
         self._domain_rand = None
@@ -293,9 +295,12 @@ class LocoEnv:
         recenter = [self._model.joint_id(spec[0][1]), self._model.joint_id(spec[1][1])]
         if self.trajectories is None:
             raise ValueError("the CUDA engine needs trajectory data for resets (pass traj_params)")
+        n_grf, grf_group = self._grf_spec()
+        types = list(types) + [OBS_GRF] * (3 * n_grf)           # the mean ground forces are the last entries
+        idxs = list(idxs) + list(range(3 * n_grf))
         return TaskSpec(types, idxs, done_terms, rtype, rints, rparams, self.norm_act_mean, self.norm_act_delta,
                         self._n_substeps, self._reset_table(), self._n_goal(), recenter, self._use_absorbing_states,
-                        act_idx=self._action_indices)
+                        act_idx=self._action_indices, n_grf=n_grf, grf_group=grf_group)
 
     def domain_randomization_pool(self):
         """[K, P] parameter pool: K consecutive randomised recompilations of the model (see domain_randomization.py)."""
@@ -410,7 +415,37 @@ class LocoEnv:
         return len([k for k in keys if k.startswith("q_")]), len([k for k in keys if k.startswith("dq_")])
 
     def _get_observation_space(self):
-        return self.info.observation_space.low[2:], self.info.observation_space.high[2:]
+        lo, hi = self.info.observation_space.low[2:], self.info.observation_space.high[2:]
+        return self._append_grf_space(lo, hi)
+
+    def _append_grf_space(self, lo, hi):
+        if self._use_foot_forces:      # base.py:576-580
+            n = self._get_grf_size()
+            lo, hi = np.concatenate([lo, -np.ones(n) * np.inf]), np.concatenate([hi, np.ones(n) * np.inf])
+        return lo, hi
+
+    @staticmethod
+    def _get_grf_size():
+        return 12
+
+    def _grf_group_names(self):
+        """Foot groups in the order of `_get_ground_forces` (base.py:667-679)."""
+        return ["foot_r", "front_foot_r", "foot_l", "front_foot_l"]
+
+    def _grf_spec(self):
+        """(n_groups, per-geom group id) for the engine; the floor group is matched against every foot group."""
+        if not self._use_foot_forces:
+            return 0, None
+        groups = dict(self._collision_groups)
+        names = self._grf_group_names()
+        assert 3 * len(names) == self._get_grf_size()
+        gid = -np.ones(self._model.ngeom, dtype=np.int32)
+        for g in groups["floor"]:
+            gid[self._model.geom_id(g)] = GRF_FLOOR
+        for k, name in enumerate(names):
+            for g in groups[name]:
+                gid[self._model.geom_id(g)] = k
+        return len(names), gid
 
     def _create_observation(self, obs):
         return np.concatenate([obs[2:]]).flatten()

@@ -21,6 +21,18 @@ _ARM_MOT = ["shoulder_flex", "shoulder_add", "shoulder_rot", "elbow_flex", "pro_
 
 
 class BaseHumanoid(LocoEnv):
+    def _collision_groups_spec(self):
+        if self._use_box_feet:      # base_humanoid.py:106-114
+            return [("floor", ["floor"]), ("foot_r", ["foot_box_r"]), ("foot_l", ["foot_box_l"])]
+        return [("floor", ["floor"]), ("foot_r", ["r_foot"]), ("front_foot_r", ["r_bofoot"]), ("foot_l", ["l_foot"]),
+                ("front_foot_l", ["l_bofoot"])]
+
+    def _get_grf_size(self):        # base_humanoid.py:182-191
+        return 6 if self._use_box_feet else 12
+
+    def _grf_group_names(self):     # base_humanoid.py:193-209
+        return ["foot_r", "foot_l"] if self._use_box_feet else ["foot_r", "front_foot_r", "foot_l", "front_foot_l"]
+
     def __init__(self, use_muscles=False, use_box_feet=True, disable_arms=True, alpha_box_feet=0.5, **kwargs):
         if use_muscles:
             raise NotImplementedError("muscle actuation (tendons / <muscle>) is out of scope")
@@ -44,7 +56,7 @@ class BaseHumanoid(LocoEnv):
                     h = self._reorient_arms(h)
         else:
             h = None
-        super().__init__(h, action_spec, observation_spec, **kwargs)
+        super().__init__(h, action_spec, observation_spec, self._collision_groups_spec(), **kwargs)
 
     def create_dataset(self, ignore_keys=None):
         if ignore_keys is None:

@@ -42,7 +42,12 @@ class BaseRobotHumanoid(LocoEnv):
             xml_handle = self._delete_from_xml_handle(xml_handle, joints_to_remove, motors_to_remove, equ)
         else:
             xml_handle = None
-        super().__init__(xml_handle, action_spec, observation_spec, **kwargs)
+        super().__init__(xml_handle, action_spec, observation_spec, self._collision_groups_spec(), **kwargs)
+
+    def _collision_groups_spec(self):
+        # atlas.py:292-296 (4 groups, base-class _get_ground_forces)
+        return [("floor", ["floor"]), ("foot_r", ["right_foot_back"]), ("front_foot_r", ["right_foot_front"]),
+                ("foot_l", ["left_foot_back"]), ("front_foot_l", ["left_foot_front"])]
 
     def _modify_xml(self, xml_handle):
         return xml_handle
@@ -131,6 +136,16 @@ class Talos(BaseRobotHumanoid):
         super().__init__(disable_arms=disable_arms, disable_back_joint=disable_back_joint, hold_weight=hold_weight,
                          weight_mass=weight_mass, **kwargs)
 
+    def _collision_groups_spec(self):
+        return [("floor", ["floor"]), ("foot_r", ["right_foot"]), ("foot_l", ["left_foot"])]
+
+    @staticmethod
+    def _get_grf_size():
+        return 6
+
+    def _grf_group_names(self):
+        return ["foot_r", "foot_l"]
+
     def _modify_xml(self, xml_handle):
         if self._disable_arms:
             # arms are kept fixed in a reoriented pose (talos.py:503-521)
@@ -187,6 +202,16 @@ class UnitreeH1(BaseRobotHumanoid):
     def __init__(self, disable_arms=True, disable_back_joint=False, hold_weight=False, weight_mass=None, **kwargs):
         super().__init__(disable_arms=disable_arms, disable_back_joint=disable_back_joint, hold_weight=hold_weight,
                          weight_mass=weight_mass, **kwargs)
+
+    def _collision_groups_spec(self):
+        return [("floor", ["floor"]), ("foot_r", ["right_foot"]), ("foot_l", ["left_foot"])]
+
+    @staticmethod
+    def _get_grf_size():
+        return 6
+
+    def _grf_group_names(self):
+        return ["foot_r", "foot_l"]
 
     def _modify_xml(self, xml_handle):
         if self._disable_arms:

@@ -49,7 +49,9 @@ class UnitreeA1(LocoEnv):
             #  unitreeA1.py:755-776: visualisation only, no geoms, no inertia -> not part of the physics model)
         else:
             xml_handle = None
-        super().__init__(xml_handle, action_spec, observation_spec, **kwargs)
+        collision_groups = [("floor", ["floor"]), ("foot_FR", ["FR_foot"]), ("foot_FL", ["FL_foot"]),
+                            ("foot_RR", ["RR_foot"]), ("foot_RL", ["RL_foot"])]      # unitreeA1.py:223-227
+        super().__init__(xml_handle, action_spec, observation_spec, collision_groups, **kwargs)
 
     # -- observation layout -------------------------------------------------------------------------------
     def _get_observation_space(self):
@@ -57,7 +59,10 @@ class UnitreeA1(LocoEnv):
         lo, hi = self.info.observation_space.low[2:], self.info.observation_space.high[2:]
         lo = np.concatenate([lo[:dir_arrow_idx[0]], [-1, -1], [-np.inf]])
         hi = np.concatenate([hi[:dir_arrow_idx[0]], [1, 1], [np.inf]])
-        return lo, hi
+        return self._append_grf_space(lo, hi)        # unitreeA1.py:432-439
+
+    def _grf_group_names(self):
+        return ["foot_FL", "foot_FR", "foot_RL", "foot_RR"]      # unitreeA1.py:551-562
 
     def _obs_sources(self):
         spec = self.obs_helper.observation_spec

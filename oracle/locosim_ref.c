@@ -1369,9 +1369,10 @@ void ref_step(RefSim* s, const double* ctrl, int nsub) {
 /* ---------------------------------------------------------------------------------------------------- */
 typedef struct {
   int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter[2], ri[4], use_absorbing;
+  int n_grf, n_grf_geom;
   double rp[2];
   int *ibuf; double* rbuf;
-  const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx;
+  const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx, *grf_group;
   const double *act_mean, *act_delta, *done_lo, *done_hi, *table;
 } Task;
 
@@ -1384,10 +1385,13 @@ static int task_load(Task* t, int nu, int nv, const int* ti, int nti, const doub
   t->recenter[0] = ti[TKI_RECENTER0]; t->recenter[1] = ti[TKI_RECENTER1];
   for (int k = 0; k < 4; k++) t->ri[k] = ti[TKI_REWARD_I0 + k];
   t->use_absorbing = ti[TKI_USE_ABSORBING];
+  t->n_grf = ti[TKI_N_GRF]; t->n_grf_geom = ti[TKI_N_GRF_GEOM];
+  if (t->n_grf < 0 || t->n_grf > LS_MAX_GRF) return -3;
   t->rp[0] = tr[TKR_REWARD_P0]; t->rp[1] = tr[TKR_REWARD_P1];
   const int* ip = t->ibuf + TKI_HEADER_LEN;
   t->obs_src_type = ip; ip += t->obs_dim; t->obs_src_idx = ip; ip += t->obs_dim; t->done_obs_idx = ip; ip += t->n_done;
   t->act_idx = ip; ip += nu;
+  t->grf_group = ip; ip += t->n_grf_geom;
   const double* rp = t->rbuf + TKR_HEADER_LEN;
   t->act_mean = rp; rp += nu; t->act_delta = rp; rp += nu; t->done_lo = rp; rp += t->n_done; t->done_hi = rp; rp += t->n_done;
   t->table = rp; rp += (long)t->n_traj * t->traj_len * (2 * nv + t->n_goal);
@@ -1395,7 +1399,7 @@ static int task_load(Task* t, int nu, int nv, const int* ti, int nti, const doub
   return 0;
 }
 
-struct RefEnv { RefSim* sim; Task task; double goal[8]; double obs[128]; };
+struct RefEnv { RefSim* sim; Task task; double goal[8]; double obs[128]; double grf[3 * LS_MAX_GRF]; };
 
 RefEnv* refenv_create(const int* ints, int n_ints, const double* reals, int n_reals, const int* ti, int nti,
                       const double* tr, int ntr) {
@@ -1417,6 +1421,7 @@ static void build_obs(const RefEnv* e, double* obs) {
     switch (t->obs_src_type[k]) {
       case LS_OBS_QPOS: obs[k] = e->sim->qpos[idx]; break;
       case LS_OBS_QVEL: obs[k] = e->sim->qvel[idx]; break;
+      case LS_OBS_GRF: obs[k] = e->grf[idx] / (1000.0 * t->n_substeps); break;   /* mean_grf.mean / 1000 (base.py:596-599) */
       default: obs[k] = e->goal[idx]; break;
     }
   }
@@ -1451,6 +1456,7 @@ void refenv_reset_to(RefEnv* e, int traj_no, int step_no, double* obs) {
   if (t->recenter[1] >= 0) qpos[t->recenter[1]] = 0;
   ref_reset(e->sim, qpos, row + nv);
   for (int k = 0; k < t->n_goal; k++) e->goal[k] = row[2 * nv + k];
+  memset(e->grf, 0, sizeof(e->grf));   /* RunningAveragedWindow reset with the episode */
   build_obs(e, e->obs);
   if (obs) memcpy(obs, e->obs, sizeof(double) * t->obs_dim);
 }
@@ -1459,7 +1465,26 @@ void refenv_step(RefEnv* e, const double* action, double* obs, double* reward, i
   int nu = e->sim->m.nu;
   double ctrl[MAXNV], cur[128];
   for (int i = 0; i < nu; i++) ctrl[t->act_idx[i]] = action[i] * t->act_delta[i] + t->act_mean[i];
-  ref_step(e->sim, ctrl, t->n_substeps);
+  if (t->n_grf == 0) ref_step(e->sim, ctrl, t->n_substeps);
+  else {
+    /* use_foot_forces (base.py:94-98,623-631): n_intermediate_steps x mj_step(1), after each one the contact-frame force
+       of the FIRST floor contact of every foot group (mushroom _get_collision_force -> mj_contactForce); the window
+       of the running mean is exactly the n_substeps samples of this control step */
+    memset(e->grf, 0, sizeof(e->grf));
+    for (int k = 0; k < t->n_substeps; k++) {
+      ref_step(e->sim, ctrl, 1);
+      for (int g = 0; g < t->n_grf; g++) {
+        for (int ci = 0; ci < e->sim->ncon; ci++) {
+          int a = t->grf_group[e->sim->con[ci].geom1], b = t->grf_group[e->sim->con[ci].geom2];
+          if (!((a == LS_GRF_FLOOR && b == g) || (b == LS_GRF_FLOOR && a == g))) continue;
+          double o[16];
+          ref_get_contact(e->sim, ci, o);
+          for (int c = 0; c < 3; c++) e->grf[3 * g + c] += o[10 + c];
+          break;
+        }
+      }
+    }
+  }
   build_obs(e, cur);
   int ab = t->use_absorbing ? has_fallen(t, cur) : 0;
   if (reward) *reward = reward_fn(t, e->obs);

@@ -63,8 +63,29 @@ def _near_threshold(env, obs, eps=1e-3):
 
 @pytest.mark.parametrize("task", GOLDEN_TASKS)
 def test_batched_steps_match_oracle(oracle, bundled_only, task):
-    n, n_steps = (96, 3) if task.startswith("UnitreeA1") else (48, 2)
-    env = make_env(task, num_envs=n, seed=5)
+    _batched_vs_oracle(oracle, task)
+
+
+@pytest.mark.parametrize("task", ["UnitreeA1.simple", "HumanoidTorque.run", "Atlas.walk", "Talos.walk"])
+def test_foot_forces_match_oracle(oracle, bundled_only, task):
+    """use_foot_forces=True: the mean per-foot contact forces (/1000) are appended to the observation
+    (base.py:584-604,623-631; not pinned by any reference golden, checked against the oracle's mj_contactForce decode)."""
+    env = _batched_vs_oracle(oracle, task, n_steps=4, use_foot_forces=True)
+    n_grf = env._get_grf_size()
+    assert env.info.observation_space.shape[0] == env.task_spec().obs_dim
+    obs = env.reset()
+    assert float(obs[:, -n_grf:].abs().max()) == 0.0            # mean_grf is reset with the episode
+    seen = 0.0
+    for _ in range(10):
+        obs, _, _, _ = env.step(torch.zeros((env.num_envs, env.info.action_space.shape[0]), device="cuda"))
+        seen = max(seen, float(obs[:, -n_grf:].abs().max()))
+    assert seen > 1e-3, "no ground reaction force ever observed"
+
+
+def _batched_vs_oracle(oracle, task, n_steps=None, **kw):
+    n, default_steps = (96, 3) if task.startswith("UnitreeA1") else (48, 2)
+    n_steps = default_steps if n_steps is None else n_steps
+    env = make_env(task, num_envs=n, seed=5, **kw)
     eng = env._get_engine()
     mb, tb = blobs(env)
     rng = np.random.RandomState(0)
@@ -92,6 +113,7 @@ def test_batched_steps_match_oracle(oracle, bundled_only, task):
                 alive[i] = False
     for oe in oes:
         oe.close()
+    return env
 
 
 def test_sharded_envs_equal_single_batch(bundled_only):
