@@ -39,7 +39,7 @@ int locosim_obs_dim(const locosim_t* h);
 int locosim_action_dim(const locosim_t* h);
 int locosim_nq(const locosim_t* h);
 
-/* Newton-solver controls of the fp32 engine (defaults: tolerance 1e-5, ls_tolerance 0.01, max_iter 20, ls_iter 16) */
+/* Newton-solver controls of the fp32 engine (defaults: tolerance 1e-5, ls_tolerance 0.1, max_iter 20, ls_iter 16) */
 int locosim_set_solver(locosim_t* h, float tolerance, float ls_tolerance, int max_iter, int ls_iter);
 
 /* Replaces LocoEnv.reset() (base.py:178-203 -> setup :205-241 -> Trajectory.reset_trajectory trajectory.py:236-273

@@ -347,7 +347,7 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   else if (cfg_fits<CfgPyrEuler>(h->hm, h->ht)) h->cfg = 1;
   else if (cfg_fits<CfgPyrRK4>(h->hm, h->ht)) h->cfg = 2;
   else return fail("no compiled configuration fits this model (cone / integrator / sizes: see locosim_config.h)");
-  h->so.tolerance = 1e-5f; h->so.ls_tolerance = 0.01f; h->so.ls_iter = 16;
+  h->so.tolerance = 1e-5f; h->so.ls_tolerance = 0.1f; h->so.ls_iter = 16;
   h->so.max_iter = h->hm.iterations < 20 ? h->hm.iterations : 20;
   auto up = [&](void** dst, const void* src, size_t bytes) -> bool {
     if (cudaMalloc(dst, bytes ? bytes : 4) != cudaSuccess) return false;

@@ -1388,8 +1388,14 @@ LS_FN void ls_prepare(const int ms, EnvS<C>& e) {
   SYNC();
 }
 
+#if defined(LS_EMULATE)
+static long g_ls_evals = 0, g_ls_searches = 0;
+#endif
 template <class C>
 LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alpha) {
+#if defined(LS_EMULATE)
+  g_ls_evals++;
+#endif
   const DevModel& m = c_models[ms];
   const int nefc = e.nefc;
   float c = 0, d1 = 0, d2 = 0;
@@ -1443,10 +1449,10 @@ LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alp
 }
 
 template <class C>
-LS_FN float line_search(const int ms, EnvS<C>& e, const SolverOpts so, float gauss, float scale) {
+LS_FN float line_search(const int ms, EnvS<C>& e, const SolverOpts so, float gauss, float scale, float cost0) {
   const DevModel& m = c_models[ms];
   const int nv = m.nv;
-  float sn = 0, q1 = 0, q2 = 0;
+  float sn = 0, q1 = 0, q2 = 0, gs = 0;
   mulM(ms, e, e.Mv, e.search);
   mulJ(ms, e, e.r_Jv, e.search);
   SYNC();
@@ -1455,14 +1461,20 @@ LS_FN float line_search(const int ms, EnvS<C>& e, const SolverOpts so, float gau
     sn += s * s;
     q1 += s * (e.Ma[i] - e.qfrc_smooth[i]);
     q2 += 0.5f * s * e.Mv[i];
+    gs += s * e.grad[i];
   }
-  sn = WARP_SUM(sn); q1 = WARP_SUM(q1); q2 = WARP_SUM(q2);
+  sn = WARP_SUM(sn); q1 = WARP_SUM(q1); q2 = WARP_SUM(q2); gs = WARP_SUM(gs);
   float snorm = sqrtf(sn);
   if (snorm < LS_MINVAL) return 0;
   float gtol = so.tolerance * so.ls_tolerance * snorm / scale;
   float qg[3] = {gauss, q1, q2};
+#if defined(LS_EMULATE)
+  g_ls_searches++;
+#endif
   if (C::CONE == 1) ls_prepare(ms, e);
-  LSPoint p0 = ls_eval(ms, e, qg, 0.0f);
+  // The point alpha = 0 needs no evaluation: its cost is the current cost, its slope is grad . search and, because
+  // search = -H^-1 grad with the exact Hessian of this point, its curvature search^T H search equals -slope.
+  LSPoint p0 = {0.0f, cost0, gs, gs < 0 ? -gs : LS_MINVAL};
   LSPoint p1 = ls_eval(ms, e, qg, p0.alpha - p0.d1 / p0.d2);
   if (p0.cost < p1.cost) p1 = p0;
   if (fabsf(p1.d1) < gtol) return p1.alpha;
@@ -1566,7 +1578,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
       chol_solve<EnvS<C>::NV, EnvS<C>::NVP>(e.H, e.Mgrad);
       PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
       SYNC();
-      alpha = line_search(ms, e, so, gauss, scale);
+      alpha = line_search(ms, e, so, gauss, scale, cost);
       if (alpha == 0) { active = false; force_dirty = (C::CONE == 1); }
     }
     BLOCK_SYNC(so.sync_phases & 128);

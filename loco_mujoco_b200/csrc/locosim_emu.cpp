@@ -73,7 +73,7 @@ EmuBase* emu_create(const int* ints, int n_ints, const double* reals, int n_real
   s->hm = hm;
   bind_model(s->m, s->hm, s->hm.ints.data(), s->hm.reals.data());
   s->bind_prm();
-  s->so.tolerance = 1e-5f; s->so.ls_tolerance = 0.01f; s->so.max_iter = 20; s->so.ls_iter = 16;
+  s->so.tolerance = 1e-5f; s->so.ls_tolerance = 0.1f; s->so.max_iter = 20; s->so.ls_iter = 16;
   return s;
 }
 void emu_destroy(EmuBase* s) { delete s; }
@@ -87,6 +87,8 @@ void emu_get_state(EmuBase* s, double* qpos, double* qvel) { s->get(qpos, qvel, 
 void emu_get_qacc(EmuBase* s, double* qacc) { s->get(nullptr, nullptr, qacc, nullptr); }
 void emu_get_ws(EmuBase* s, double* w) { s->get(nullptr, nullptr, nullptr, w); }
 void emu_set_ws(EmuBase* s, const double* w) { s->set_ws(w); }
+long emu_ls_evals() { return g_ls_evals; }
+long emu_ls_searches() { return g_ls_searches; }
 int emu_ncon(EmuBase* s) { return s->info(0); }
 void emu_contact(EmuBase* s, int k, double* o) { s->contact(k, o); }
 void emu_set_grf(EmuBase* s, const int* group, int ng, int n_grf) { s->grf_group.assign(group, group + ng); s->n_grf = n_grf; }

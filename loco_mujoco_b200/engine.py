@@ -125,7 +125,7 @@ class CudaEngine:
         except Exception:
             pass
 
-    def set_solver(self, tolerance=1e-5, ls_tolerance=0.01, max_iter=20, ls_iter=16):
+    def set_solver(self, tolerance=1e-5, ls_tolerance=0.1, max_iter=20, ls_iter=16):
         self._check(self.lib.locosim_set_solver(self.h, tolerance, ls_tolerance, max_iter, ls_iter))
 
     def reset(self, mask=None, traj_no=None, step_no=None, out=None):
