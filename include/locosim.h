@@ -48,6 +48,10 @@ int locosim_set_solver(locosim_t* h, float tolerance, float ls_tolerance, int ma
  * observation to d_obs ([n_envs, obs_dim], may be NULL). */
 int locosim_reset(locosim_t* h, const uint8_t* d_mask, const int32_t* d_traj_no, const int32_t* d_step_no, float* d_obs,
                   void* stream);
+/* Same, with the parameter-pool row (= the model of a multi-model env, `np.random.randint(0, len(self._models))` in
+ * base.py:187-191) pinned per env as well: d_pool_row int32 [n_envs] or NULL (draw from the counter-based stream). */
+int locosim_reset_rows(locosim_t* h, const uint8_t* d_mask, const int32_t* d_traj_no, const int32_t* d_step_no,
+                       const int32_t* d_pool_row, float* d_obs, void* stream);
 
 /* Replaces LocoEnv.step(action) (mushroom MuJoCo.step: _preprocess_action base.py:606-621, n_substeps x mj_step,
  * _create_observation :584-604, is_absorbing :243-255, reward :170-176) for every env of the batch, followed by an
@@ -72,8 +76,9 @@ int locosim_get_counters(locosim_t* h, int32_t* d_out, void* stream);
 
 /* Domain randomisation (replaces DomainRandomizationHandler + per-reset MjModel recompilation,
  * /root/reference/loco_mujoco/utils/domain_randomization.py:191-296, hooked at base.py:183-185): a HOST pool of n_rows
- * parameter sets (row layout: loco_mujoco_b200/domain_randomization.py POOL_FIELDS, row_len floats as float64) is
- * uploaded once; every (auto-)reset draws one row per env from the engine's counter-based stream. */
+ * parameter sets (row layout: loco_mujoco_b200/domain_randomization.py POOL_FIELDS + meaninertia + 4 user features, row_len
+ * floats as float64) is uploaded once; the same mechanism carries multi-model envs (carry tasks: one row per weight,
+ * user feature 0 = the weight's mass, observed through LS_OBS_PARAM); every (auto-)reset draws one row per env from the engine's counter-based stream. */
 int locosim_param_pool_row_len(const locosim_t* h);
 int locosim_set_param_pool(locosim_t* h, const double* pool, int n_rows, int row_len);
 /* pool row currently used by each env: d_out int32 [n_envs] */

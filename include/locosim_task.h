@@ -46,6 +46,10 @@ enum { LS_OBS_QPOS = 0, LS_OBS_QVEL = 1, LS_OBS_GOAL = 2,
        LS_OBS_GRF = 3 /* idx = 3*group + component: mean over the sub-steps of the control step of the contact-frame force
                          (normal, tangent1, tangent2: mj_contactForce) of the FIRST floor contact of the group, / 1000
                          (base.py:94-98,596-599,623-631; 0 in the reset observation) */ };
+/* LS_OBS_PARAM = 4: idx-th user feature of the env's parameter-pool row (multi-model envs: the carried weight's mass,
+   base_robot_humanoid.py:119-123; the row layout ends with meaninertia, LS_POOL_USER user floats, padding) */
+#define LS_OBS_PARAM 4
+#define LS_POOL_USER 4
 #define LS_GRF_FLOOR 127
 #define LS_MAX_GRF 4
 /* reward types (utils/reward.py) */

@@ -52,7 +52,8 @@ __device__ __forceinline__ int draw_pool_row(uint64_t seed, int64_t genv, int ep
 // reset kernel: one warp per env, no shared memory
 // ----------------------------------------------------------------------------------------------------------
 __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* mask, const int* traj_no,
-                             const int* step_no, float* obs, int n_envs, uint64_t seed, int64_t env_off) {
+                             const int* step_no, const int* pool_row, float* obs, int n_envs, uint64_t seed,
+                             int64_t env_off) {
   int env = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (env >= n_envs) return;
@@ -65,6 +66,8 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
   if (traj_no) tr = traj_no[env];
   if (step_no) sp = step_no[env];
   const float* row = t.table + ((size_t)tr * t.traj_len + sp) * ncol;
+  int prow = draw_pool_row(seed, env_off + env, ep, st.pool_K);     // the model of this episode (base.py:187-191)
+  if (pool_row) prow = min(max(pool_row[env], 0), st.pool_K - 1);
   for (int i = lane; i < nv; i += 32) {
     float q = row[i];
     if (i == t.recenter0 || i == t.recenter1) q = 0;
@@ -80,13 +83,14 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
       if (ty == LS_OBS_QPOS) v = (idx == t.recenter0 || idx == t.recenter1) ? 0.0f : row[idx];
       else if (ty == LS_OBS_QVEL) v = row[nv + idx];
       else if (ty == LS_OBS_GRF) v = 0.0f;           // the running mean of the foot forces is reset with the episode
+      else if (ty == LS_OBS_PARAM) v = st.pool[(size_t)prow * m.pool_P + t.po_user + idx];
       else v = row[2 * nv + idx];
       obs[(size_t)env * t.obs_dim + k] = v;
     }
   }
   if (lane == 0) {
     st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1;
-    st.dr_row[env] = draw_pool_row(seed, env_off + env, ep, st.pool_K);
+    st.dr_row[env] = prow;
   }
 }
 
@@ -188,9 +192,12 @@ __global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts
     __syncwarp();
     reset_env(ms, t, e, tr, sp);
     if (lane == 0) {
+      const int prow = draw_pool_row(seed, env_off + env, ep, st.pool_K);
       st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1;
-      st.dr_row[env] = draw_pool_row(seed, env_off + env, ep, st.pool_K);
+      st.dr_row[env] = prow;
+      e.prm = st.pool + (size_t)prow * m.pool_P;      // the next episode's model (LS_OBS_PARAM entries of next_obs)
     }
+    __syncwarp();
     for (int k = lane; k < t.n_goal; k += 32) st.goal[(size_t)env * 4 + k] = e.goal[k];
   }
   if (next_obs) for (int k = lane; k < D; k += 32) next_obs[(size_t)env * D + k] = obs_value(t, e, k);
@@ -377,6 +384,7 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
     g_create_error = std::string("cudaMemcpyToSymbol: ") + cudaGetErrorString(cudaGetLastError()); locosim_destroy(h); return 1;
   }
   bind_task(h->dt, h->ht, h->hm.nu, h->d_tints, h->d_treals);
+  h->dt.po_user = h->hm.po[12];
   int rc = 0;
   switch (h->cfg) {
     case 0: rc = setup_cfg<CfgEllEuler>(h); break;
@@ -408,14 +416,18 @@ int locosim_set_solver(locosim_t* h, float tol, float ls_tol, int max_iter, int 
   return 0;
 }
 
-int locosim_reset(locosim_t* h, const uint8_t* d_mask, const int32_t* d_traj, const int32_t* d_step, float* d_obs,
-                  void* stream) {
+int locosim_reset_rows(locosim_t* h, const uint8_t* d_mask, const int32_t* d_traj, const int32_t* d_step,
+                       const int32_t* d_pool_row, float* d_obs, void* stream) {
   CK(cudaSetDevice(h->device));
   int threads = 128, blocks = (h->n_envs * 32 + threads - 1) / threads;
-  reset_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(h->slot, h->dt, h->st, d_mask, d_traj, d_step, d_obs, h->n_envs,
-                                                             h->seed, h->env_off);
+  reset_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(h->slot, h->dt, h->st, d_mask, d_traj, d_step, d_pool_row, d_obs,
+                                                             h->n_envs, h->seed, h->env_off);
   CK(cudaGetLastError());
   return 0;
+}
+int locosim_reset(locosim_t* h, const uint8_t* d_mask, const int32_t* d_traj, const int32_t* d_step, float* d_obs,
+                  void* stream) {
+  return locosim_reset_rows(h, d_mask, d_traj, d_step, nullptr, d_obs, stream);
 }
 
 int locosim_step(locosim_t* h, const float* a, float* o, float* r, uint8_t* d, float* no, int auto_reset, void* stream) {

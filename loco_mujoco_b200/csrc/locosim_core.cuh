@@ -83,12 +83,13 @@ struct DevModel {
   const int* tri_ij;         // [nv(nv+1)/2] packed (i << 8) | j of the lower triangle, row major
   // per-env parameter pool (domain randomisation): float offsets of each field inside one pool row
   int po_dof_damping, po_dof_frictionloss, po_dof_armature, po_jnt_stiffness, po_dof_invweight0, po_body_mass,
-      po_body_inertia, po_body_ipos, po_body_iquat, po_geom_friction, po_geom_invweight0, po_meaninertia, pool_P;
+      po_body_inertia, po_body_ipos, po_body_iquat, po_geom_friction, po_geom_invweight0, po_meaninertia, po_user, pool_P;
 };
 
 struct DevTask {
   int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter0, recenter1, ri[4], use_absorbing;
   int n_grf;                      // foot-force groups (use_foot_forces), 0 = off
+  int po_user;                    // offset of the user features inside a parameter-pool row (LS_OBS_PARAM)
   float rp[2];
   const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx, *grf_group;
   const float *act_mean, *act_delta, *done_lo, *done_hi, *table;
@@ -1744,6 +1745,7 @@ LS_DEV float obs_value(const DevTask& t, const EnvS<C>& e, int k) {
   int idx = t.obs_src_idx[k];
   int ty = t.obs_src_type[k];
   if (ty == LS_OBS_GRF) return e.grf[idx] * (1.0f / (1000.0f * (float)t.n_substeps));
+  if (ty == LS_OBS_PARAM) return e.prm[t.po_user + idx];
   return ty == LS_OBS_QPOS ? e.qpos[idx] : (ty == LS_OBS_QVEL ? e.qvel[idx] : e.goal[idx]);
 }
 

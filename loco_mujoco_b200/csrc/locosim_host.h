@@ -13,7 +13,7 @@ struct HostModel {
   int nb, nv, ng, nu, np, nm, integrator, cone, iterations, nlevel, nfric, has_damping;
   float timestep, gravity[3], impratio, tolerance, meaninertia;
   int max_condim;
-  int po[12], pool_P;          // parameter pool row layout (float offsets), see domain_randomization.py POOL_FIELDS
+  int po[13], pool_P;          // parameter pool row layout (float offsets), see domain_randomization.py POOL_FIELDS
   std::vector<float> default_row;   // the model's own parameters as one pool row
 };
 
@@ -79,7 +79,8 @@ static inline std::string parse_model(HostModel& h, const int* ints, int n_ints,
   h.ints.insert(h.ints.end(), mask.begin(), mask.end());
   h.ints.insert(h.ints.end(), frow.begin(), frow.end());
   for (int i = 0; i < 32; i++) for (int j = 0; j <= i; j++) h.ints.push_back((i << 8) | j);   // row-major lower triangle, n <= 32
-  // ---- parameter pool layout: POOL_FIELDS of loco_mujoco_b200/domain_randomization.py, then meaninertia, padded to 4
+  // ---- parameter pool layout: POOL_FIELDS of loco_mujoco_b200/domain_randomization.py, meaninertia, LS_POOL_USER user
+  //      features, padded to 4
   {
     const char* names[11] = {"dof_damping", "dof_frictionloss", "dof_armature", "jnt_stiffness", "dof_invweight0", "body_mass",
                              "body_inertia", "body_ipos", "body_iquat", "geom_friction", "geom_invweight0"};
@@ -97,6 +98,9 @@ static inline std::string parse_model(HostModel& h, const int* ints, int n_ints,
     h.po[11] = off;
     h.default_row.push_back(h.meaninertia);
     off += 1;
+    h.po[12] = off;                                    // user features (LS_OBS_PARAM)
+    for (int k = 0; k < LS_POOL_USER; k++) h.default_row.push_back(0.0f);
+    off += LS_POOL_USER;
     while (off % 4) { h.default_row.push_back(0.0f); off++; }
     h.pool_P = off;
   }
@@ -124,7 +128,7 @@ static inline void bind_model(DevModel& m, const HostModel& h, const int* ibase,
   m.tri_ij = ip; ip += 32 * 33 / 2;
   m.po_dof_damping = h.po[0]; m.po_dof_frictionloss = h.po[1]; m.po_dof_armature = h.po[2]; m.po_jnt_stiffness = h.po[3];
   m.po_dof_invweight0 = h.po[4]; m.po_body_mass = h.po[5]; m.po_body_inertia = h.po[6]; m.po_body_ipos = h.po[7];
-  m.po_body_iquat = h.po[8]; m.po_geom_friction = h.po[9]; m.po_geom_invweight0 = h.po[10]; m.po_meaninertia = h.po[11];
+  m.po_body_iquat = h.po[8]; m.po_geom_friction = h.po[9]; m.po_geom_invweight0 = h.po[10]; m.po_meaninertia = h.po[11]; m.po_user = h.po[12];
   m.pool_P = h.pool_P;
   (void)nu; (void)np; (void)nm; (void)ng;
 }

@@ -40,6 +40,8 @@ def load_library():
     lib.locosim_set_solver.argtypes = [vp, ctypes.c_float, ctypes.c_float, ip, ip]
     lib.locosim_reset.restype = ip
     lib.locosim_reset.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.locosim_reset_rows.restype = ip
+    lib.locosim_reset_rows.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.locosim_step.restype = ip
     lib.locosim_step.argtypes = [vp, vp, vp, vp, vp, vp, ip, vp]
     lib.locosim_get_state.restype = ip
@@ -66,7 +68,7 @@ EXPORTED_SYMBOLS = ["locosim_create", "locosim_destroy", "locosim_last_error", "
                     "locosim_action_dim", "locosim_nq", "locosim_set_solver", "locosim_reset", "locosim_step",
                     "locosim_get_state", "locosim_set_state", "locosim_get_counters", "locosim_launch_info",
                     "locosim_param_pool_row_len", "locosim_set_param_pool", "locosim_get_param_rows",
-                    "locosim_kernels_per_step"]
+                    "locosim_kernels_per_step", "locosim_reset_rows"]
 
 
 def _ptr(t):
@@ -128,9 +130,10 @@ class CudaEngine:
     def set_solver(self, tolerance=1e-5, ls_tolerance=0.1, max_iter=20, ls_iter=16):
         self._check(self.lib.locosim_set_solver(self.h, tolerance, ls_tolerance, max_iter, ls_iter))
 
-    def reset(self, mask=None, traj_no=None, step_no=None, out=None):
+    def reset(self, mask=None, traj_no=None, step_no=None, out=None, pool_row=None):
         out = self.next_obs if out is None else out
-        self._check(self.lib.locosim_reset(self.h, _ptr(mask), _ptr(traj_no), _ptr(step_no), _ptr(out), self._stream()))
+        self._check(self.lib.locosim_reset_rows(self.h, _ptr(mask), _ptr(traj_no), _ptr(step_no), _ptr(pool_row), _ptr(out),
+                                                self._stream()))
         self.launches += 1
         return out
 

@@ -23,7 +23,7 @@ from itertools import product
 import numpy as np
 
 from .. import mjcf, modelpack
-from ..task import (TaskSpec, OBS_QPOS, OBS_QVEL, OBS_GOAL, OBS_GRF, GRF_FLOOR, REWARD_NONE, REWARD_TARGET_VELOCITY,
+from ..task import (TaskSpec, OBS_QPOS, OBS_QVEL, OBS_GOAL, OBS_GRF, OBS_PARAM, GRF_FLOOR, REWARD_NONE, REWARD_TARGET_VELOCITY,
                     REWARD_POS)
 from ..trajectory import Trajectory
 from ..utils.reward import NoReward, CustomReward, TargetVelocityReward, PosReward
@@ -141,8 +141,8 @@ class LocoEnv:
         if type(xml_handles) != list:
             xml_handles = [xml_handles]
         self._xml_handles = xml_handles
-        if len(xml_handles) != 1:
-            raise NotImplementedError("multi-model environments (carry tasks with several weights) are not built yet")
+        # several handles = a multi-model env (carry tasks: one model per weight; base.py:86-88,183-191). All models share
+        # topology and sizes, so the engine runs them as rows of the parameter pool (one row per model).
         # use_foot_forces (base.py:93-98 of the reference): n_intermediate_steps x mj_step(1) with a contact-force hook
         # after each one. The engine always runs n_substeps physics steps per control step; dt is unchanged.
         self._collision_groups = list(collision_groups) if collision_groups else []
@@ -153,10 +153,16 @@ class LocoEnv:
         self._n_substeps = n_substeps
         self._n_intermediate_steps = 1
         self._use_foot_forces = use_foot_forces
-        self._model = compiled_model if compiled_model is not None else mjcf.compile_model(xml_handles[0], timestep=timestep)
+        if compiled_model is not None:
+            self._models = list(compiled_model) if isinstance(compiled_model, (list, tuple)) else [compiled_model]
+        else:
+            self._models = [mjcf.compile_model(h, timestep=timestep) for h in xml_handles]
+        self._model = self._models[0]
         if timestep is None:
             self._timestep = self._model.opt_timestep
-        self._models = [self._model]
+        self._model_user_features = [()] * len(self._models)     # per model: values observable through OBS_PARAM
+        if len(self._models) > 1 and domain_randomization_config is not None:
+            raise NotImplementedError("domain randomisation of a multi-model env")
         self._action_spec = list(action_spec) if len(action_spec) else list(self._model.actuator_names)
         self._action_indices = [self._model.actuator_id(n) for n in self._action_spec]
         if sorted(self._action_indices) != list(range(self._model.nu)):
@@ -296,8 +302,11 @@ class LocoEnv:
         if self.trajectories is None:
             raise ValueError("the CUDA engine needs trajectory data for resets (pass traj_params)")
         n_grf, grf_group = self._grf_spec()
-        types = list(types) + [OBS_GRF] * (3 * n_grf)           # the mean ground forces are the last entries
+        types = list(types) + [OBS_GRF] * (3 * n_grf)           # mean ground forces, then per-model features (weight)
         idxs = list(idxs) + list(range(3 * n_grf))
+        n_user = len(self._model_user_features[0])
+        types += [OBS_PARAM] * n_user
+        idxs += list(range(n_user))
         return TaskSpec(types, idxs, done_terms, rtype, rints, rparams, self.norm_act_mean, self.norm_act_delta,
                         self._n_substeps, self._reset_table(), self._n_goal(), recenter, self._use_absorbing_states,
                         act_idx=self._action_indices, n_grf=n_grf, grf_group=grf_group)
@@ -313,6 +322,11 @@ class LocoEnv:
             self._dr_pool = self._domain_rand.build_pool(self._domain_rand_pool_size)
         return self._dr_pool
 
+    def model_pool(self):
+        """[n_models, P] parameter pool of a multi-model env (one row per model incl. its user features)."""
+        from ..domain_randomization import pool_row
+        return np.stack([pool_row(m, u) for m, u in zip(self._models, self._model_user_features)])
+
     def _get_engine(self):
         if self._engine is None:
             from ..engine import CudaEngine
@@ -322,6 +336,8 @@ class LocoEnv:
                                       device=dev.index or 0, seed=self._seed, env_id_offset=self._env_id_offset)
             if self._domain_rand_config is not None:
                 self._engine.set_param_pool(self.domain_randomization_pool())
+            elif len(self._models) > 1 or len(self._model_user_features[0]):
+                self._engine.set_param_pool(self.model_pool())
         return self._engine
 
     # ---------------------------------------------------------------------------------------------------
@@ -338,7 +354,7 @@ class LocoEnv:
         self._reward_function.reset_state()
         if not self.batched:
             # reference semantics incl. the legacy global numpy RNG draw order (base.py:187-191, trajectory.py:253-259)
-            np.random.randint(0, len(self._models))
+            model_no = np.random.randint(0, len(self._models))
             if self._random_start:
                 traj_no = np.random.randint(0, self.trajectories.number_of_trajectories)
                 step_no = np.random.randint(0, self.trajectories.trajectory_length)
@@ -350,7 +366,9 @@ class LocoEnv:
             self.trajectories.traj_no, self.trajectories.subtraj_step_no = traj_no, step_no
             t = torch.tensor([traj_no], dtype=torch.int32, device=eng.device)
             s = torch.tensor([step_no], dtype=torch.int32, device=eng.device)
-            out = eng.reset(traj_no=t, step_no=s)
+            r = torch.tensor([model_no], dtype=torch.int32, device=eng.device) if len(self._models) > 1 else None
+            out = eng.reset(traj_no=t, step_no=s, pool_row=r)
+            self._current_model_idx = model_no
             self._obs = out[0].double().cpu().numpy()
             return self._obs.copy()
         out = eng.reset()

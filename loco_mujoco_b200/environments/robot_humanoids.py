@@ -23,26 +23,46 @@ class BaseRobotHumanoid(LocoEnv):
     _xml_rel = None
     _mini_dataset = None
 
+    _valid_weights = [0.1, 1.0, 5.0, 10.0]
+
     def __init__(self, disable_arms=True, disable_back_joint=True, hold_weight=False, weight_mass=None, **kwargs):
         if hold_weight:
-            raise NotImplementedError("carry tasks (multi-model batches + weight observation) are not built yet")
+            assert disable_arms is True, "If you want the robot to carry a weight, please disable the arms. " \
+                                         "They will be kept fixed."
         self._disable_arms, self._disable_back_joint, self._hold_weight = disable_arms, disable_back_joint, hold_weight
+        self._weight_mass = weight_mass
         action_spec = self._get_action_specification()
         observation_spec = self._get_observation_specification()
         joints_to_remove, motors_to_remove, equ = self._get_xml_modifications()
         hide = ["q_" + j for j in joints_to_remove] + ["dq_" + j for j in joints_to_remove]
         observation_spec = [e for e in observation_spec if e[0] not in hide]
         action_spec = [a for a in action_spec if a not in motors_to_remove]
+        weights = ([weight_mass] if weight_mass is not None else list(self._valid_weights)) if hold_weight else []
         if kwargs.get("compiled_model") is None:
             root = reference_data_root()
             if root is None:
                 raise FileNotFoundError("loco_mujoco model data not found (set LOCO_MUJOCO_PATH)")
             xml_handle = mjcf.XmlHandle(os.path.join(root, "environments", "data", *self._xml_rel))
-            xml_handle = self._modify_xml(xml_handle)
             xml_handle = self._delete_from_xml_handle(xml_handle, joints_to_remove, motors_to_remove, equ)
+            if hold_weight:     # one model per weight (atlas.py:316-331, talos.py:310-322)
+                xml_handle = [self._add_weight(xml_handle.copy(), w) for w in weights]
+            else:
+                xml_handle = self._modify_xml(xml_handle)
         else:
             xml_handle = None
         super().__init__(xml_handle, action_spec, observation_spec, self._collision_groups_spec(), **kwargs)
+        if hold_weight:
+            assert len(self._models) == len(weights)
+            self._model_user_features = [(float(w),) for w in weights]     # observed weight mass
+
+    def _add_weight(self, xml_handle, mass):
+        raise NotImplementedError("%s has no carry task" % type(self).__name__)
+
+    def _get_observation_space(self):
+        lo, hi = super()._get_observation_space()
+        if self._hold_weight:       # base_robot_humanoid.py:100-103
+            lo, hi = np.concatenate([lo, [self._valid_weights[0]]]), np.concatenate([hi, [self._valid_weights[-1]]])
+        return lo, hi
 
     def _collision_groups_spec(self):
         # atlas.py:292-296 (4 groups, base-class _get_ground_forces)
@@ -67,8 +87,10 @@ class BaseRobotHumanoid(LocoEnv):
         check_validity_task_mode_dataset(cls.__name__, task, None, dataset_type, *cls.valid_task_confs.get_all())
         if dataset_type != "real":
             raise NotImplementedError("perfect datasets are not shipped (network download in the reference)")
-        if task not in ("walk", "run"):
+        if task not in ("walk", "run", "carry"):
             raise NotImplementedError("task %r is not built yet" % task)
+        if task == "carry":
+            kwargs["hold_weight"] = True
         reward_type = kwargs.pop("reward_type", "target_velocity")
         reward_params = kwargs.pop("reward_params", dict(target_velocity=2.5 if task == "run" else 1.25))
         root = reference_data_root()
@@ -85,7 +107,12 @@ class BaseRobotHumanoid(LocoEnv):
         else:
             from .. import modelpack
             asset = np.load(os.path.join(ASSET_DIR, "%s.%s.npz" % (cls.__name__, task)), allow_pickle=False)
-            model = modelpack.from_npz_dict({k[6:]: asset[k] for k in asset.files if k.startswith("model_")})
+            n_models = int(asset["n_models"]) if "n_models" in asset.files else 1
+            if n_models > 1:
+                model = [modelpack.from_npz_dict({k[len("model%d_" % i):]: asset[k] for k in asset.files
+                                                  if k.startswith("model%d_" % i)}) for i in range(n_models)]
+            else:
+                model = modelpack.from_npz_dict({k[6:]: asset[k] for k in asset.files if k.startswith("model_")})
             mdp = cls(reward_type=reward_type, reward_params=reward_params, compiled_model=model, **kwargs)
             mdp.load_trajectory(dict(processed={k[5:]: asset[k] for k in asset.files if k.startswith("traj_")}))
         return mdp
@@ -104,6 +131,13 @@ class Atlas(BaseRobotHumanoid):
             joints += ["back_bkz", "back_bky", "back_bkx"]
             motors += ["back_bkz_actuator", "back_bky_actuator", "back_bkx_actuator"]
         return joints, motors, []
+
+    def _add_weight(self, h, mass):        # atlas.py:456-482
+        w = h.add(h.find("body", "utorso"), "body", name="weight")
+        h.add(w, "geom", type="box", size="0.1 0.27 0.1", pos="0.72 0 -0.25", group="0", mass=repr(float(mass)))
+        h.find("body", "r_clav").set("quat", "1.0 0.0 -0.35 0.0")
+        h.find("body", "l_clav").set("quat", "0.0 -0.35 0.0 1.0")
+        return h
 
     def _has_fallen_terms(self):
         terms = self._pelvis_terms()
@@ -145,6 +179,14 @@ class Talos(BaseRobotHumanoid):
 
     def _grf_group_names(self):
         return ["foot_r", "foot_l"]
+
+    def _add_weight(self, h, mass):        # talos.py:469-500
+        w = h.add(h.find("body", "torso_2_link"), "body", name="weight")
+        h.add(w, "geom", type="box", size="0.1 0.25 0.1", pos="0.45 0 -0.20", group="0", mass=repr(float(mass)))
+        for name, quat in (("arm_right_4_link", "1.0 0.0 -0.65 0.0"), ("arm_left_4_link", "1.0 0.0 -0.65 0.0"),
+                           ("arm_right_6_link", "1.0 0.0 -0.0 1.0"), ("arm_left_6_link", "1.0 0.0 -0.0 1.0")):
+            h.find("body", name).set("quat", quat)
+        return h
 
     def _modify_xml(self, xml_handle):
         if self._disable_arms:

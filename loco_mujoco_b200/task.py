@@ -6,7 +6,7 @@ import numpy as np
 
 MAGIC = 0x5441534B
 VERSION = 3
-OBS_QPOS, OBS_QVEL, OBS_GOAL, OBS_GRF = 0, 1, 2, 3
+OBS_QPOS, OBS_QVEL, OBS_GOAL, OBS_GRF, OBS_PARAM = 0, 1, 2, 3, 4
 GRF_FLOOR = 127
 REWARD_NONE, REWARD_TARGET_VELOCITY, REWARD_VELOCITY_VECTOR, REWARD_POS = 0, 1, 2, 3
 

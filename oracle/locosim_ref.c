@@ -1399,7 +1399,7 @@ static int task_load(Task* t, int nu, int nv, const int* ti, int nti, const doub
   return 0;
 }
 
-struct RefEnv { RefSim* sim; Task task; double goal[8]; double obs[128]; double grf[3 * LS_MAX_GRF]; };
+struct RefEnv { RefSim* sim; Task task; double goal[8]; double obs[128]; double grf[3 * LS_MAX_GRF]; double user[LS_POOL_USER]; };
 
 RefEnv* refenv_create(const int* ints, int n_ints, const double* reals, int n_reals, const int* ti, int nti,
                       const double* tr, int ntr) {
@@ -1412,6 +1412,7 @@ RefEnv* refenv_create(const int* ints, int n_ints, const double* reals, int n_re
 }
 void refenv_destroy(RefEnv* e) { if (e) { ref_destroy(e->sim); free(e->task.ibuf); free(e->task.rbuf); free(e); } }
 int refenv_obs_dim(const RefEnv* e) { return e->task.obs_dim; }
+void refenv_set_user(RefEnv* e, const double* user) { memcpy(e->user, user, sizeof(e->user)); }
 RefSim* refenv_sim(RefEnv* e) { return e->sim; }
 
 static void build_obs(const RefEnv* e, double* obs) {
@@ -1421,6 +1422,7 @@ static void build_obs(const RefEnv* e, double* obs) {
     switch (t->obs_src_type[k]) {
       case LS_OBS_QPOS: obs[k] = e->sim->qpos[idx]; break;
       case LS_OBS_QVEL: obs[k] = e->sim->qvel[idx]; break;
+      case LS_OBS_PARAM: obs[k] = e->user[idx]; break;   /* e.g. the carried weight's mass (base_robot_humanoid.py:119-123) */
       case LS_OBS_GRF: obs[k] = e->grf[idx] / (1000.0 * t->n_substeps); break;   /* mean_grf.mean / 1000 (base.py:596-599) */
       default: obs[k] = e->goal[idx]; break;
     }

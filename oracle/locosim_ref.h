@@ -62,6 +62,8 @@ RefEnv* refenv_create(const int* ints, int n_ints, const double* reals, int n_re
                       const int* task_ints, int n_task_ints, const double* task_reals, int n_task_reals);
 void refenv_destroy(RefEnv* e);
 int refenv_obs_dim(const RefEnv* e);
+/* user features observed through LS_OBS_PARAM (multi-model envs: the carried weight's mass) */
+void refenv_set_user(RefEnv* e, const double* user);
 void refenv_reset_to(RefEnv* e, int traj_no, int step_no, double* obs);
 void refenv_step(RefEnv* e, const double* action, double* obs, double* reward, int* absorbing);
 RefSim* refenv_sim(RefEnv* e);

@@ -18,6 +18,8 @@ class Oracle:
         lib.refenv_create.argtypes = [vp, ip, vp, ip, vp, ip, vp, ip]
         lib.refenv_sim.restype = vp
         lib.refenv_sim.argtypes = [vp]
+        lib.refenv_set_user.restype = None
+        lib.refenv_set_user.argtypes = [vp, vp]
         lib.refenv_obs_dim.restype = ip
         lib.refenv_obs_dim.argtypes = [vp]
         for f, args in [("ref_destroy", [vp]), ("refenv_destroy", [vp]), ("ref_reset", [vp, vp, vp]),
@@ -56,6 +58,11 @@ class OracleEnv:
         self.sim = ctypes.c_void_p(self.lib.refenv_sim(self.h))
         self.obs_dim = self.lib.refenv_obs_dim(self.h)
         self.nv = self.lib.ref_nv(self.sim)
+
+    def set_user(self, user):
+        u = np.zeros(4)
+        u[:len(user)] = user
+        self.lib.refenv_set_user(self.h, _p(u))
 
     def reset_to(self, traj_no, step_no):
         obs = np.zeros(self.obs_dim)

@@ -12,7 +12,7 @@ Stated fp32 tolerances (the engine computes in fp32, the reference in fp64):
 import numpy as np
 import pytest
 
-from helpers import GOLDEN_TASKS, PINNED_ROWS, golden, make_env, blobs
+from helpers import GOLDEN_TASKS, PINNED_ROWS, golden, make_env, blobs, oracle_env
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -92,7 +92,10 @@ def _batched_vs_oracle(oracle, task, n_steps=None, **kw):
     tr = rng.randint(0, env.trajectories.number_of_trajectories, n).astype(np.int32)
     st = rng.randint(0, env.trajectories.trajectory_length, n).astype(np.int32)
     obs0 = eng.reset(traj_no=torch.tensor(tr, device=eng.device), step_no=torch.tensor(st, device=eng.device)).cpu().numpy()
-    oes = [oracle.env(mb, tb) for _ in range(n)]
+    rows = eng.param_rows().cpu().numpy()           # multi-model envs (carry): the model each env drew at reset
+    if len(env._models) > 1:
+        assert len(set(rows.tolist())) > 1
+    oes = [oracle_env(oracle, env, int(rows[i]) if len(env._models) > 1 else 0) for i in range(n)]
     for i, oe in enumerate(oes):
         assert np.abs(oe.reset_to(tr[i], st[i]) - obs0[i]).max() < 1e-5
     alive = np.ones(n, dtype=bool)

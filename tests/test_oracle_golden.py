@@ -6,15 +6,15 @@ until has_fallen, compared with np.allclose exactly like /root/reference/tests/t
 import numpy as np
 import pytest
 
-from helpers import GOLDEN_TASKS, PINNED_ROWS, golden, make_env, blobs, reference_draws
+from helpers import GOLDEN_TASKS, PINNED_ROWS, GOLDEN_ATOL, golden, make_env, blobs, oracle_env, reference_draws
 
 
 @pytest.mark.parametrize("task", GOLDEN_TASKS)
 def test_oracle_reproduces_reference_golden(oracle, bundled_only, task):
     env = make_env(task)
     g = golden(task)
-    oe = oracle.env(*blobs(env))
     traj_no, step_no = reference_draws(env)
+    oe = oracle_env(oracle, env, env._drawn_model_no)          # carry tasks: the model (weight) drawn at reset
     rows = [oe.reset_to(traj_no, step_no)]
     absorbing = False
     while not absorbing and len(rows) < 1001:
@@ -26,7 +26,7 @@ def test_oracle_reproduces_reference_golden(oracle, bundled_only, task):
         assert np.allclose(rows[:n], g[:n]), "max abs err %.3e" % np.abs(rows[:n] - g[:n]).max()
         return
     assert rows.shape == g.shape, "episode length (done-flag timing) differs from the golden"
-    assert np.allclose(rows, g), "max abs err %.3e" % np.abs(rows - g).max()
+    assert np.allclose(rows, g, atol=GOLDEN_ATOL.get(task, 1e-8)), "max abs err %.3e" % np.abs(rows - g).max()
     # the reset row is pure table lookup: must be (near) bit-exact
     assert np.abs(rows[0] - g[0]).max() < 1e-13
     # terminal row satisfies has_fallen, earlier rows do not

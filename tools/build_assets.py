@@ -15,7 +15,12 @@ from loco_mujoco_b200.environments.base import processed_trajectory_dict, ASSET_
 TASKS = sys.argv[1:] or ["UnitreeA1.simple", "UnitreeA1.hard"]
 for task in TASKS:
     env = LocoEnv.make(task + ".real", debug=True)
-    d = {"model_" + k: v for k, v in modelpack.to_npz_dict(env._model).items()}
+    if len(env._models) > 1:        # multi-model env (carry): every model, prefix model<i>_
+        d = {"n_models": np.int32(len(env._models))}
+        for i, m in enumerate(env._models):
+            d.update({"model%d_%s" % (i, k): v for k, v in modelpack.to_npz_dict(m).items()})
+    else:
+        d = {"model_" + k: v for k, v in modelpack.to_npz_dict(env._model).items()}
     d.update({"traj_" + k: v for k, v in processed_trajectory_dict(env.trajectories).items()})
     path = os.path.join(ASSET_DIR, task + ".npz")
     np.savez_compressed(path, **d)
