@@ -353,6 +353,7 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   if (cfg_fits<CfgEllEuler>(h->hm, h->ht)) h->cfg = 0;
   else if (cfg_fits<CfgPyrEuler>(h->hm, h->ht)) h->cfg = 1;
   else if (cfg_fits<CfgPyrRK4>(h->hm, h->ht)) h->cfg = 2;
+  else if (cfg_fits<CfgPyrEuler29>(h->hm, h->ht)) h->cfg = 3;
   else return fail("no compiled configuration fits this model (cone / integrator / sizes: see locosim_config.h)");
   h->so.tolerance = 1e-5f; h->so.ls_tolerance = 0.1f; h->so.ls_iter = 16;
   h->so.max_iter = h->hm.iterations < 20 ? h->hm.iterations : 20;
@@ -389,6 +390,7 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   switch (h->cfg) {
     case 0: rc = setup_cfg<CfgEllEuler>(h); break;
     case 1: rc = setup_cfg<CfgPyrEuler>(h); break;
+    case 3: rc = setup_cfg<CfgPyrEuler29>(h); break;
     default: rc = setup_cfg<CfgPyrRK4>(h); break;
   }
   if (rc) { g_create_error = h->err; locosim_destroy(h); return 1; }
@@ -437,6 +439,7 @@ int locosim_step(locosim_t* h, const float* a, float* o, float* r, uint8_t* d, f
   switch (h->cfg) {
     case 0: return launch_step<CfgEllEuler>(h, a, o, r, d, no, auto_reset, s);
     case 1: return launch_step<CfgPyrEuler>(h, a, o, r, d, no, auto_reset, s);
+    case 3: return launch_step<CfgPyrEuler29>(h, a, o, r, d, no, auto_reset, s);
     default: return launch_step<CfgPyrRK4>(h, a, o, r, d, no, auto_reset, s);
   }
 }

@@ -67,6 +67,7 @@ EmuBase* emu_create(const int* ints, int n_ints, const double* reals, int n_real
   if (!err.empty()) { fprintf(stderr, "emu: %s\n", err.c_str()); return nullptr; }
   EmuBase* s;
   if (hm.cone == 1 && hm.integrator == 0) s = new EmuT<CfgEllEuler>();
+  else if (hm.cone == 0 && hm.integrator == 0 && hm.nv > 18) s = new EmuT<CfgPyrEuler29>();
   else if (hm.cone == 0 && hm.integrator == 0) s = new EmuT<CfgPyrEuler>();
   else if (hm.cone == 0 && hm.integrator == 1) s = new EmuT<CfgPyrRK4>();
   else { fprintf(stderr, "emu: no config\n"); return nullptr; }

@@ -290,3 +290,68 @@ class UnitreeH1(BaseRobotHumanoid):
     def generate(task="walk", dataset_type="real", **kwargs):
         stub = "05-run_UnitreeH1.npz" if task == "run" else "02-constspeed_UnitreeH1.npz"
         return UnitreeH1._generate(stub, task, dataset_type, clip_trajectory_to_joint_ranges=True, **kwargs)
+
+
+_G1_ARMS = ["%s_%s_joint" % (side, j) for side in ("right", "left")
+            for j in ("shoulder_pitch", "shoulder_roll", "shoulder_yaw", "elbow_pitch", "elbow_roll")]
+_G1_JOINTS = _PELVIS + ["%s_%s_joint" % (side, j) for side in ("left", "right")
+                        for j in ("hip_pitch", "hip_roll", "hip_yaw", "knee", "ankle_pitch", "ankle_roll")] + \
+    ["torso_joint"] + ["%s_%s_joint" % (side, j) for side in ("left", "right")
+                       for j in ("shoulder_pitch", "shoulder_roll", "shoulder_yaw", "elbow_pitch", "elbow_roll")]
+_G1_ARM_QUATS = {"left_shoulder_pitch_link": [1.0, 0.25, 0.1, 0.0], "right_elbow_pitch_link": [1.0, 0.0, 0.25, 0.0],
+                 "right_shoulder_pitch_link": [1.0, -0.25, 0.1, 0.0], "left_elbow_pitch_link": [1.0, 0.0, 0.25, 0.0]}
+
+
+class UnitreeG1(BaseRobotHumanoid):
+    """Unitree G1 (unitreeG1.py): 29 dofs / 23 motors with arms (default). Observation and action order follow the
+    joints / motors of g1.xml (unitreeG1.py:450-481); the feet touch the floor through four small spheres each."""
+    valid_task_confs = ValidTaskConf(tasks=["walk", "run"], data_types=["real", "perfect"])
+    _xml_rel = ("unitree_g1", "g1.xml")
+
+    def __init__(self, disable_arms=False, disable_back_joint=False, **kwargs):
+        super().__init__(disable_arms=disable_arms, disable_back_joint=disable_back_joint, hold_weight=False, **kwargs)
+
+    def _collision_groups_spec(self):       # unitreeG1.py:263-271
+        return [("floor", ["floor"])] + [("%s_foot_%d" % (s, k), ["%s_foot_%d_col" % (s, k)])
+                                         for s in ("right", "left") for k in (1, 2, 3, 4)]
+
+    @staticmethod
+    def _get_grf_size():
+        return 24
+
+    def _grf_group_names(self):              # unitreeG1.py:295-317
+        return ["%s_foot_%d" % (s, k) for s in ("right", "left") for k in (1, 2, 3, 4)]
+
+    def _modify_xml(self, xml_handle):
+        if self._disable_arms:
+            for name, quat in _G1_ARM_QUATS.items():       # unitreeG1.py:426-448
+                xml_handle.find("body", name).set("quat", " ".join(repr(float(x)) for x in quat))
+        return xml_handle
+
+    def _get_xml_modifications(self):
+        joints, motors = [], []
+        if self._disable_arms:
+            joints += _G1_ARMS
+            motors += _G1_ARMS                      # the motors carry the joints' names
+        if self._disable_back_joint:
+            joints += ["torso_joint"]
+            motors += ["torso_joint"]
+        return joints, motors, []
+
+    def _has_fallen_terms(self):                     # unitreeG1.py:372-376
+        return [("q_pelvis_ty", -0.3, 0.1), ("q_pelvis_tilt", -np.pi / 4.5, np.pi / 12),
+                ("q_pelvis_list", -np.pi / 12, np.pi / 8), ("q_pelvis_rotation", -np.pi / 8, np.pi / 8)]
+
+    @staticmethod
+    def _get_observation_specification():
+        return [("q_" + j, j, ObservationType.JOINT_POS) for j in _G1_JOINTS] + \
+               [("dq_" + j, j, ObservationType.JOINT_VEL) for j in _G1_JOINTS]
+
+    @staticmethod
+    def _get_action_specification():
+        return list(_G1_JOINTS[6:])
+
+    @staticmethod
+    def generate(task="walk", dataset_type="real", **kwargs):
+        stub = "05-run_UnitreeG1.npz" if task == "run" else "02-constspeed_UnitreeG1.npz"
+        return UnitreeG1._generate(stub, task, dataset_type, clip_trajectory_to_joint_ranges=True, **kwargs)
