@@ -8,6 +8,7 @@ Atlas.register()
 Talos.register()
 UnitreeH1.register()
 UnitreeG1.register()
-from .humanoids import HumanoidTorque
+from .humanoids import HumanoidTorque, HumanoidTorque4Ages
 
 HumanoidTorque.register()
+HumanoidTorque4Ages.register()

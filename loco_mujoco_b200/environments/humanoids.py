@@ -33,7 +33,8 @@ class BaseHumanoid(LocoEnv):
     def _grf_group_names(self):     # base_humanoid.py:193-209
         return ["foot_r", "foot_l"] if self._use_box_feet else ["foot_r", "front_foot_r", "foot_l", "front_foot_l"]
 
-    def __init__(self, use_muscles=False, use_box_feet=True, disable_arms=True, alpha_box_feet=0.5, **kwargs):
+    def __init__(self, use_muscles=False, use_box_feet=True, disable_arms=True, alpha_box_feet=0.5, _scaling=None,
+                 **kwargs):
         if use_muscles:
             raise NotImplementedError("muscle actuation (tendons / <muscle>) is out of scope")
         self._use_muscles, self._use_box_feet, self._disable_arms = use_muscles, use_box_feet, disable_arms
@@ -48,10 +49,12 @@ class BaseHumanoid(LocoEnv):
             if root is None:
                 raise FileNotFoundError("loco_mujoco model data not found (set LOCO_MUJOCO_PATH)")
             h = mjcf.XmlHandle(os.path.join(root, "environments", "data", "humanoid", "humanoid_torque.xml"))
+            if _scaling is not None:
+                h = self.scale_body(h, _scaling)
             if use_box_feet or disable_arms:
                 h = self._delete_from_xml_handle(h, joints_to_remove, motors_to_remove, equ)
                 if use_box_feet:
-                    h = self._add_box_feet_to_xml_handle(h, alpha_box_feet)
+                    h = self._add_box_feet_to_xml_handle(h, alpha_box_feet, 1.0 if _scaling is None else _scaling)
                 if disable_arms:
                     h = self._reorient_arms(h)
         else:
@@ -153,3 +156,89 @@ class HumanoidTorque(BaseHumanoid):
     def generate(task="walk", dataset_type="real", **kwargs):
         return HumanoidTorque._generate({"walk": "02-constspeed_reduced_humanoid.npz",
                                          "run": "05-run_reduced_humanoid.npz"}, task, dataset_type, **kwargs)
+
+
+class HumanoidTorque4Ages(BaseHumanoid):
+    """HumanoidTorque scaled to one of four body sizes (base_humanoid_4_ages.py:28-105,243-277,305-358): 0.4 (infant),
+    0.6, 0.8, 1.0 (adult); the 2-bit env id is appended to the observation and scales the default reward's target.
+
+    Modes "1".."4" (one scaling) are built. Mode "all" mixes four models of DIFFERENT kinematics (body offsets, mesh and
+    foot sizes, gears) in one env; the engine's multi-model mechanism only swaps inertial / joint parameters, so a mixed
+    batch needs one engine per scaling (use four envs) and is not offered as a single env."""
+    valid_task_confs = ValidTaskConf(tasks=["walk", "run"], modes=["all", "1", "2", "3", "4"], data_types=["real", "perfect"])
+    _default_scalings = [0.4, 0.6, 0.8, 1.0]
+
+    def __init__(self, scaling=None, scaling_trajectory_map=None, **kwargs):
+        if "use_muscles" in kwargs:
+            assert kwargs.pop("use_muscles") is False, "Activating muscles in this environment not allowed. "
+        scalings = self._default_scalings if scaling is None else (scaling if type(scaling) == list else [scaling])
+        if len(scalings) != 1:
+            raise NotImplementedError("HumanoidTorque4Ages with several scalings in one env (mode 'all'): the models differ "
+                                      "in kinematics; create one env per scaling")
+        self._scalings = scalings
+        target = kwargs.get("reward_params")
+        if kwargs.get("reward_type") == "multi_target_velocity":
+            # MultiTargetVelocityReward (utils/reward.py:77-97): target = target_velocity * scaling of the env id
+            kwargs["reward_type"] = "target_velocity"
+            kwargs["reward_params"] = dict(target_velocity=target["target_velocity"] * scalings[0])
+        super().__init__(use_muscles=False, _scaling=scalings[0], **kwargs)
+        idx = self._default_scalings.index(scalings[0]) if scalings[0] in self._default_scalings else 0
+        self._model_user_features = [(float((idx >> 1) & 1), float(idx & 1))]      # mushroom _get_env_id_map: binary id
+
+    def _get_observation_space(self):
+        lo, hi = super()._get_observation_space()
+        return np.concatenate([lo, np.zeros(2)]), np.concatenate([hi, np.ones(2)])
+
+    @staticmethod
+    def scale_body(h, scaling):
+        head_geoms = ["hat_skull", "hat_jaw", "hat_ribs_cap"]
+        for mesh in h.root.iter("mesh"):
+            if mesh.get("name") not in head_geoms and mesh.get("file") is not None:
+                sc = np.array([float(x) for x in mesh.get("scale", "1 1 1").split()]) * scaling
+                mesh.set("scale", " ".join(repr(float(x)) for x in sc))
+        wb = h.root.find("worldbody")
+        for g in wb.iter("geom"):
+            if g.get("name") in head_geoms:
+                g.set("pos", "0.0 %r 0.0" % (-0.5 * (1 - scaling)))
+        for b in wb.iter("body"):
+            pos = np.array([float(x) for x in b.get("pos", "0 0 0").split()]) * scaling
+            b.set("pos", " ".join(repr(float(x)) for x in pos))
+            inertial = b.find("inertial")
+            inertial.set("mass", repr(float(inertial.get("mass")) * scaling ** 3))
+            fi = np.array([float(x) for x in inertial.get("fullinertia").split()])
+            assert np.array_equal(fi[3:], np.zeros(3))
+            inertial.set("fullinertia", " ".join(repr(float(x)) for x in fi * scaling ** 5))
+        for a in h.root.find("actuator"):
+            gear = np.array([float(x) for x in a.get("gear", "1").split()]) * scaling ** 2
+            a.set("gear", " ".join(repr(float(x)) for x in gear))
+        return h
+
+    @classmethod
+    def _generate4(cls, task="walk", mode="all", dataset_type="real", debug=False, **kwargs):
+        check_validity_task_mode_dataset(cls.__name__, task, mode, dataset_type, *cls.valid_task_confs.get_all())
+        if dataset_type != "real":
+            raise NotImplementedError("perfect datasets are not shipped (network download in the reference)")
+        if mode == "all":
+            raise NotImplementedError("mode 'all' (four kinematically different models in one env): create one env per mode")
+        scaling = cls._default_scalings[int(mode) - 1]
+        reward_type = kwargs.pop("reward_type", "multi_target_velocity")
+        reward_params = kwargs.pop("reward_params", dict(target_velocity=1.25 if task == "walk" else 2.5))
+        stub = ("02-constspeed" if task == "walk" else "05-run") + "_reduced_humanoid_POMDP_%s.npz" % mode
+        root = reference_data_root()
+        if root is not None:
+            mdp = cls(scaling=scaling, reward_type=reward_type, reward_params=reward_params, **kwargs)
+            path = os.path.join(root, "datasets", "humanoids", "real", stub)
+            if debug or not os.path.exists(path):
+                path = os.path.join(root, "datasets", "humanoids", "real", "mini_datasets", stub)
+            mdp.load_trajectory(dict(traj_path=path, traj_dt=1 / 500.0, control_dt=mdp.dt))
+        else:
+            from .. import modelpack
+            asset = np.load(os.path.join(ASSET_DIR, "%s.%s.%s.npz" % (cls.__name__, task, mode)), allow_pickle=False)
+            model = modelpack.from_npz_dict({k[6:]: asset[k] for k in asset.files if k.startswith("model_")})
+            mdp = cls(scaling=scaling, reward_type=reward_type, reward_params=reward_params, compiled_model=model, **kwargs)
+            mdp.load_trajectory(dict(processed={k[5:]: asset[k] for k in asset.files if k.startswith("traj_")}))
+        return mdp
+
+    @staticmethod
+    def generate(task="walk", mode="all", dataset_type="real", **kwargs):
+        return HumanoidTorque4Ages._generate4(task, mode, dataset_type, **kwargs)

@@ -6,7 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 GOLDEN_TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "HumanoidTorque.walk", "Atlas.walk", "Talos.walk",
-                "UnitreeH1.run", "Atlas.carry", "Talos.carry", "UnitreeG1.run", "UnitreeG1.walk"]
+                "UnitreeH1.run", "Atlas.carry", "Talos.carry", "UnitreeG1.run", "UnitreeG1.walk"] + \
+    ["HumanoidTorque4Ages.%s.%s" % (t, m) for t in ("run", "walk") for m in "1234"]
 
 
 # HumanoidTorque.walk: from row 20 on the reference rollout contains a convex mesh-mesh self-contact (fixed arm/hand
@@ -18,7 +19,10 @@ GOLDEN_TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "Hum
 # rows before the first foot strike of the golden (10 rows = 90 steps of free flight incl. joint limits) are pinned.
 # UnitreeG1.walk: the feet are spheres (pinned exactly), but in the last two rows of the golden a convex-mesh body part
 # touches something (same unbuilt mesh narrow phase as HumanoidTorque.walk): rows 0..25 pinned (1e-13).
-PINNED_ROWS = {"HumanoidTorque.walk": 20, "UnitreeH1.run": 10, "UnitreeG1.walk": 26}
+# HumanoidTorque4Ages (one scaling per env): run.1 / run.2 / run.4 / walk.1 are reproduced completely; the others up to the
+# first convex-mesh contact of the episode (same gap as HumanoidTorque.walk).
+PINNED_ROWS = {"HumanoidTorque.walk": 20, "UnitreeH1.run": 10, "UnitreeG1.walk": 26, "HumanoidTorque4Ages.run.3": 39,
+               "HumanoidTorque4Ages.walk.2": 36, "HumanoidTorque4Ages.walk.3": 19, "HumanoidTorque4Ages.walk.4": 20}
 
 
 # Talos.carry: the oracle follows the golden to 2.0e-7 over the whole episode (same episode length / done timing); a few
