@@ -47,6 +47,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-flush", action="store_true", help="diagnostic: do not flush L2 between timed steps")
     p.add_argument("--gather", action="store_true", help="all-gather the rollout buffer across ranks every step")
+    p.add_argument("--dr-pool", default=None, help="npz with a domain-randomisation parameter pool (key `pool`, e.g. "
+                   "tests/golden/dr_atlas_pool.npz for Atlas.walk): per-env parameters drawn at every reset")
     return p.parse_args()
 
 
@@ -154,6 +156,10 @@ def main():
     env = LocoEnv.make(a.task + ".real", debug=True, num_envs=a.envs, device="cuda:%d" % local, seed=0,
                        env_id_offset=rank * a.envs)
     eng = env._get_engine()
+    if a.dr_pool:
+        import numpy as _np
+        eng.set_param_pool(_np.load(a.dr_pool)["pool"])
+        cfg["domain_randomization"] = "parameter pool %s" % os.path.basename(a.dr_pool)
     nu, D, N = eng.action_dim, eng.obs_dim, a.envs
     env.reset()
     total = a.warmup + a.steps
