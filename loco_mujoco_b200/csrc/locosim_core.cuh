@@ -1198,10 +1198,105 @@ LS_FN float update_constraint(const int ms, EnvS<C>& e, float* gauss_out) {
 }
 
 #ifndef LS_EMULATE
-// CUDA build: lane i accumulates row i of H = M + J^T diag(w) J (+ cone blocks) in registers, factors it in place
-// (chol_rows) and publishes L (with 1/L_ii on the diagonal) to e.H for the triangular solves.
+// CUDA build, nv <= 20: H = M + J^T diag(w) J (+ cone blocks) accumulated in registers by 24 lanes. Lanes 0..NV-1 own
+// row `lane`, columns 0..11 (chunks 0-2 of four); for rows >= 12, whose lower triangle reaches beyond column 11, helper
+// lanes NV.. own columns 8..19 (chunks 2-4). Every lane therefore runs 3 float4 chunks per active constraint row instead
+// of 5. The factorisation (chol_factor) only reads the lower triangle.
 template <class C>
-LS_FN void make_hessian(const int ms, EnvS<C>& e) {
+LS_FN void make_hessian_split(const int ms, EnvS<C>& e) {
+  const DevModel& m = c_models[ms];
+  typedef EnvS<C> E;
+  constexpr int NV = E::NV, JS = E::JS;
+  static_assert(JS == 20 && NV >= 12 && NV + (NV - 12) <= 32, "split layout: 5 chunks, helpers for rows 12..NV-1");
+  const int nv = m.nv, nrow = e.nrow, nunit = e.nunit;
+  const int lane = LS_LANE;
+  const bool owner = lane < NV, helper = lane >= NV && lane < NV + (NV - 12);
+  const int row = owner ? lane : (helper ? 12 + (lane - NV) : NV - 1);
+  const int q0 = helper ? 2 : 0;                       // first of this lane's three chunks
+  const int c0 = 4 * q0;
+  PAR_FOR(r, e.nefc) e.r_Jv[r] = (e.r_state[r] == ST_QUADRATIC) ? e.r_D[r] : 0.0f;
+  float h[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) h[k] = (c0 + k < NV) ? e.M[row][c0 + k] : 0.0f;
+  __syncwarp();
+  const float* w = e.r_Jv + nunit;
+  NOUNROLL for (int r = 0; r < nrow; r++) {
+    const float wr = w[r];
+    if (wr == 0.0f) continue;                       // warp-uniform: satisfied / linear / cone rows
+    const float t = wr * e.J[r][row];
+    const float4* rp = reinterpret_cast<const float4*>(e.J[r]) + q0;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const float4 v = rp[q];
+      h[4 * q] = fmaf(t, v.x, h[4 * q]); h[4 * q + 1] = fmaf(t, v.y, h[4 * q + 1]);
+      h[4 * q + 2] = fmaf(t, v.z, h[4 * q + 2]); h[4 * q + 3] = fmaf(t, v.w, h[4 * q + 3]);
+    }
+  }
+  // unit rows (frictionloss / joint limits) only touch the diagonal
+  if ((owner || helper) && row < nv) {
+    float dsum = 0;
+    const int fr = m.dof_frow[row];
+    if (fr >= 0) dsum += e.r_Jv[fr];
+    const int l0 = e.d_lrow[row][0], l1 = e.d_lrow[row][1];
+    if (l0 >= 0) dsum += e.r_Jv[l0];
+    if (l1 >= 0) dsum += e.r_Jv[l1];
+#pragma unroll
+    for (int k = 0; k < 12; k++) if (c0 + k == row) h[k] += dsum;
+  }
+  if (C::CONE == 1) {
+    NOUNROLL for (int ci = 0; ci < e.ncon; ci++) {
+      const int r0 = nunit + e.con_row[ci];
+      if (e.r_state[r0] != ST_CONE) continue;
+      const int dim = e.con_dim[ci], jr0 = r0 - nunit;
+      const float mu = e.con_mu[ci];
+      float TT = 0;
+      NOUNROLL for (int j = 1; j < dim; j++) { float u = e.r_jar[r0 + j] * e.con_fri[ci][j - 1]; TT += u * u; }
+      if (lane < dim) {
+        float sc = lane == 0 ? mu : e.con_fri[ci][lane - 1];
+        e.coneS[lane] = sc; e.coneU[lane] = e.r_jar[r0 + lane] * sc;
+      }
+      __syncwarp();
+      const float N = e.r_jar[r0] * mu, T = sqrtf(TT);
+      const float Dm = e.r_D[r0] / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
+      const float invT = 1.0f / T;
+      const float c1 = mu * N * invT * invT * invT, c2 = mu * mu - mu * N * invT;
+      // Hc (jar space) = Dm S [ e0 e0^T - (mu/T)(e0 U^T + U e0^T) + c1 U U^T + c2 I_t ] S  (U, I_t tangential only):
+      // v = Hc p for this lane's column p_a = J[a][row] in O(dim), then H[row][:] += sum_b v_b J[b][:]
+      const float p0 = e.coneS[0] * e.J[jr0][row];
+      float pU = 0;
+      NOUNROLL for (int a = 1; a < dim; a++) pU = fmaf(e.coneU[a], e.coneS[a] * e.J[jr0 + a][row], pU);
+      const float muT = mu * invT;
+      NOUNROLL for (int b2 = 0; b2 < dim; b2++) {
+        float vb;
+        if (b2 == 0) vb = p0 - muT * pU;
+        else vb = e.coneU[b2] * (c1 * pU - muT * p0) + c2 * e.coneS[b2] * e.J[jr0 + b2][row];
+        vb *= Dm * e.coneS[b2];
+        const float4* rp = reinterpret_cast<const float4*>(e.J[jr0 + b2]) + q0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const float4 v = rp[q];
+          h[4 * q] = fmaf(vb, v.x, h[4 * q]); h[4 * q + 1] = fmaf(vb, v.y, h[4 * q + 1]);
+          h[4 * q + 2] = fmaf(vb, v.z, h[4 * q + 2]); h[4 * q + 3] = fmaf(vb, v.w, h[4 * q + 3]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // owners publish columns 0..11, helpers 12..NV-1 (their columns 8..11 duplicate the owner's values)
+  if (owner) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) e.H[row][k] = h[k];
+  } else if (helper) {
+#pragma unroll
+    for (int k = 4; k < 12; k++) if (c0 + k < NV) e.H[row][c0 + k] = h[k];
+  }
+  __syncwarp();
+  chol_factor<NV, E::NVP>(ms, e.H);
+}
+
+// CUDA build, any nv <= 32: lane i accumulates the whole row i of H in registers
+template <class C>
+LS_FN void make_hessian_wide(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
   typedef EnvS<C> E;
   constexpr int NV = E::NV, JS = E::JS;
@@ -1282,6 +1377,11 @@ LS_FN void make_hessian(const int ms, EnvS<C>& e) {
   }
   __syncwarp();
   chol_factor<NV, E::NVP>(ms, e.H);
+}
+template <class C>
+LS_DEV void make_hessian(const int ms, EnvS<C>& e) {
+  if constexpr (EnvS<C>::JS == 20) make_hessian_split(ms, e);
+  else make_hessian_wide(ms, e);
 }
 #else
 template <class C>
