@@ -98,7 +98,7 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
 // step kernel: one warp per env, EnvS in dynamic shared memory
 // ----------------------------------------------------------------------------------------------------------
 template <class C>
-__global__ void __launch_bounds__(448) step_kernel(int ms, DevTask t, SolverOpts so, EngineState st,
+__global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverOpts so, EngineState st,
                                                     const float* __restrict__ action, float* __restrict__ obs,
                                                     float* __restrict__ reward, uint8_t* __restrict__ done,
                                                     float* __restrict__ next_obs, int n_envs, int auto_reset,
@@ -302,15 +302,15 @@ static int setup_cfg(locosim_handle* h) {
     return (b > 32 ? 32 : b) * w;
   };
   int best = 1, best_env = 0;
-  for (int w = 1; w <= 14; w++) { int ev = envs_per_sm(w); if (ev > best_env) { best_env = ev; best = w; } }
+  for (int w = 1; w <= 16; w++) { int ev = envs_per_sm(w); if (ev > best_env) { best_env = ev; best = w; } }
   // Warps of one block are kept in lock-step with block barriers (every sub-step and every Newton iteration) so that
   // they execute the same code at the same time and share instruction-cache lines; measured on B200 (A1, 4096 envs):
   // no barriers 417k, 2 blocks x 7 warps 564k, 1 block x 14 warps 633k env-steps/s -> take the largest block.
   h->sync_substeps = 1;
-  for (int w = 14; w >= 1; w--) {
+  for (int w = 16; w >= 1; w--) {
     if (envs_per_sm(w) == best_env) { best = w; break; }
   }
-  if (getenv("LOCOSIM_WPB")) { int w = atoi(getenv("LOCOSIM_WPB")); if (w >= 1 && w <= 14 && w * per_env <= dev_max) best = w; }
+  if (getenv("LOCOSIM_WPB")) { int w = atoi(getenv("LOCOSIM_WPB")); if (w >= 1 && w <= 16 && w * per_env <= dev_max) best = w; }
   if (getenv("LOCOSIM_SYNC")) h->sync_substeps = atoi(getenv("LOCOSIM_SYNC"));
   h->so.sync_iters = 1;
   h->regroup = 1;

@@ -136,26 +136,26 @@ struct alignas(16) EnvS {
       con_B[MAXCON], con_incl[MAXCON], con_mu[MAXCON];
   int con_dim[MAXCON], con_g1[MAXCON], con_g2[MAXCON], con_row[MAXCON];
   // Two phases share storage: (a) smooth dynamics scratch, dead once qfrc_smooth / qacc_smooth are known;
-  // (b) constraint rows [0,nunit) unit rows (frictionloss, then joint limits), [nunit, nunit+nrow) contact rows.
+  // (b) the constraint phase: rows [0,nunit) unit rows (frictionloss, then joint limits), [nunit, nunit+nrow) contact
+  //     rows, and the solver's vectors (alive from make_constraint to the integrator).
   union {
     struct {
       float xipos[NB][3], ximat[NB][9], xanchor[NV][3], xaxis[NV][3];
-      float cinert[NB][10], crb[NB][10], cdof_dot[NV][6], cvel[NB][6], cacc[NB][6];
+      float cinert[NB][10], crb[NB][10], cdof_dot[NV][6];
     };
     struct {
-      int r_ti[MAXEFC];                                      // type | id << 8 | k << 24  (k: row within contact / limit side)
       float r_D[MAXEFC], r_aref[MAXEFC], r_jar[MAXEFC], r_Jv[MAXEFC], r_force[MAXEFC];
+      float Ma[NV], grad[NV], Mgrad[NV], search[NV], Mv[NV];   // solver vectors
+      float coneU[8], coneS[8];
+      int r_ti[MAXEFC];                                      // type | id << 8 | k << 24  (k: row within contact / limit side)
+      int d_lrow[NV][2];                                     // limit row of dof d (side 0/1) or -1
       unsigned char r_state[MAXEFC];
     };
   };
-  int d_lrow[NV][2];      // limit row of dof d (side 0/1) or -1
   alignas(16) float J[MAXROW][JS];   // contact Jacobian rows, zero padded to a float4 multiple
-  // solver vectors
-  float Ma[NV], grad[NV], Mgrad[NV], search[NV], Mv[NV];
 #ifdef LS_EMULATE
   float Y[6][NV];
 #endif
-  float coneU[8], coneS[8];
   // task
   float goal[4];
   float grf[3 * LS_MAX_GRF];   // use_foot_forces: per foot group, contact-frame force summed over the sub-steps
@@ -268,8 +268,8 @@ LS_FN void init_workspace(const int ms, EnvS<C>& e) {
   // entries [nv, NV) of the solver vectors are never written by the phases (they loop to nv): keep them 0
   PAR_FOR(i, EnvS<C>::NV) {
     if (i >= m.nv) {
-      e.qacc[i] = 0; e.qacc_ws[i] = 0; e.qacc_smooth[i] = 0; e.search[i] = 0; e.Mgrad[i] = 0; e.grad[i] = 0;
-      e.Ma[i] = 0; e.Mv[i] = 0; e.qfrc_smooth[i] = 0; e.qfrc_constraint[i] = 0; e.qvel[i] = 0; e.qpos[i] = 0;
+      e.qacc[i] = 0; e.qacc_ws[i] = 0; e.qacc_smooth[i] = 0;
+      e.qfrc_smooth[i] = 0; e.qfrc_constraint[i] = 0; e.qvel[i] = 0; e.qpos[i] = 0;
     }
   }
   SYNC();
@@ -1677,7 +1677,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
     float alpha = 0;
     if (active) {
       chol_solve<EnvS<C>::NV, EnvS<C>::NVP>(e.H, e.Mgrad);
-      PAR_FOR(i, nv) e.search[i] = -e.Mgrad[i];
+      PAR_FOR(i, EnvS<C>::NV) e.search[i] = i < nv ? -e.Mgrad[i] : 0.0f;   // (padding read by the unrolled J product)
       SYNC();
       alpha = line_search(ms, e, so, gauss, scale, cost);
       if (alpha == 0) { active = false; force_dirty = (C::CONE == 1); }
