@@ -4,5 +4,5 @@
 #pragma once
 struct CfgEllEuler { enum { NV = 18, NB = 14, NG = 40,  MAXCON = 16, MAXROW = 64, MAXOBS = 64, CONE = 1, RK4 = 0 }; };  // UnitreeA1
 struct CfgPyrEuler { enum { NV = 18, NB = 14, NG = 56,  MAXCON = 16, MAXROW = 64, MAXOBS = 64, CONE = 0, RK4 = 0 }; };  // Talos
-struct CfgPyrRK4   { enum { NV = 19, NB = 14, NG = 104, MAXCON = 16, MAXROW = 64, MAXOBS = 64, CONE = 0, RK4 = 1 }; };  // Atlas, HumanoidTorque
+struct CfgPyrRK4   { enum { NV = 19, NB = 12, NG = 100, MAXCON = 16, MAXROW = 64, MAXOBS = 64, CONE = 0, RK4 = 1 }; };  // Atlas, HumanoidTorque
 struct CfgPyrEuler29 { enum { NV = 29, NB = 26, NG = 48,  MAXCON = 16, MAXROW = 64, MAXOBS = 64, CONE = 0, RK4 = 0 }; };  // UnitreeG1 (29 dofs <= 32 lanes)

@@ -122,7 +122,7 @@ struct alignas(16) EnvS {
          MAXUNIT = 2 * C::NV, MAXEFC = 2 * C::NV + C::MAXROW, NRK = C::RK4 ? C::NV : 1 };
   // state + per-sub-step vectors
   float qpos[NV], qvel[NV], qacc[NV], qacc_ws[NV], ctrl[NV];
-  float qfrc_smooth[NV], qacc_smooth[NV], qfrc_constraint[NV];
+  float qfrc_smooth[NV], qacc_smooth[NV];
   float x0q[NRK], x0v[NRK], accq[NRK], accv[NRK];           // RK4 accumulators (RK4 configurations only)
   // kinematics that stays alive through collision / constraint assembly
   float xpos[NB][3], xquat[NB][4], xmat[NB][9];
@@ -145,7 +145,7 @@ struct alignas(16) EnvS {
     };
     struct {
       float r_D[MAXEFC], r_aref[MAXEFC], r_jar[MAXEFC], r_Jv[MAXEFC], r_force[MAXEFC];
-      float Ma[NV], grad[NV], Mgrad[NV], search[NV], Mv[NV];   // solver vectors
+      float Ma[NV], grad[NV], Mgrad[NV], search[NV], Mv[NV], qfrc_constraint[NV];   // solver vectors
       float coneU[8], coneS[8];
       int r_ti[MAXEFC];                                      // type | id << 8 | k << 24  (k: row within contact / limit side)
       int d_lrow[NV][2];                                     // limit row of dof d (side 0/1) or -1
@@ -269,7 +269,7 @@ LS_FN void init_workspace(const int ms, EnvS<C>& e) {
   PAR_FOR(i, EnvS<C>::NV) {
     if (i >= m.nv) {
       e.qacc[i] = 0; e.qacc_ws[i] = 0; e.qacc_smooth[i] = 0;
-      e.qfrc_smooth[i] = 0; e.qfrc_constraint[i] = 0; e.qvel[i] = 0; e.qpos[i] = 0;
+      e.qfrc_smooth[i] = 0; e.qvel[i] = 0; e.qpos[i] = 0;
     }
   }
   SYNC();
