@@ -206,16 +206,17 @@ def main():
     resets = int(counters[:, 1].sum().item())
 
     # ---- end-to-end through the public API with host buffers ----
-    # per step: H2D of this step's actions (pinned) -> LocoEnv.step -> one packed D2H of (obs, reward, done) -> sync
+    # per step: H2D of this step's actions (pinned) -> LocoEnv.step -> one D2H of the step's (obs, reward, done) -> sync
+    # (the engine keeps the three outputs in one device allocation: eng.packed_out)
     host_actions = (torch.rand((a.steps, N, nu)) * 2 - 1).pin_memory()
-    h_out = torch.empty((N, D + 2), dtype=torch.float32).pin_memory()
+    h_out = torch.empty_like(eng.packed_out, device="cpu").pin_memory()
     d_act = torch.empty((N, nu), dtype=torch.float32, device=dev)
     barrier()
     t0 = time.perf_counter()
     for k in range(a.steps):
         d_act.copy_(host_actions[k], non_blocking=True)
         obs, rew, done, info = env.step(d_act)
-        h_out.copy_(torch.cat([obs, rew[:, None], done[:, None].to(torch.float32)], dim=1), non_blocking=True)
+        h_out.copy_(eng.packed_out, non_blocking=True)
         torch.cuda.synchronize()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -240,7 +241,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": cfg, "clocks": clocks, "gpu_launches": gpu_launches,
                 "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4,
-                        "d2h_bytes_per_step": N * (D + 2) * 4},
+                        "d2h_bytes_per_step": N * (4 * D + 5)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (NCU_TRAFFIC_BYTES.get(robot) if N == 4096 else None), "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)", "peak_source": which, "algorithmic_bytes_per_env_step": bytes_per,
                              "note": "compute/latency-bound by design: state stays in shared memory across the 10 "

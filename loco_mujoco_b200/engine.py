@@ -102,10 +102,14 @@ class CudaEngine:
         self.obs_dim = self.lib.locosim_obs_dim(h)
         self.action_dim = self.lib.locosim_action_dim(h)
         self.nq = self.lib.locosim_nq(h)
-        self.obs = torch.zeros((n_envs, self.obs_dim), dtype=torch.float32, device=self.device)
+        # obs / reward / done of a step live in ONE device allocation (three views), so that a consumer on the host can
+        # fetch the whole step result with a single D2H copy of `packed_out`
+        N, D = int(n_envs), self.obs_dim
+        self.packed_out = torch.zeros((N * (4 * D + 5),), dtype=torch.uint8, device=self.device)
+        self.obs = self.packed_out[:4 * N * D].view(torch.float32).view(N, D)
+        self.reward = self.packed_out[4 * N * D:4 * N * D + 4 * N].view(torch.float32)
+        self.done = self.packed_out[4 * N * D + 4 * N:]
         self.next_obs = torch.zeros((n_envs, self.obs_dim), dtype=torch.float32, device=self.device)
-        self.reward = torch.zeros((n_envs,), dtype=torch.float32, device=self.device)
-        self.done = torch.zeros((n_envs,), dtype=torch.uint8, device=self.device)
         self.launches = 0
         self.kernels_per_step = self.lib.locosim_kernels_per_step(h)
 

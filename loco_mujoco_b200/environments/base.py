@@ -397,7 +397,7 @@ class LocoEnv:
             cb = self._reward_function._reward_callback
             reward = cb(self._obs, action, obs) if cb is not None else torch.zeros_like(reward)
         self._obs = next_obs
-        return obs, reward, done.bool(), info
+        return obs, reward, done.view(torch.bool), info      # (0/1 bytes reinterpreted, no kernel)
 
     def is_absorbing(self, obs):
         return self._has_fallen(obs) if self._use_absorbing_states else False
