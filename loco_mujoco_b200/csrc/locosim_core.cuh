@@ -1816,11 +1816,6 @@ LS_FN void contact_forces(const int ms, EnvS<C>& e, const int* grf_group, int n_
         f1 = (e.r_force[r0] - e.r_force[r0 + 1]) * e.con_fri[ci][0];
         if (dim > 2) f2 = (e.r_force[r0 + 2] - e.r_force[r0 + 3]) * e.con_fri[ci][1];
       }
-#if !defined(LS_EMULATE) && defined(LS_DEBUG_GRF)
-      if ((int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) == LS_DEBUG_GRF)
-        printf("grf k %d ci %d of %d g %d-%d dim %d r0 %d -> %.3f %.3f %.3f\n", k, ci, ncon, e.con_g1[ci], e.con_g2[ci], dim, r0,
-               f0, f1, f2);
-#endif
       e.grf[3 * k] += f0; e.grf[3 * k + 1] += f1; e.grf[3 * k + 2] += f2;
     }
   }
