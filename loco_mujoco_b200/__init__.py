@@ -8,7 +8,7 @@ loco_mujoco_b200: B200-native batched `LocoEnv.step()`.
 __version__ = "0.1.0"
 
 from .environments import LocoEnv
-from .environments.gymnasium import GymnasiumWrapper, make_gym
+from .environments.gymnasium import GymnasiumWrapper, VectorGymnasiumWrapper, make_gym
 
 
 def get_all_task_names():

@@ -76,6 +76,49 @@ class GymnasiumWrapper(_Base):
             _spaces.Box(low, high, space.shape, np.float64)
 
 
+class VectorGymnasiumWrapper:
+    """Batched counterpart with the Gymnasium VectorEnv call contract: `num_envs` independent copies on
+    one GPU, autoreset in the same step ("SAME_STEP" mode: for sub-envs that terminated, `obs` is already the first
+    observation of the next episode and `info["final_obs"]` holds the terminal observation of ALL sub-envs, to be
+    masked with `terminated`). Tensors stay on the device (torch.cuda) unless `to_numpy=True`.
+    The reference has no vector interface; its single-env wrapper is `GymnasiumWrapper` (gymnasium.py:11-173)."""
+
+    def __init__(self, env_name, num_envs, device="cuda:0", seed=0, to_numpy=False, **kwargs):
+        self._env = LocoEnv.make(env_name, num_envs=num_envs, device=device, seed=seed, **kwargs)
+        self.num_envs = int(num_envs)
+        self._to_numpy = to_numpy
+        one_obs, one_act = self._env.info.observation_space, self._env.info.action_space
+        self.single_observation_space = GymnasiumWrapper._convert_space(one_obs)
+        self.single_action_space = GymnasiumWrapper._convert_space(one_act)
+        self.observation_space = _spaces.Box(np.min(one_obs.low), np.max(one_obs.high),
+                                             shape=(self.num_envs,) + tuple(one_obs.shape), dtype=np.float64)
+        self.action_space = _spaces.Box(np.min(one_act.low), np.max(one_act.high),
+                                        shape=(self.num_envs,) + tuple(one_act.shape), dtype=np.float64)
+        self.metadata = {"autoreset_mode": "same_step", "render_fps": 1.0 / self._env.dt}
+
+    def _out(self, t):
+        return t.detach().cpu().numpy() if self._to_numpy else t
+
+    def reset(self, *, seed=None, options=None):
+        return self._out(self._env.reset()), {}
+
+    def step(self, actions):
+        import torch
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.float32), device=self._env._get_engine().device)
+        obs, reward, done, info = self._env.step(actions)
+        truncated = torch.zeros_like(done)
+        return (self._out(info["next_obs"]), self._out(reward), self._out(done), self._out(truncated),
+                {"final_obs": self._out(obs)})
+
+    def close(self):
+        self._env.stop()
+
+    @property
+    def unwrapped(self):
+        return self._env
+
+
 def make_gym(env_id, **kwargs):
     if env_id != "LocoMujoco":
         raise KeyError(env_id)

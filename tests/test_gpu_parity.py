@@ -53,6 +53,21 @@ def test_gymnasium_wrapper_contract(bundled_only):
     assert env.unwrapped.info.action_space.shape == (12,)
 
 
+def test_vector_gymnasium_wrapper(bundled_only):
+    from loco_mujoco_b200 import VectorGymnasiumWrapper
+    venv = VectorGymnasiumWrapper("UnitreeA1.simple.real", num_envs=64, debug=True, seed=3)
+    obs, info = venv.reset()
+    assert tuple(obs.shape) == (64, 37) == venv.observation_space.shape and venv.single_action_space.shape == (12,)
+    n_term = 0
+    for _ in range(30):
+        obs, rew, term, trunc, info = venv.step(torch.rand((64, 12), device="cuda") * 2 - 1)
+        assert not bool(trunc.any()) and tuple(info["final_obs"].shape) == (64, 37)
+        keep = ~term
+        assert torch.equal(obs[keep], info["final_obs"][keep])          # no reset: same observation
+        n_term += int(term.sum())
+    assert n_term > 0 and bool(torch.isfinite(obs).all())
+
+
 def _near_threshold(env, obs, eps=1e-3):
     for key, lo, hi in env._has_fallen_terms():
         v = obs[env.get_obs_idx(key)[0]]
