@@ -96,17 +96,19 @@ def oracle_lib():
     return oracle_binding.load(so)
 
 
-def cpu_rollout(env, seconds, threads):
+def cpu_rollout(env, seconds, threads, rate=None):
     """Time the CPU restatement (oracle/locosim_ref.c ref_rollout: same LocoEnv.step contract, same random-action law,
-    auto-reset) on `threads` host threads for about `seconds`; returns (env-steps/s, description)."""
+    auto-reset) on `threads` host threads for about `seconds`; returns (env-steps/s, description). `rate` (env-steps/s
+    from an earlier call) skips the calibration rollout."""
     from loco_mujoco_b200 import modelpack
     o = oracle_lib()
     mb, tb = modelpack.pack(env._model), env.task_spec().pack()
     n_envs = threads * 4
-    t0 = time.perf_counter()
-    n, _ = o.rollout(mb, tb, n_envs, 25, threads, seed=1)
-    rate = n / (time.perf_counter() - t0)
-    steps = max(25, int(rate * seconds / n_envs))
+    if rate is None:
+        t0 = time.perf_counter()
+        n, _ = o.rollout(mb, tb, n_envs, 25, threads, seed=1)
+        rate = n / (time.perf_counter() - t0)
+    steps = max(10, int(rate * seconds / n_envs))
     t0 = time.perf_counter()
     n, resets = o.rollout(mb, tb, n_envs, steps, threads, seed=2)
     dt = time.perf_counter() - t0
@@ -130,11 +132,13 @@ def main():
             return
         env = LocoEnv.make(a.task + ".real", debug=True)
         threads = host_threads()
-        per_step = max(2.0, min(20.0, 120.0 / max(1, a.steps + a.warmup)))
+        # every "step" is a bounded sample of the workload; the whole run is sized to ~2.5 minutes whatever K and W are
+        per_step = max(0.25, min(20.0, 150.0 / max(1, a.steps + a.warmup)))
         vals = []
-        desc = ""
+        desc, rate = "", None
         for k in range(a.warmup + a.steps):
-            v, desc = cpu_rollout(env, per_step, threads)
+            v, desc = cpu_rollout(env, per_step, threads, rate)
+            rate = v
             if k >= a.warmup:
                 vals.append(v)
         value = sum(vals) / len(vals)
