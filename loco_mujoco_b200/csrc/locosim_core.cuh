@@ -288,6 +288,38 @@ LS_DEV void rotvec(float* r, const float* q, const float* v) {
 // (2) the kinematic chain, level by level, in quaternion algebra only (the only serial part: per joint one vector
 // rotation and one quaternion product when the joint anchor is the body origin, which it is for almost every joint of
 // the in-scope robots); (3) all bodies in parallel: rotation matrices, inertial frames; then geoms.
+// one body of the kinematic chain; its joints' local data was staged in shared memory by phase 1 of kinematics():
+// xanchor[j] = jnt_pos (body frame), xaxis[j] = jnt_axis (body frame), cdof_dot[j] = {joint quaternion | slide q, .., type,
+// anchor-at-origin flag}; both are overwritten here with the world-frame anchor / axis.
+template <class C>
+LS_DEV void kin_body(EnvS<C>& e, const int b, const int p, const float* bpos, const float* bquat, const int jn,
+                     const int ja) {
+  float pos[3], quat[4], tmp[3];
+  rotvec(tmp, e.xquat[p], bpos);
+  for (int k = 0; k < 3; k++) pos[k] = e.xpos[p][k] + tmp[k];
+  mulquat(quat, e.xquat[p], bquat);
+  NOUNROLL for (int k = 0; k < jn; k++) {
+    const int j = ja + k;
+    const float* o = e.cdof_dot[j];
+    const float jp[3] = {e.xanchor[j][0], e.xanchor[j][1], e.xanchor[j][2]};
+    const float ja_[3] = {e.xaxis[j][0], e.xaxis[j][1], e.xaxis[j][2]};
+    const bool at_origin = o[5] != 0.0f;
+    float anchor[3] = {pos[0], pos[1], pos[2]}, axis[3];
+    if (!at_origin) { rotvec(tmp, quat, jp); anchor[0] += tmp[0]; anchor[1] += tmp[1]; anchor[2] += tmp[2]; }
+    rotvec(axis, quat, ja_);
+    for (int c = 0; c < 3; c++) { e.xanchor[j][c] = anchor[c]; e.xaxis[j][c] = axis[c]; }
+    if (o[4] != 0.0f) {                       // slide
+      for (int c = 0; c < 3; c++) pos[c] += axis[c] * o[0];
+    } else {
+      mulquat(quat, quat, o);
+      if (!at_origin) { rotvec(tmp, quat, jp); for (int c = 0; c < 3; c++) pos[c] = anchor[c] - tmp[c]; }
+    }
+  }
+  const float inv = rsqrtf(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
+  for (int c = 0; c < 3; c++) e.xpos[b][c] = pos[c];
+  for (int c = 0; c < 4; c++) e.xquat[b][c] = quat[c] * inv;
+}
+
 template <class C>
 LS_FN void kinematics(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
@@ -295,48 +327,47 @@ LS_FN void kinematics(const int ms, EnvS<C>& e) {
     e.xpos[0][0] = e.xpos[0][1] = e.xpos[0][2] = 0;
     e.xquat[0][0] = 1; e.xquat[0][1] = e.xquat[0][2] = e.xquat[0][3] = 0;
   }
-  PAR_FOR(j, m.nv) {          // joint-local motion -> cdof_dot[j][0..3] (scratch until smooth_forces)
+  PAR_FOR(j, m.nv) {          // joint-local data -> shared-memory scratch (cdof_dot is free until smooth_forces)
     const float q = e.qpos[j] - m.qpos0[j];
     float* o = e.cdof_dot[j];
-    if (m.jnt_type[j] == LS_JNT_SLIDE) { o[0] = q; }
+    const float ax = m.jnt_axis[3 * j], ay = m.jnt_axis[3 * j + 1], az = m.jnt_axis[3 * j + 2];
+    const float px = m.jnt_pos[3 * j], py = m.jnt_pos[3 * j + 1], pz = m.jnt_pos[3 * j + 2];
+    e.xaxis[j][0] = ax; e.xaxis[j][1] = ay; e.xaxis[j][2] = az;
+    e.xanchor[j][0] = px; e.xanchor[j][1] = py; e.xanchor[j][2] = pz;
+    o[5] = ((px == 0.0f) & (py == 0.0f) & (pz == 0.0f)) ? 1.0f : 0.0f;
+    if (m.jnt_type[j] == LS_JNT_SLIDE) { o[0] = q; o[4] = 1.0f; }
     else {
       float sn, cs;
       sincosf(0.5f * q, &sn, &cs);
-      o[0] = cs; o[1] = m.jnt_axis[3 * j] * sn; o[2] = m.jnt_axis[3 * j + 1] * sn; o[3] = m.jnt_axis[3 * j + 2] * sn;
+      o[0] = cs; o[1] = ax * sn; o[2] = ay * sn; o[3] = az * sn; o[4] = 0.0f;
     }
   }
   SYNC();
-  for (int lev = 1; lev < m.nlevel; lev++) {
-    PAR_FOR(b, m.nb) {
-      if (m.body_level[b] != lev) continue;
-      const int p = m.body_parentid[b];
-      float pos[3], quat[4], tmp[3];
-      rotvec(tmp, e.xquat[p], m.body_pos + 3 * b);
-      for (int k = 0; k < 3; k++) pos[k] = e.xpos[p][k] + tmp[k];
-      mulquat(quat, e.xquat[p], m.body_quat + 4 * b);
-      const int jn = m.body_jntnum[b], ja = m.body_jntadr[b];
-      NOUNROLL for (int k = 0; k < jn; k++) {
-        const int j = ja + k;
-        const float* jp = m.jnt_pos + 3 * j;
-        const bool at_origin = (jp[0] == 0.0f) & (jp[1] == 0.0f) & (jp[2] == 0.0f);
-        float anchor[3] = {pos[0], pos[1], pos[2]}, axis[3];
-        if (!at_origin) { rotvec(tmp, quat, jp); anchor[0] += tmp[0]; anchor[1] += tmp[1]; anchor[2] += tmp[2]; }
-        rotvec(axis, quat, m.jnt_axis + 3 * j);
-        for (int c = 0; c < 3; c++) { e.xanchor[j][c] = anchor[c]; e.xaxis[j][c] = axis[c]; }
-        const float* o = e.cdof_dot[j];
-        if (m.jnt_type[j] == LS_JNT_SLIDE) {
-          for (int c = 0; c < 3; c++) pos[c] += axis[c] * o[0];
-        } else {
-          mulquat(quat, quat, o);
-          if (!at_origin) { rotvec(tmp, quat, jp); for (int c = 0; c < 3; c++) pos[c] = anchor[c] - tmp[c]; }
-        }
-      }
-      const float inv = rsqrtf(quat[0] * quat[0] + quat[1] * quat[1] + quat[2] * quat[2] + quat[3] * quat[3]);
-      for (int c = 0; c < 3; c++) e.xpos[b][c] = pos[c];
-      for (int c = 0; c < 4; c++) e.xquat[b][c] = quat[c] * inv;
+#ifdef LS_EMULATE
+  for (int lev = 1; lev < m.nlevel; lev++)
+    for (int b = 1; b < m.nb; b++)
+      if (m.body_level[b] == lev)
+        kin_body(e, b, m.body_parentid[b], m.body_pos + 3 * b, m.body_quat + 4 * b, m.body_jntnum[b], m.body_jntadr[b]);
+#else
+  {
+    static_assert(C::NB <= 32, "lane b owns body b");
+    // lane b owns body b (nb <= 32): its constants are loaded once, ahead of the serial level sweep, so that the sweep
+    // itself touches registers and shared memory only
+    const int b = LS_LANE;
+    const bool has = b > 0 && b < m.nb;
+    const int lev_b = has ? m.body_level[b] : -1, par = has ? m.body_parentid[b] : 0;
+    const int jn = has ? m.body_jntnum[b] : 0, ja = has ? m.body_jntadr[b] : 0;
+    float bpos[3] = {0, 0, 0}, bquat[4] = {1, 0, 0, 0};
+    if (has) {
+      for (int c = 0; c < 3; c++) bpos[c] = m.body_pos[3 * b + c];
+      for (int c = 0; c < 4; c++) bquat[c] = m.body_quat[4 * b + c];
     }
-    SYNC();
+    for (int lev = 1; lev < m.nlevel; lev++) {
+      if (lev_b == lev) kin_body(e, b, par, bpos, bquat, jn, ja);
+      SYNC();
+    }
   }
+#endif
   PAR_FOR(b, m.nb) {
     float mat[9], tmp[3], iq[4];
     quat2mat(mat, e.xquat[b]);
