@@ -762,20 +762,18 @@ LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p) {
 }
 
 // contact parameters (mj_contactParam), frame completion (mju_makeFrame) and storage of one raw contact
+// inclusion distance of a contact of the pair (margin - gap): raw contacts with dist >= incl never enter the constraint set
+LS_DEV float pair_incl(const DevModel& m, int g1, int g2, float margin) {
+  return margin - fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
+}
+
+// fill contact slot ci from a raw narrow-phase result: parameter mixing (mj_contactParam), impedance, frame
 template <class C>
-LS_FN void finish_contact(const int ms, EnvS<C>& e, int g1, int g2, float margin, const RawCon* rawk) {
+LS_FN void fill_contact(const int ms, EnvS<C>& e, const int ci, int g1, int g2, float incl, const RawCon* raw) {
   const DevModel& m = c_models[ms];
-  const RawCon* raw = rawk;
-  const int k = 0;
-  int base = e.ncon;
-  if (base >= EnvS<C>::MAXCON) return;
-  do {
+  {
     // contact parameters (mj_contactParam)
     int p1 = m.geom_priority[g1], p2 = m.geom_priority[g2];
-    float gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
-    float incl = margin - gap;
-    if (raw[k].dist >= incl) break;   // not active: never enters the constraint set
-    int ci = base++;
     float fri[3], solref[2], solimp[5];
     if (p1 != p2) {
       int g = p1 > p2 ? g1 : g2;
@@ -796,16 +794,16 @@ LS_FN void finish_contact(const int ms, EnvS<C>& e, int g1, int g2, float margin
       for (int c = 0; c < 5; c++) solimp[c] = mix * m.geom_solimp[5 * g1 + c] + (1 - mix) * m.geom_solimp[5 * g2 + c];
       for (int c = 0; c < 3; c++) fri[c] = fmaxf(PRM(geom_friction)[3 * g1 + c], PRM(geom_friction)[3 * g2 + c]);
     }
-    impedance_KB(solref, solimp, raw[k].dist, incl, m.timestep, &e.con_imp[ci], &e.con_K[ci], &e.con_B[ci]);
+    impedance_KB(solref, solimp, raw->dist, incl, m.timestep, &e.con_imp[ci], &e.con_K[ci], &e.con_B[ci]);
     e.con_fri[ci][0] = fri[0]; e.con_fri[ci][1] = fri[0]; e.con_fri[ci][2] = fri[1]; e.con_fri[ci][3] = fri[2];
     e.con_fri[ci][4] = fri[2];
     e.con_incl[ci] = incl;
-    e.con_dist[ci] = raw[k].dist;
+    e.con_dist[ci] = raw->dist;
     e.con_g1[ci] = g1; e.con_g2[ci] = g2;
-    for (int c = 0; c < 3; c++) e.con_pos[ci][c] = raw[k].pos[c];
+    for (int c = 0; c < 3; c++) e.con_pos[ci][c] = raw->pos[c];
     // mju_makeFrame
     float f[9];
-    for (int c = 0; c < 6; c++) f[c] = raw[k].frame[c];
+    for (int c = 0; c < 6; c++) f[c] = raw->frame[c];
     normalize3(f);
     if (dot3(f + 3, f + 3) < 0.25f) {
       f[3] = f[4] = f[5] = 0;
@@ -816,13 +814,12 @@ LS_FN void finish_contact(const int ms, EnvS<C>& e, int g1, int g2, float margin
     normalize3(f + 3);
     cross3(f + 6, f, f + 3);
     for (int c = 0; c < 9; c++) e.con_frame[ci][c] = f[c];
-  } while (0);
-  e.ncon = base;
+  }
 }
 
-// narrow phase of pair p, appending to the env's contact list (executed by a single lane)
+// narrow phase of pair p: up to 4 raw contacts (one lane per pair)
 template <class C>
-LS_FN void pair_narrow(const int ms, EnvS<C>& e, int p) {
+LS_FN int pair_narrow(const int ms, EnvS<C>& e, int p, RawCon* raw, int* g1_out, int* g2_out, float* margin_out) {
   const DevModel& m = c_models[ms];
   int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
   int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
@@ -832,7 +829,6 @@ LS_FN void pair_narrow(const int ms, EnvS<C>& e, int p) {
   float mat1[9], mat2[9];
   geom_mat(ms, e, g1, mat1);
   geom_mat(ms, e, g2, mat2);
-  RawCon raw[4];
   int n = 0;
   if (t1 == LS_GEOM_PLANE) {
     float nrm[3] = {mat1[2], mat1[5], mat1[8]};
@@ -850,7 +846,8 @@ LS_FN void pair_narrow(const int ms, EnvS<C>& e, int p) {
   } else if (t1 == LS_GEOM_CAPSULE && t2 == LS_GEOM_CAPSULE) {
     n = capsule_capsule(raw, margin, pos1, mat1, size1, pos2, mat2, size2);
   }
-  NOUNROLL for (int k = 0; k < n; k++) finish_contact(ms, e, g1, g2, margin, raw + k);
+  *g1_out = g1; *g2_out = g2; *margin_out = margin;
+  return n;
 }
 
 template <class C>
@@ -859,19 +856,52 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
   LANE0 { e.ncon = 0; }
   SYNC();
 #ifdef LS_EMULATE
-  for (int p = 0; p < m.np; p++) if (pair_filter(ms, e, p)) pair_narrow(ms, e, p);
+  for (int p = 0; p < m.np; p++) {
+    if (!pair_filter(ms, e, p)) continue;
+    RawCon raw[4];
+    int g1, g2; float margin;
+    const int n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
+    const float incl = pair_incl(m, g1, g2, margin);
+    for (int k = 0; k < n; k++)
+      if (raw[k].dist < incl && e.ncon < EnvS<C>::MAXCON) fill_contact(ms, e, e.ncon++, g1, g2, incl, raw + k);
+  }
 #else
+  // 32 candidate pairs at a time: every lane filters its pair, the lanes that hit run the narrow phase in parallel,
+  // an exclusive scan over the lanes' contact counts assigns the slots, i.e. the list order is pair order, contact
+  // order within the pair: the same order as the serial loop (and as the oracle).
   const int lane = LS_LANE;
   for (int base = 0; base < m.np; base += 32) {
-    int p = base + lane;
-    bool hit = (p < m.np) && pair_filter(ms, e, p);
-    unsigned mask = __ballot_sync(0xffffffffu, hit);
-    while (mask) {
-      int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      if (lane == src) pair_narrow(ms, e, p);
-      __syncwarp();
+    const int p = base + lane;
+    const bool hit = (p < m.np) && pair_filter(ms, e, p);
+    RawCon raw[4];
+    int g1 = 0, g2 = 0, n = 0, nact = 0;
+    float margin = 0, incl = 0;
+    if (hit) {
+      n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
+      incl = pair_incl(m, g1, g2, margin);
+      for (int k = 0; k < 4; k++) if (k < n && raw[k].dist < incl) nact++;
     }
+    int incl_sum = nact;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl_sum, d);
+      if (lane >= d) incl_sum += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl_sum, 31);
+    if (total == 0) continue;
+    const int first = e.ncon + incl_sum - nact;
+    if (nact > 0) {
+      int w = 0;
+      for (int k = 0; k < 4; k++) {
+        if (k < n && raw[k].dist < incl) {
+          const int ci = first + w++;
+          if (ci < EnvS<C>::MAXCON) fill_contact(ms, e, ci, g1, g2, incl, raw + k);
+        }
+      }
+    }
+    __syncwarp();
+    LANE0 { const int nc = e.ncon + total; e.ncon = nc < EnvS<C>::MAXCON ? nc : EnvS<C>::MAXCON; }
+    __syncwarp();
   }
 #endif
   SYNC();
