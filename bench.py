@@ -29,7 +29,7 @@ os.environ.setdefault("LOCO_MUJOCO_B200_FORCE_BUNDLED", "1")     # the GPU box h
 
 ALGO_BYTES = {"UnitreeA1": 633, "HumanoidTorque": 657, "Atlas": 549, "Talos": 621}
 # DRAM bytes per launch of step_kernel from the last committed `ncu --set full` capture (profiles/README.md), 4096 envs
-NCU_TRAFFIC_BYTES = {"UnitreeA1": 10.5e6, "HumanoidTorque": 15.2e6}
+NCU_TRAFFIC_BYTES = {"UnitreeA1": 11.4e6, "HumanoidTorque": 15.2e6}
 # FP32 flops per env-step (2*FFMA + FMUL + FADD thread instructions of one launch / 4096 envs, same ncu captures)
 NCU_FLOPS_PER_ENV_STEP = {"UnitreeA1": 1.53e6, "HumanoidTorque": 2.50e6}
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12      # 148 SMs x 128 FMA lanes x 2 flop x 1.965 GHz (non-tensor)
