@@ -237,7 +237,7 @@ def main():
         launch_ms = ms / a.steps
         achieved = bytes_per * N / (launch_ms / 1e3) / 1e9
         cpu = None
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:      # reported at N=1 only
             v, desc = cpu_rollout(env, a.cpu_seconds, host_threads())
             cpu = {"value": v, "unit": "env-steps/s", "cores": host_threads(), "kind": "port", "sample": desc}
         line = {"metric": "env-steps/sec (batched random-action rollout)", "value": value, "unit": "env-steps/s",
