@@ -1,0 +1,77 @@
+"""The engine core (loco_mujoco_b200/csrc/locosim_core.cuh) is written against a handful of macros (PAR_FOR, SYNC,
+WARP_SUM, ...) so that the SAME source also compiles as a serial fp32 program (csrc/locosim_emu.cpp, -DLS_EMULATE).
+That build is a development / test aid only - it is never loaded by the package - and lets the CPU test tier exercise
+the kernel's algorithms (everything except the CUDA-only register/shuffle variants of the dense linear algebra and the
+lane-parallel collision driver) against the reference goldens: whole episodes, fp32, from the golden's first row.
+
+Stated tolerance: |obs - golden| <= 2e-3 over the pinned rows (measured: A1 <= 1e-5, Humanoid <= 1e-4, Talos <= 3e-4,
+Atlas <= 1e-3, G1 <= 3e-5)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, PINNED_ROWS, golden, make_env
+
+TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "Atlas.walk", "Talos.walk", "UnitreeG1.run",
+         "HumanoidTorque4Ages.run.1"]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "liblocosim_emu.so")
+    csrc = os.path.join(ROOT, "loco_mujoco_b200", "csrc")
+    srcs = [os.path.join(csrc, f) for f in ("locosim_emu.cpp", "locosim_core.cuh", "locosim_host.h", "locosim_config.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-Wno-unknown-pragmas", "-o", so, srcs[0], "-lm"])
+    lib = ctypes.CDLL(so)
+    lib.emu_create.restype = ctypes.c_void_p
+    lib.emu_create.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.emu_destroy.argtypes = [ctypes.c_void_p]
+    for f in ("emu_reset", "emu_step", "emu_get_state"):
+        getattr(lib, f).restype = None
+    lib.emu_reset.argtypes = lib.emu_get_state.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.emu_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_fp32_core_tracks_reference_golden(emu, bundled_only, task):
+    from loco_mujoco_b200 import modelpack
+    env = make_env(task)
+    m, spec, g = env._model, env.task_spec(), golden(task)
+    n = PINNED_ROWS.get(task, len(g))
+    ints, reals = modelpack.pack(m)
+    sim = emu.emu_create(_p(ints), len(ints), _p(reals), len(reals))
+    assert sim
+    np.random.seed(0)
+    np.random.randint(0, len(env._models))
+    np.random.randint(0, env.trajectories.number_of_trajectories)
+    np.random.randint(0, env.trajectories.trajectory_length)
+    q, v = np.zeros(m.nq), np.zeros(m.nq)
+    for t, i, val in zip(spec.obs_src_type, spec.obs_src_idx, g[0]):
+        if t == 0:
+            q[i] = val
+        elif t == 1:
+            v[i] = val
+    emu.emu_reset(sim, _p(q), _p(v))
+    worst = 0.0
+    for k in range(1, n):
+        a = np.random.randn(m.nu) * 0.1
+        ctrl = np.zeros(m.nu)
+        ctrl[spec.act_idx] = a * spec.act_delta + spec.act_mean
+        emu.emu_step(sim, _p(ctrl), spec.n_substeps)
+        emu.emu_get_state(sim, _p(q), _p(v))
+        obs = np.array([q[i] if t == 0 else (v[i] if t == 1 else val)
+                        for t, i, val in zip(spec.obs_src_type, spec.obs_src_idx, g[k])])
+        worst = max(worst, float(np.abs(obs - g[k]).max()))
+    emu.emu_destroy(sim)
+    assert worst < 2e-3, "fp32 core drifted %.3e from the golden" % worst
