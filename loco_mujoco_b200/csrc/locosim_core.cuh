@@ -1234,11 +1234,11 @@ LS_FN float constraint_update(const int ms, EnvS<C>& e) {
 }
 
 // qfrc_constraint = J^T force ; returns total cost incl. Gauss term
+// second half of mj_constraintUpdate: qfrc_constraint = J^T force; returns the Gauss term of the cost
 template <class C>
-LS_FN float update_constraint(const int ms, EnvS<C>& e, float* gauss_out) {
+LS_FN float finish_constraint(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
   const int nv = m.nv, nrow = e.nrow, nunit = e.nunit;
-  float cost = constraint_update(ms, e);
   float g = 0;
   PAR_FOR(d, nv) {
     float a = 0;
@@ -1254,6 +1254,12 @@ LS_FN float update_constraint(const int ms, EnvS<C>& e, float* gauss_out) {
   }
   g = WARP_SUM(g);
   SYNC();
+  return g;
+}
+template <class C>
+LS_FN float update_constraint(const int ms, EnvS<C>& e, float* gauss_out) {
+  const float cost = constraint_update(ms, e);
+  const float g = finish_constraint(ms, e);
   *gauss_out = g;
   return cost + g;
 }
@@ -1694,34 +1700,32 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
     PAR_FOR(i, nv) { e.qacc[i] = e.qacc_smooth[i]; e.qfrc_constraint[i] = 0; }
     SYNC();
   } else {
-    // ---- warmstart choice ----
-    PAR_FOR(i, nv) e.qacc[i] = e.qacc_ws[i];
-    SYNC();
-    mulM(ms, e, e.Ma, e.qacc);
-    mulJ(ms, e, e.r_jar, e.qacc);
+    // ---- warmstart choice (mj_solNewton start point): the cost at qacc_smooth is evaluated FIRST, so that the states
+    //      and forces left behind belong to the warmstart, which wins almost always and then needs no re-evaluation ----
+    mulJ(ms, e, e.r_jar, e.qacc_smooth);
     SYNC();
     PAR_FOR(r, nefc) e.r_jar[r] -= e.r_aref[r];
     SYNC();
-    float cw = constraint_update(ms, e);
-    float g = 0;
-    PAR_FOR(i, nv) g += 0.5f * (e.Ma[i] - e.qfrc_smooth[i]) * (e.qacc[i] - e.qacc_smooth[i]);
-    cw += WARP_SUM(g);
+    const float cs = constraint_update(ms, e);          // (Gauss term is 0 at qacc_smooth)
+    PAR_FOR(i, nv) e.qacc[i] = e.qacc_ws[i];
     SYNC();
-    mulJ(ms, e, e.r_Jv, e.qacc_smooth);   // r_Jv used as scratch for J*qacc_smooth
+    mulM(ms, e, e.Ma, e.qacc);
+    mulJ(ms, e, e.r_Jv, e.qacc);
     SYNC();
-    // cost at qacc_smooth: swap in jar = J qacc_smooth - aref
+    // jar <- J qacc_ws - aref, the smooth point's jar is parked in r_Jv
     PAR_FOR(r, nefc) { float t = e.r_jar[r]; e.r_jar[r] = e.r_Jv[r] - e.r_aref[r]; e.r_Jv[r] = t; }
     SYNC();
-    float cs = constraint_update(ms, e);
-    if (cw > cs) {
+    const float cwc = constraint_update(ms, e);
+    gauss = finish_constraint(ms, e);
+    cost = cwc + gauss;
+    if (cost > cs) {                                    // rare: fall back to the unconstrained acceleration
       PAR_FOR(i, nv) e.qacc[i] = e.qacc_smooth[i];
+      PAR_FOR(r, nefc) e.r_jar[r] = e.r_Jv[r];
       SYNC();
       mulM(ms, e, e.Ma, e.qacc);
-    } else {
-      PAR_FOR(r, nefc) e.r_jar[r] = e.r_Jv[r];
+      SYNC();
+      cost = update_constraint(ms, e, &gauss);
     }
-    SYNC();
-    cost = update_constraint(ms, e, &gauss);
     gn = update_gradient(ms, e);
   }
   // ---- Newton iterations ----
