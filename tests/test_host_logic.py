@@ -98,3 +98,55 @@ def test_bundled_assets_match_live_compile():
     a, b = np.load("/tmp/_ls_live.npz"), np.load("/tmp/_ls_bundled.npz")
     for k in a.files:
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_taskspec_v3_layout_and_feature_sources(bundled_only):
+    """Wire format of the task description (include/locosim_task.h, version 3): header fields and array lengths."""
+    from loco_mujoco_b200 import task as T
+    env = make_env("UnitreeA1.simple", use_foot_forces=True)
+    spec = env.task_spec()
+    ints, reals = spec.pack()
+    assert ints[0] == T.MAGIC and ints[1] == T.VERSION == 3 and ints[2] == spec.obs_dim == 49
+    assert ints[16] == 4 and ints[17] == env._model.ngeom                      # TKI_N_GRF, TKI_N_GRF_GEOM
+    nu = len(spec.act_idx)
+    assert len(ints) == 20 + 2 * spec.obs_dim + len(spec.done_terms) + nu + env._model.ngeom
+    n_traj, T_len, ncol = spec.table.shape
+    assert len(reals) == 8 + 2 * nu + 2 * len(spec.done_terms) + n_traj * T_len * ncol
+    assert list(spec.obs_src_type[-12:]) == [T.OBS_GRF] * 12 and list(spec.obs_src_idx[-12:]) == list(range(12))
+    groups = spec.grf_group
+    assert (groups == T.GRF_FLOOR).sum() == 1 and sorted(groups[groups >= 0][groups[groups >= 0] < 127].tolist()) == [0, 1, 2, 3]
+
+
+def test_multi_model_envs_are_parameter_pools(bundled_only):
+    """Carry tasks: one model per weight, pooled; the weight is a user feature of the pool row (OBS_PARAM)."""
+    from loco_mujoco_b200 import task as T
+    from loco_mujoco_b200.domain_randomization import POOL_FIELDS, N_USER
+    env = make_env("Atlas.carry")
+    assert len(env._models) == 4 and [u[0] for u in env._model_user_features] == [0.1, 1.0, 5.0, 10.0]
+    spec = env.task_spec()
+    assert spec.obs_src_type[-1] == T.OBS_PARAM and spec.obs_src_idx[-1] == 0
+    assert env.info.observation_space.shape == (31,) and env.info.observation_space.low[-1] == 0.1
+    pool = env.model_pool()
+    m = env._model
+    dims = dict(nv=m.nq, nbody=m.nbody, ngeom=m.ngeom)
+    n = sum(dims[k] * c for _, k, c in POOL_FIELDS) + 1 + N_USER
+    assert pool.shape == (4, n + (-n) % 4)
+    assert np.allclose(pool[:, n - N_USER], [0.1, 1.0, 5.0, 10.0]) and not np.allclose(pool[0], pool[3])
+    # the heavier box shows up in the torso's mass only
+    mass = np.array([mm.body_mass for mm in env._models])
+    assert np.count_nonzero(np.abs(mass[3] - mass[0]) > 1e-9) == 1 and abs((mass[3] - mass[0]).sum() - 9.9) < 1e-9
+
+
+def test_humanoid_4ages_modes(bundled_only):
+    env = make_env("HumanoidTorque4Ages.run.2")
+    assert env._model_user_features == [(0.0, 1.0)] and env.info.observation_space.shape == (38,)
+    assert abs(env._reward_params["target_velocity"] - 2.5 * 0.6) < 1e-12      # MultiTargetVelocityReward: target x scaling
+    with pytest.raises(NotImplementedError):
+        make_env("HumanoidTorque4Ages.run.all")
+
+
+def test_vector_wrapper_spaces(bundled_only):
+    from loco_mujoco_b200 import VectorGymnasiumWrapper
+    v = VectorGymnasiumWrapper("UnitreeG1.run.real", num_envs=8, debug=True)       # no engine until reset()
+    assert v.observation_space.shape == (8, 56) and v.action_space.shape == (8, 23)
+    assert v.single_observation_space.shape == (56,) and v.metadata["autoreset_mode"] == "same_step"
