@@ -468,6 +468,43 @@ class LocoEnv:
     def _create_observation(self, obs):
         return np.concatenate([obs[2:]]).flatten()
 
+    # hidable parts of the observation, in observation order (POMDP masks; base_robot_humanoid.py:38-90,
+    # base_humanoid_4_ages.py:187-241)
+    _hidable_obs = ("positions", "velocities", "foot_forces")
+
+    def _len_qpos_qvel(self):
+        spec = self.obs_helper.observation_spec
+        n_pos = sum(1 for _, _, ot in spec if ot == ObservationType.JOINT_POS)
+        n_vel = sum(1 for _, _, ot in spec if ot == ObservationType.JOINT_VEL)
+        return n_pos, n_vel
+
+    def get_mask(self, obs_to_hide):
+        """Boolean mask over the observation: False for the parts named in `obs_to_hide` ("positions", "velocities",
+        "foot_forces", and per env "weight" / "env_type")."""
+        if type(obs_to_hide) == str:
+            obs_to_hide = (obs_to_hide,)
+        assert all(x in self._hidable_obs for x in obs_to_hide), "Some of the observations you want to hide are not" \
+                                                                 "supported. Valid observations to hide are %s." \
+                                                                 % (self._hidable_obs,)
+        pos_dim, vel_dim = self._len_qpos_qvel()
+        mask = [np.full(pos_dim - 2, "positions" not in obs_to_hide), np.full(vel_dim, "velocities" not in obs_to_hide)]
+        if self._use_foot_forces:
+            mask.append(np.full(self._get_grf_size(), "foot_forces" not in obs_to_hide))
+        else:
+            assert "foot_forces" not in obs_to_hide, "Creating a mask to hide foot forces without activating " \
+                                                     "the latter is not allowed."
+        n_user = len(self._model_user_features[0])
+        if n_user:
+            key = self._user_feature_name()
+            mask.append(np.full(n_user, key not in obs_to_hide))
+        else:
+            assert not any(k in obs_to_hide for k in ("weight", "env_type")), \
+                "Creating a mask to hide the carried weight / env type without activating the latter is not allowed."
+        return np.concatenate(mask).ravel().astype(bool)
+
+    def _user_feature_name(self):
+        return "weight"
+
     def _preprocess_action(self, action):
         return (np.asarray(action).copy() * self.norm_act_delta) + self.norm_act_mean
 

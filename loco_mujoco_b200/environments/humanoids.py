@@ -167,6 +167,10 @@ class HumanoidTorque4Ages(BaseHumanoid):
     batch needs one engine per scaling (use four envs) and is not offered as a single env."""
     valid_task_confs = ValidTaskConf(tasks=["walk", "run"], modes=["all", "1", "2", "3", "4"], data_types=["real", "perfect"])
     _default_scalings = [0.4, 0.6, 0.8, 1.0]
+    _hidable_obs = ("positions", "velocities", "foot_forces", "env_type")
+
+    def _user_feature_name(self):
+        return "env_type"
 
     def __init__(self, scaling=None, scaling_trajectory_map=None, **kwargs):
         if "use_muscles" in kwargs:

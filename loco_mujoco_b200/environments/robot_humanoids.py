@@ -24,6 +24,7 @@ class BaseRobotHumanoid(LocoEnv):
     _mini_dataset = None
 
     _valid_weights = [0.1, 1.0, 5.0, 10.0]
+    _hidable_obs = ("positions", "velocities", "foot_forces", "weight")
 
     def __init__(self, disable_arms=True, disable_back_joint=True, hold_weight=False, weight_mass=None, **kwargs):
         if hold_weight:

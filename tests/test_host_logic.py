@@ -150,3 +150,15 @@ def test_vector_wrapper_spaces(bundled_only):
     v = VectorGymnasiumWrapper("UnitreeG1.run.real", num_envs=8, debug=True)       # no engine until reset()
     assert v.observation_space.shape == (8, 56) and v.action_space.shape == (8, 23)
     assert v.single_observation_space.shape == (56,) and v.metadata["autoreset_mode"] == "same_step"
+
+
+def test_get_mask_pomdp(bundled_only):
+    """POMDP masks (base_robot_humanoid.py:38-90): parts of the observation by name, in observation order."""
+    e = make_env("Atlas.carry")
+    m = e.get_mask(("velocities", "weight"))
+    assert m.shape == (31,) and m[:14].all() and not m[14:].any()
+    e = make_env("Talos.walk", use_foot_forces=True)
+    m = e.get_mask("foot_forces")
+    assert m.shape == e.info.observation_space.shape == (40,) and m[:34].all() and not m[34:].any()
+    with pytest.raises(AssertionError):
+        make_env("Talos.walk").get_mask("foot_forces")
