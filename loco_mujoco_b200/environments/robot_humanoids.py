@@ -256,6 +256,11 @@ class UnitreeH1(BaseRobotHumanoid):
     def _grf_group_names(self):
         return ["foot_r", "foot_l"]
 
+    def _add_weight(self, h, mass):        # unitreeH1.py:425-444 (the arms keep their default pose)
+        w = h.add(h.find("body", "torso_link"), "body", name="weight")
+        h.add(w, "geom", type="box", size="0.1 0.18 0.1", pos="0.35 0 0.1", group="0", mass=repr(float(mass)))
+        return h
+
     def _modify_xml(self, xml_handle):
         if self._disable_arms:
             for name, quat in _H1_ARM_QUATS.items():       # unitreeH1.py:447-468

@@ -162,3 +162,11 @@ def test_get_mask_pomdp(bundled_only):
     assert m.shape == e.info.observation_space.shape == (40,) and m[:34].all() and not m[34:].any()
     with pytest.raises(AssertionError):
         make_env("Talos.walk").get_mask("foot_forces")
+
+
+def test_unitree_h1_carry_builds(bundled_only):
+    """UnitreeH1.carry (unitreeH1.py:235-296,425-444): four weight models, the weight is observed. No golden row beyond
+    the reset row pins it (H1's mesh-foot contacts), so there is no parity test for it."""
+    env = make_env("UnitreeH1.carry")
+    assert len(env._models) == 4 and env.info.observation_space.shape == (33,)
+    assert [u[0] for u in env._model_user_features] == [0.1, 1.0, 5.0, 10.0]
