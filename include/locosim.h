@@ -69,6 +69,11 @@ int locosim_step(locosim_t* h, const float* d_action, float* d_obs, float* d_rew
 int locosim_get_state(locosim_t* h, float* d_qpos, float* d_qvel, float* d_qacc_warmstart, void* stream);
 int locosim_set_state(locosim_t* h, const float* d_qpos, const float* d_qvel, const float* d_qacc_warmstart, void* stream);
 
+/* Per-episode goal features (UnitreeA1: cos / sin of the goal direction and the goal speed, GoalDirectionVelocity set in
+ * setup() unitreeA1.py:287-291); normally loaded from the reset table, settable for reset(obs=...) (base.py:217-218,633-654).
+ * d_goal fp32 [n_envs, 4]. */
+int locosim_set_goal(locosim_t* h, const float* d_goal, void* stream);
+
 /* Diagnostics: per-env counters since create: [0]=env steps, [1]=resets, [2]=Newton iterations of the last control
  * step (summed over its sub-steps; also the regrouping key), [3]=contacts of the last sub-step, [4]=terminations caused by
  * a non-finite state, [5..7]=max over control steps of [2] / the last sub-step's contacts / constraint rows.  d_out int32 [n_envs, 8]. */

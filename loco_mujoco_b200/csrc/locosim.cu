@@ -63,8 +63,8 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
   int tr, sp;
   int ep = st.episode[env];
   draw_reset(seed, env_off + env, ep, t.n_traj, t.traj_len, &tr, &sp);
-  if (traj_no) tr = traj_no[env];
-  if (step_no) sp = step_no[env];
+  if (traj_no) tr = min(max(traj_no[env], 0), t.n_traj - 1);       // (pinned rows are clamped into the table)
+  if (step_no) sp = min(max(step_no[env], 0), t.traj_len - 1);
   const float* row = t.table + ((size_t)tr * t.traj_len + sp) * ncol;
   int prow = draw_pool_row(seed, env_off + env, ep, st.pool_K);     // the model of this episode (base.py:187-191)
   if (pool_row) prow = min(max(pool_row[env], 0), st.pool_K - 1);
@@ -459,6 +459,11 @@ int locosim_set_state(locosim_t* h, const float* q, const float* v, const float*
   if (v) CK(cudaMemcpyAsync(h->st.qvel, v, bytes, cudaMemcpyDeviceToDevice, s));
   if (w) CK(cudaMemcpyAsync(h->st.ws, w, bytes, cudaMemcpyDeviceToDevice, s));
   else CK(cudaMemsetAsync(h->st.ws, 0, bytes, s));
+  return 0;
+}
+int locosim_set_goal(locosim_t* h, const float* g, void* stream) {
+  if (!g) { h->err = "null buffer"; return 1; }
+  CK(cudaMemcpyAsync(h->st.goal, g, (size_t)h->n_envs * 16, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 int locosim_get_counters(locosim_t* h, int32_t* d_out, void* stream) {

@@ -1318,25 +1318,24 @@ LS_FN void make_hessian_split(const int ms, EnvS<C>& e) {
       const float mu = e.con_mu[ci];
       float TT = 0;
       NOUNROLL for (int j = 1; j < dim; j++) { float u = e.r_jar[r0 + j] * e.con_fri[ci][j - 1]; TT += u * u; }
+      const float N = e.r_jar[r0] * mu, T = sqrtf(TT), invT = 1.0f / T;
       if (lane < dim) {
         float sc = lane == 0 ? mu : e.con_fri[ci][lane - 1];
-        e.coneS[lane] = sc; e.coneU[lane] = e.r_jar[r0 + lane] * sc;
+        e.coneS[lane] = sc; e.coneU[lane] = e.r_jar[r0 + lane] * sc * invT;     // unit tangential direction U / T
       }
       __syncwarp();
-      const float N = e.r_jar[r0] * mu, T = sqrtf(TT);
       const float Dm = e.r_D[r0] / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
-      const float invT = 1.0f / T;
-      const float c1 = mu * N * invT * invT * invT, c2 = mu * mu - mu * N * invT;
-      // Hc (jar space) = Dm S [ e0 e0^T - (mu/T)(e0 U^T + U e0^T) + c1 U U^T + c2 I_t ] S  (U, I_t tangential only):
+      const float kk = mu * N * invT, c2 = mu * mu - kk;
+      // Hc (jar space) = Dm S [ e0 e0^T - mu (e0 u^T + u e0^T) + (mu N / T) u u^T + c2 I_t ] S  with u = U / T (unit,
+      // tangential only; no 1/T^3 factor, which overflows in fp32 for a vanishing tangential velocity), I_t tangential:
       // v = Hc p for this lane's column p_a = J[a][row] in O(dim), then H[row][:] += sum_b v_b J[b][:]
       const float p0 = e.coneS[0] * e.J[jr0][row];
       float pU = 0;
       NOUNROLL for (int a = 1; a < dim; a++) pU = fmaf(e.coneU[a], e.coneS[a] * e.J[jr0 + a][row], pU);
-      const float muT = mu * invT;
       NOUNROLL for (int b2 = 0; b2 < dim; b2++) {
         float vb;
-        if (b2 == 0) vb = p0 - muT * pU;
-        else vb = e.coneU[b2] * (c1 * pU - muT * p0) + c2 * e.coneS[b2] * e.J[jr0 + b2][row];
+        if (b2 == 0) vb = p0 - mu * pU;
+        else vb = e.coneU[b2] * (kk * pU - mu * p0) + c2 * e.coneS[b2] * e.J[jr0 + b2][row];
         vb *= Dm * e.coneS[b2];
         const float4* rp = reinterpret_cast<const float4*>(e.J[jr0 + b2]) + q0;
 #pragma unroll
@@ -1408,24 +1407,22 @@ LS_FN void make_hessian_wide(const int ms, EnvS<C>& e) {
       const float mu = e.con_mu[ci];
       float TT = 0;
       NOUNROLL for (int j = 1; j < dim; j++) { float u = e.r_jar[r0 + j] * e.con_fri[ci][j - 1]; TT += u * u; }
+      const float N = e.r_jar[r0] * mu, T = sqrtf(TT), invT = 1.0f / T;
       if (lane < dim) {
         float sc = lane == 0 ? mu : e.con_fri[ci][lane - 1];
-        e.coneS[lane] = sc; e.coneU[lane] = e.r_jar[r0 + lane] * sc;
+        e.coneS[lane] = sc; e.coneU[lane] = e.r_jar[r0 + lane] * sc * invT;     // unit tangential direction U / T
       }
       __syncwarp();
-      const float N = e.r_jar[r0] * mu, T = sqrtf(TT);
       const float Dm = e.r_D[r0] / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
-      const float invT = 1.0f / T;
-      const float c1 = mu * N * invT * invT * invT, c2 = mu * mu - mu * N * invT;
-      // Hc (jar space) = Dm S [ e0 e0^T - (mu/T)(e0 U^T + U e0^T) + c1 U U^T + c2 I_t ] S  with U, I_t tangential only.
+      const float kk = mu * N * invT, c2 = mu * mu - kk;
+      // Hc (jar space) = Dm S [ e0 e0^T - mu (e0 u^T + u e0^T) + (mu N / T) u u^T + c2 I_t ] S  with u = U / T, I_t tangential.
       // v = Hc p for this lane's column p_a = J[a][lane] in O(dim), then H[lane][:] += sum_b v_b J[b][:]
       float p0 = e.coneS[0] * e.J[jr0][li], pU = 0;
       NOUNROLL for (int a = 1; a < dim; a++) pU = fmaf(e.coneU[a], e.coneS[a] * e.J[jr0 + a][li], pU);
-      const float muT = mu * invT;
       NOUNROLL for (int b = 0; b < dim; b++) {
         float vb;
-        if (b == 0) vb = p0 - muT * pU;
-        else vb = e.coneU[b] * (c1 * pU - muT * p0) + c2 * e.coneS[b] * e.J[jr0 + b][li];
+        if (b == 0) vb = p0 - mu * pU;
+        else vb = e.coneU[b] * (kk * pU - mu * p0) + c2 * e.coneS[b] * e.J[jr0 + b][li];
         vb *= Dm * e.coneS[b];
         const float4* row = reinterpret_cast<const float4*>(e.J[jr0 + b]);
 #pragma unroll
@@ -1489,15 +1486,14 @@ LS_FN void make_hessian(const int ms, EnvS<C>& e) {
       float* scl = e.coneS;
       float TT = 0;
       NOUNROLL for (int j = 1; j < dim; j++) { float u = e.r_jar[r0 + j] * e.con_fri[ci][j - 1]; TT += u * u; }
+      float N = e.r_jar[r0] * mu, T = sqrtf(TT), invT = 1.0f / T;
       PAR_FOR(j, dim) {
         float sc = j == 0 ? mu : e.con_fri[ci][j - 1];
-        scl[j] = sc; U[j] = e.r_jar[r0 + j] * sc;
+        scl[j] = sc; U[j] = e.r_jar[r0 + j] * sc * invT;      // unit tangential direction (see the CUDA variants)
       }
       SYNC();
-      float N = e.r_jar[r0] * mu, T = sqrtf(TT);
       float Dm = e.r_D[r0] / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
-      float invT = 1.0f / T;
-      float c1 = mu * N * invT * invT * invT, c2 = mu * mu - mu * N * invT;
+      float kk = mu * N * invT, c2 = mu * mu - kk;
       // Y[a][d] = sum_b Hc[a][b] J[b][d]
       PAR_FOR(item, dim * nv) {
         int a = item / nv, d = item - a * nv;
@@ -1505,9 +1501,9 @@ LS_FN void make_hessian(const int ms, EnvS<C>& e) {
         NOUNROLL for (int b = 0; b < dim; b++) {
           float h;
           if (a == 0 && b == 0) h = 1;
-          else if (a == 0) h = -mu * U[b] * invT;
-          else if (b == 0) h = -mu * U[a] * invT;
-          else h = c1 * U[a] * U[b] + (a == b ? c2 : 0.0f);
+          else if (a == 0) h = -mu * U[b];
+          else if (b == 0) h = -mu * U[a];
+          else h = kk * U[a] * U[b] + (a == b ? c2 : 0.0f);
           y += Dm * h * scl[a] * scl[b] * e.J[r0 - nunit + b][d];
         }
         e.Y[a][d] = y;
@@ -1596,7 +1592,11 @@ LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alp
         } else if (mu * N + T <= 0) { c += qc; d1 += q1; d2 += q2; }
         else {
           float Dm = D / fmaxf(LS_MINVAL, mu * mu * (1 + mu * mu));
-          float N1 = V0, T1 = (UV + alpha * VV) / T, T2 = VV / T - (UV + alpha * VV) * T1 / (T * T);
+          // T'' = (VV T^2 - W^2) / T^3 >= 0 (Cauchy-Schwarz). In fp32 the difference of the two quotients VV/T - W^2/T^3
+          // cancels catastrophically where the tangential velocity passes through ~0 on the search line and came out
+          // hugely negative: d2 <= 0 -> "curvature" LS_MINVAL -> alpha ~ 1e18 -> non-finite state. Clamped numerator.
+          const float W = UV + alpha * VV;
+          float N1 = V0, T1 = W / T, T2 = fmaxf(0.0f, VV * Tsqr - W * W) / (T * Tsqr);
           float NmT = N - mu * T, s = N1 - mu * T1;
           c += 0.5f * Dm * NmT * NmT;
           d1 += Dm * NmT * s;
@@ -1613,6 +1613,9 @@ LS_FN LSPoint ls_eval(const int ms, const EnvS<C>& e, const float* qg, float alp
   d2 += 2 * qg[2];
   if (d2 <= 0) d2 = LS_MINVAL;
   LSPoint p = {alpha, c, d1, d2};
+#if defined(LS_EMULATE) && defined(LS_TRACE)
+  printf("    ls_eval alpha %.6e cost %.9e d1 %.6e d2 %.6e (qg %.4e %.4e %.4e)\n", alpha, c, d1, d2, qg[0], qg[1], qg[2]);
+#endif
   return p;
 }
 
@@ -1642,9 +1645,12 @@ LS_FN float line_search(const int ms, EnvS<C>& e, const SolverOpts so, float gau
   if (C::CONE == 1) ls_prepare(ms, e);
   // The point alpha = 0 needs no evaluation: its cost is the current cost, its slope is grad . search and, because
   // search = -H^-1 grad with the exact Hessian of this point, its curvature search^T H search equals -slope.
-  LSPoint p0 = {0.0f, cost0, gs, gs < 0 ? -gs : LS_MINVAL};
+  // (gs >= 0 -- the fp32 factorisation lost positive definiteness and `search` is not a descent direction -- is rare:
+  //  then the point is evaluated honestly, so that its curvature is the true, positive one.)
+  LSPoint p0 = {0.0f, cost0, gs, -gs};
+  if (!(gs < 0)) p0 = ls_eval(ms, e, qg, 0.0f);
   LSPoint p1 = ls_eval(ms, e, qg, p0.alpha - p0.d1 / p0.d2);
-  if (p0.cost < p1.cost) p1 = p0;
+  if (!(p1.cost <= p0.cost)) p1 = p0;               // (also catches a non-finite evaluation)
   if (fabsf(p1.d1) < gtol) return p1.alpha;
   int iter = 0;
   float dir = p1.d1 < 0 ? 1.0f : -1.0f;
@@ -1745,6 +1751,7 @@ LS_FN void fwd_constraint(const int ms, EnvS<C>& e, const SolverOpts so) {
       PAR_FOR(i, EnvS<C>::NV) e.search[i] = i < nv ? -e.Mgrad[i] : 0.0f;   // (padding read by the unrolled J product)
       SYNC();
       alpha = line_search(ms, e, so, gauss, scale, cost);
+      if (!(fabsf(alpha) <= 1e30f)) alpha = 0;      // never step to a non-finite point
       if (alpha == 0) { active = false; force_dirty = (C::CONE == 1); }
     }
     BLOCK_SYNC(so.sync_phases & 128);

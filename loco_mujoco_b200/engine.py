@@ -48,6 +48,8 @@ def load_library():
     lib.locosim_get_state.argtypes = [vp, vp, vp, vp, vp]
     lib.locosim_set_state.restype = ip
     lib.locosim_set_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.locosim_set_goal.restype = ip
+    lib.locosim_set_goal.argtypes = [vp, vp, vp]
     lib.locosim_get_counters.restype = ip
     lib.locosim_get_counters.argtypes = [vp, vp, vp]
     lib.locosim_param_pool_row_len.restype = ip
@@ -68,7 +70,7 @@ EXPORTED_SYMBOLS = ["locosim_create", "locosim_destroy", "locosim_last_error", "
                     "locosim_action_dim", "locosim_nq", "locosim_set_solver", "locosim_reset", "locosim_step",
                     "locosim_get_state", "locosim_set_state", "locosim_get_counters", "locosim_launch_info",
                     "locosim_param_pool_row_len", "locosim_set_param_pool", "locosim_get_param_rows",
-                    "locosim_kernels_per_step", "locosim_reset_rows"]
+                    "locosim_kernels_per_step", "locosim_reset_rows", "locosim_set_goal"]
 
 
 def _ptr(t):
@@ -106,12 +108,16 @@ class CudaEngine:
         # fetch the whole step result with a single D2H copy of `packed_out`
         N, D = int(n_envs), self.obs_dim
         self.packed_out = torch.zeros((N * (4 * D + 5),), dtype=torch.uint8, device=self.device)
-        self.obs = self.packed_out[:4 * N * D].view(torch.float32).view(N, D)
-        self.reward = self.packed_out[4 * N * D:4 * N * D + 4 * N].view(torch.float32)
-        self.done = self.packed_out[4 * N * D + 4 * N:]
+        self.obs, self.reward, self.done = self.views_of(self.packed_out)
         self.next_obs = torch.zeros((n_envs, self.obs_dim), dtype=torch.float32, device=self.device)
         self.launches = 0
         self.kernels_per_step = self.lib.locosim_kernels_per_step(h)
+
+    def views_of(self, packed):
+        """(obs [N, D] f32, reward [N] f32, done [N] u8) views of a buffer laid out like `packed_out`."""
+        N, D, t = self.n_envs, self.obs_dim, self.torch
+        return (packed[:4 * N * D].view(t.float32).view(N, D), packed[4 * N * D:4 * N * D + 4 * N].view(t.float32),
+                packed[4 * N * D + 4 * N:])
 
     def _check(self, rc):
         if rc != 0:
@@ -166,6 +172,12 @@ class CudaEngine:
             if x is not None and (x.dtype != self.torch.float32 or not x.is_contiguous()):
                 raise ValueError("state tensors must be contiguous float32")
         self._check(self.lib.locosim_set_state(self.h, _ptr(qpos), _ptr(qvel), _ptr(qacc_warmstart), self._stream()))
+
+    def set_goal(self, goal):
+        """goal: float32 cuda [n_envs, 4] per-episode goal features (A1: cos, sin, speed)."""
+        if goal.dtype != self.torch.float32 or not goal.is_contiguous() or tuple(goal.shape) != (self.n_envs, 4):
+            raise ValueError("goal must be a contiguous float32 [n_envs, 4] tensor")
+        self._check(self.lib.locosim_set_goal(self.h, _ptr(goal), self._stream()))
 
     def set_param_pool(self, pool):
         """pool: float64 [n_rows, row_len] (domain_randomization.pool_row layout)."""

@@ -137,7 +137,7 @@ class LocoEnv:
                  init_step_no=None, timestep=0.001, use_foot_forces=False, default_camera_mode="follow",
                  use_absorbing_states=True, domain_randomization_config=None, parallel_dom_rand=True,
                  N_worker_per_xml_dom_rand=4, num_envs=None, device="cuda:0", seed=0, env_id_offset=0,
-                 compiled_model=None, **viewer_params):
+                 compiled_model=None, copy_outputs=True, **viewer_params):
         if type(xml_handles) != list:
             xml_handles = [xml_handles]
         self._xml_handles = xml_handles
@@ -194,6 +194,10 @@ class LocoEnv:
         self._device = device
         self._seed = seed
         self._env_id_offset = env_id_offset
+        # Batched mode: the engine writes every step into the same device buffers. copy_outputs=True (default) hands the
+        # caller private copies (two device-to-device copies per step), so that appending them to a rollout buffer is safe;
+        # copy_outputs=False returns views that are only valid until the next step()/reset() (zero-copy, benchmark use).
+        self._copy_outputs = bool(copy_outputs)
         self._engine = None
         self._obs = None
 
@@ -346,33 +350,88 @@ class LocoEnv:
     def reward(self, state, action, next_state, absorbing):
         return self._reward_function(state, action, next_state, absorbing)
 
+    def _state_from_obs(self, obs):
+        """Observation(s) -> (qpos, qvel) [n, nq] (root x / y = 0), goal features [n, n_goal] or None.
+        Reference: LocoEnv._init_sim_from_obs + set_sim_state (base.py:478-497,633-654)."""
+        obs = np.atleast_2d(np.asarray(obs, dtype=np.float64))
+        types, idxs = self._obs_sources()
+        assert obs.shape[1] >= len(types), "observation shorter than the observation specification"
+        nq = self._model.nq
+        q, v = np.zeros((len(obs), nq)), np.zeros((len(obs), nq))
+        goal = np.zeros((len(obs), 4))
+        for k, (t, i) in enumerate(zip(types, idxs)):
+            if t == OBS_QPOS:
+                q[:, i] = obs[:, k]
+            elif t == OBS_QVEL:
+                v[:, i] = obs[:, k]
+            elif t == OBS_GOAL:
+                goal[:, i] = obs[:, k]
+        return q, v, (goal if self._n_goal() else None)
+
+    def _reset_from_obs(self, eng, obs):
+        import torch
+        if torch.is_tensor(obs):
+            obs = obs.detach().cpu().numpy()
+        q, v, goal = self._state_from_obs(obs)
+        assert len(q) == self.num_envs, "reset(obs): one observation per env"
+        if len(self._models) > 1:
+            raise NotImplementedError("reset(obs=...) of a multi-model env")
+        eng.reset()                                   # episode bookkeeping (counters, parameter-pool row, foot forces)
+        f = lambda a: torch.tensor(a, dtype=torch.float32, device=eng.device).contiguous()
+        eng.set_state(f(q), f(v))
+        if goal is not None:
+            eng.set_goal(f(goal))
+        out = f(np.atleast_2d(np.asarray(obs, dtype=np.float64))[:, :eng.obs_dim])
+        if out.shape[1] < eng.obs_dim:                # foot forces / per-model features: zero / unchanged after a reset
+            out = torch.cat([out, eng.next_obs[:, out.shape[1]:]], dim=1)
+        eng.next_obs.copy_(out)
+        return eng.next_obs
+
     def reset(self, obs=None):
         eng = self._get_engine()
         import torch
-        if obs is not None:
-            raise NotImplementedError("reset(obs=...) is not supported by the batched engine yet")
         self._reward_function.reset_state()
+        if obs is None:
+            # argument checks of the reference's setup() (base.py:220-225)
+            if self.trajectories is None and self._random_start:
+                raise ValueError("Random start not possible without trajectory data.")
+            if self.trajectories is None and self._init_step_no is not None:
+                raise ValueError("Setting an initial step is not possible without trajectory data.")
+            if self._init_step_no is not None and self._random_start:
+                raise ValueError("Either use a random start or set an initial step, not both.")
         if not self.batched:
             # reference semantics incl. the legacy global numpy RNG draw order (base.py:187-191, trajectory.py:253-259)
             model_no = np.random.randint(0, len(self._models))
+            self._current_model_idx = model_no
+            if obs is not None:
+                out = self._reset_from_obs(eng, obs)
+                self._obs = out[0].double().cpu().numpy()
+                return self._obs.copy()
             if self._random_start:
-                traj_no = np.random.randint(0, self.trajectories.number_of_trajectories)
-                step_no = np.random.randint(0, self.trajectories.trajectory_length)
+                sample = self.trajectories.reset_trajectory()
             elif self._init_step_no is not None:
-                T = self.trajectories.trajectory_length
-                step_no, traj_no = int(self._init_step_no % T), int(self._init_step_no / T)
+                T, n_traj = self.trajectories.trajectory_length, self.trajectories.number_of_trajectories
+                assert self._init_step_no <= T * n_traj
+                sample = self.trajectories.reset_trajectory(int(self._init_step_no % T), int(self._init_step_no / T))
             else:
-                traj_no, step_no = np.random.randint(0, self.trajectories.number_of_trajectories), 0
-            self.trajectories.traj_no, self.trajectories.subtraj_step_no = traj_no, step_no
+                sample = self.trajectories.reset_trajectory(substep_no=0)
+            traj_no, step_no = self.trajectories.traj_no, self.trajectories.subtraj_step_no
             t = torch.tensor([traj_no], dtype=torch.int32, device=eng.device)
             s = torch.tensor([step_no], dtype=torch.int32, device=eng.device)
             r = torch.tensor([model_no], dtype=torch.int32, device=eng.device) if len(self._models) > 1 else None
             out = eng.reset(traj_no=t, step_no=s, pool_row=r)
-            self._current_model_idx = model_no
+            out = self._post_reset_single(eng, sample, out)
             self._obs = out[0].double().cpu().numpy()
             return self._obs.copy()
-        out = eng.reset()
-        self._obs = out
+        if obs is not None:
+            out = self._reset_from_obs(eng, obs)
+        else:
+            out = eng.reset()
+        self._obs = out.clone() if self._copy_outputs else out
+        return self._obs
+
+    def _post_reset_single(self, eng, sample, out):
+        """Hook of the drop-in single-env reset, after the engine has loaded the trajectory sample (A1: random rotation)."""
         return out
 
     def step(self, action):
@@ -391,11 +450,19 @@ class LocoEnv:
             return cur.copy(), r, absorbing, {}
         if action.dtype != torch.float32:
             action = action.float()
+        prev = self._obs
+        if self._reward_type == "custom" and not self._copy_outputs and prev is not None:
+            prev = prev.clone()          # the engine is about to overwrite the buffer `prev` is a view of
         obs, reward, done, next_obs = eng.step(action.contiguous(), auto_reset=True)
+        if self._copy_outputs:
+            packed = eng.packed_out.clone()
+            obs, reward, done = eng.views_of(packed)
+            next_obs = next_obs.clone()
         info = {"next_obs": next_obs}
         if self._reward_type == "custom":
+            # CustomReward(state, action, next_state): `state` is the observation the action was taken in (base.py:170-176)
             cb = self._reward_function._reward_callback
-            reward = cb(self._obs, action, obs) if cb is not None else torch.zeros_like(reward)
+            reward = cb(prev, action, obs) if cb is not None else torch.zeros_like(reward)
         self._obs = next_obs
         return obs, reward, done.view(torch.bool), info      # (0/1 bytes reinterpreted, no kernel)
 
@@ -427,10 +494,6 @@ class LocoEnv:
         if type(keys) != list:
             keys = [keys]
         return np.concatenate([self.obs_helper.get_from_obs(obs, k) for k in keys])
-
-    def _len_qpos_qvel(self):
-        keys = self.get_all_observation_keys()
-        return len([k for k in keys if k.startswith("q_")]), len([k for k in keys if k.startswith("dq_")])
 
     def _get_observation_space(self):
         lo, hi = self.info.observation_space.low[2:], self.info.observation_space.high[2:]
@@ -605,7 +668,7 @@ class LocoEnv:
     # ---------------------------------------------------------------------------------------------------
     @classmethod
     def register(cls):
-        LocoEnv._registered_envs.setdefault(cls.__name__, cls)
+        LocoEnv._registered_envs[cls.__name__] = cls
 
     @staticmethod
     def list_registered_loco_mujoco():

@@ -9,7 +9,12 @@
  * Section comments name the MuJoCo routine being restated; the reference call site is
  * /root/reference/loco_mujoco/environments/base.py:25,109-111 (inherited MultiMuJoCo.step -> mujoco.mj_step).
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <math.h>
+#include <sched.h>
+#include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1498,7 +1503,7 @@ void refenv_step(RefEnv* e, const double* action, double* obs, double* reward, i
 /* ---- batched CPU baseline loop (pthreads over independent envs) ------------------------------------- */
 typedef struct {
   const int* ints; int n_ints; const double* reals; int n_reals; const int* ti; int nti; const double* tr; int ntr;
-  int env0, env1, n_steps; unsigned long long seed; double* obs_out; long steps, resets;
+  int env0, env1, n_steps; unsigned long long seed; double* obs_out; long steps, resets; double cpu_s;
 } Worker;
 static inline unsigned long long splitmix(unsigned long long* x) {
   unsigned long long z = (*x += 0x9E3779B97F4A7C15ULL);
@@ -1526,24 +1531,62 @@ static void* worker_main(void* arg) {
     if (w->obs_out) memcpy(w->obs_out + (long)env * D, obs, sizeof(double) * D);
   }
   refenv_destroy(e);
+  struct timespec ts;
+  if (clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts) == 0) w->cpu_s = (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
   return NULL;
 }
-long ref_rollout(const int* ints, int n_ints, const double* reals, int n_reals, const int* ti, int nti, const double* tr,
-                 int ntr, int n_envs, int n_steps, int nthreads, unsigned long long seed, double* obs_out,
-                 long* n_resets_out) {
+/* stats_out (may be NULL): [0] wall seconds of the threaded region, [1] sum of the workers' own CPU seconds
+   (CLOCK_THREAD_CPUTIME_ID; [1]/[0] = cores the host actually granted), [2] slowest worker's CPU seconds,
+   [3] number of distinct CPUs the workers were pinned to (0: not pinned). pin != 0: worker t is pinned to the t-th CPU
+   (round robin) of the calling thread's affinity mask. */
+long ref_rollout_ex(const int* ints, int n_ints, const double* reals, int n_reals, const int* ti, int nti, const double* tr,
+                    int ntr, int n_envs, int n_steps, int nthreads, unsigned long long seed, double* obs_out,
+                    long* n_resets_out, int pin, double* stats_out) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > n_envs) nthreads = n_envs;
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
   Worker* ws = (Worker*)calloc(nthreads, sizeof(Worker));
+  cpu_set_t allowed;
+  int cpus[CPU_SETSIZE], ncpu = 0;
+  CPU_ZERO(&allowed);
+  if (pin && sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+    for (int c = 0; c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   for (int t = 0; t < nthreads; t++) {
     Worker w = {ints, n_ints, reals, n_reals, ti, nti, tr, ntr, (int)((long)n_envs * t / nthreads),
-                (int)((long)n_envs * (t + 1) / nthreads), n_steps, seed, obs_out, 0, 0};
+                (int)((long)n_envs * (t + 1) / nthreads), n_steps, seed, obs_out, 0, 0, 0.0};
     ws[t] = w;
-    pthread_create(&th[t], NULL, worker_main, &ws[t]);
+    pthread_attr_t at;
+    pthread_attr_init(&at);
+    if (ncpu > 0) {
+      cpu_set_t one;
+      CPU_ZERO(&one);
+      CPU_SET(cpus[t % ncpu], &one);
+      pthread_attr_setaffinity_np(&at, sizeof(one), &one);
+    }
+    if (pthread_create(&th[t], &at, worker_main, &ws[t]) != 0) pthread_create(&th[t], NULL, worker_main, &ws[t]);
+    pthread_attr_destroy(&at);
   }
   long total = 0, resets = 0;
-  for (int t = 0; t < nthreads; t++) { pthread_join(th[t], NULL); total += ws[t].steps; resets += ws[t].resets; }
+  double cpu_sum = 0, cpu_max = 0;
+  for (int t = 0; t < nthreads; t++) {
+    pthread_join(th[t], NULL);
+    total += ws[t].steps; resets += ws[t].resets; cpu_sum += ws[t].cpu_s;
+    if (ws[t].cpu_s > cpu_max) cpu_max = ws[t].cpu_s;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
   if (n_resets_out) *n_resets_out = resets;
+  if (stats_out) {
+    stats_out[0] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    stats_out[1] = cpu_sum; stats_out[2] = cpu_max; stats_out[3] = ncpu < nthreads ? ncpu : nthreads;
+  }
   free(th); free(ws);
   return total;
+}
+long ref_rollout(const int* ints, int n_ints, const double* reals, int n_reals, const int* ti, int nti, const double* tr,
+                 int ntr, int n_envs, int n_steps, int nthreads, unsigned long long seed, double* obs_out,
+                 long* n_resets_out) {
+  return ref_rollout_ex(ints, n_ints, reals, n_reals, ti, nti, tr, ntr, n_envs, n_steps, nthreads, seed, obs_out,
+                        n_resets_out, 0, NULL);
 }

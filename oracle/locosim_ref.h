@@ -55,6 +55,13 @@ long ref_rollout(const int* ints, int n_ints, const double* reals, int n_reals,
                  int n_envs, int n_steps, int nthreads, unsigned long long seed,
                  double* obs_out /* [n_envs, obs_dim] last obs, may be NULL */,
                  long* n_resets_out);
+/* Same loop with the workers pinned one per allowed CPU (pin != 0) and the time they actually got measured:
+ * stats_out[4] = {wall seconds, sum of worker CPU seconds, slowest worker's CPU seconds, CPUs pinned to}.
+ * cpu/wall is the number of cores the host really granted (a cgroup quota or a busy neighbour shows up here). */
+long ref_rollout_ex(const int* ints, int n_ints, const double* reals, int n_reals,
+                    const int* task_ints, int n_task_ints, const double* task_reals, int n_task_reals,
+                    int n_envs, int n_steps, int nthreads, unsigned long long seed, double* obs_out,
+                    long* n_resets_out, int pin, double* stats_out);
 
 /* single env step of the full LocoEnv.step contract (action in [-1,1]) -> obs, reward, absorbing */
 typedef struct RefEnv RefEnv;

@@ -190,13 +190,18 @@ def test_full_size_batch_properties(bundled_only, task):
     """BASELINE config sizes (4096 envs / GPU): size-independent invariants over a random-action rollout."""
     n = 4096
     env = make_env(task, num_envs=n, seed=0)
+    eng = env._get_engine()
     obs = env.reset()
     nu = env.info.action_space.shape[0]
     terms = env._has_fallen_terms()
     total_done = 0
+    gen = torch.Generator(device="cuda").manual_seed(20260923)
     for k in range(30):
-        act = torch.rand((n, nu), device="cuda") * 2 - 1
+        act = torch.rand((n, nu), device="cuda", generator=gen) * 2 - 1
         obs, rew, done, info = env.step(act)
+        # No env may end in a non-finite state (round 1 had ~3e-6 per env-step: fp32 cancellation in the elliptic-cone
+        # line-search curvature, fixed in locosim_core.cuh ls_eval); checked first, everything below relies on it.
+        assert int(eng.counters()[:, 4].sum()) == 0, "non-finite state at step %d" % k
         assert torch.isfinite(obs).all()
         assert ((rew >= 0) & (rew <= 1)).all()
         if task.startswith("UnitreeA1"):
@@ -207,9 +212,6 @@ def test_full_size_batch_properties(bundled_only, task):
         for key, lo, hi in terms:
             v = obs[:, env.get_obs_idx(key)[0]]
             pred |= (v < np.float32(lo)) | (v > np.float32(hi))
-        nonfinite = (obs == 0).all(dim=1)          # a non-finite state also terminates (obs zeroed); rare (~1e-6)
-        assert torch.equal(pred | nonfinite, done)
-        assert int(nonfinite.sum()) <= 2
-        # joint limits are soft but must roughly hold for the actuated joints
+        assert torch.equal(pred, done)
         total_done += int(done.sum())
     assert 0 < total_done < n * 30
