@@ -93,6 +93,10 @@ int locosim_get_param_rows(locosim_t* h, int32_t* d_out, void* stream);
  * buckets the envs by the solver effort of their previous step (scheduling only; results do not depend on it). */
 int locosim_kernels_per_step(const locosim_t* h);
 
+/* Measurement aid (bench.py): non-tensor FP32 FMA throughput of `device` in TFLOP/s, measured with a register-only
+ * FMA-chain kernel on all SMs (best of 5). Not part of the simulation path. */
+int locosim_measure_fp32_peak(int device, double* tflops_out);
+
 /* Launch geometry chosen for this handle: warps(envs) per block, dynamic shared memory bytes per block, blocks. */
 int locosim_launch_info(const locosim_t* h, int* warps_per_block, int* smem_bytes, int* n_blocks);
 

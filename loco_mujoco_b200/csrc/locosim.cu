@@ -312,16 +312,18 @@ static int setup_cfg(locosim_handle* h) {
   }
   if (getenv("LOCOSIM_WPB")) { int w = atoi(getenv("LOCOSIM_WPB")); if (w >= 1 && w <= 16 && w * per_env <= dev_max) best = w; }
   if (getenv("LOCOSIM_SYNC")) h->sync_substeps = atoi(getenv("LOCOSIM_SYNC"));
-  h->so.sync_iters = 1;
   h->regroup = 1;
   if (getenv("LOCOSIM_REGROUP")) h->regroup = atoi(getenv("LOCOSIM_REGROUP"));
   h->key_shift = C::RK4 ? 2 : 0;   // RK4: four solves per sub-step
   if (getenv("LOCOSIM_KEY_SHIFT")) h->key_shift = atoi(getenv("LOCOSIM_KEY_SHIFT"));
   if (getenv("LOCOSIM_KEY_MODE")) h->key_mode = atoi(getenv("LOCOSIM_KEY_MODE"));
-  if (getenv("LOCOSIM_SYNC_ITERS")) h->so.sync_iters = atoi(getenv("LOCOSIM_SYNC_ITERS"));
+  h->so.sync_iters = 16;    // lock-step group = the whole block
+  if (getenv("LOCOSIM_SYNC_ITERS")) { int v = atoi(getenv("LOCOSIM_SYNC_ITERS")); h->so.sync_iters = v == 1 ? 16 : v; }
+  if (getenv("LOCOSIM_GROUP")) h->so.sync_iters = atoi(getenv("LOCOSIM_GROUP"));
+  if (h->so.sync_iters > 0 && (best + h->so.sync_iters - 1) / h->so.sync_iters > 15) h->so.sync_iters = 16;   // 15 named barriers
   h->so.sync_phases = 32;   // one more barrier where the warps enter the solver (measured +2%)
   if (getenv("LOCOSIM_SYNC_PHASES")) h->so.sync_phases = atoi(getenv("LOCOSIM_SYNC_PHASES"));
-  if (!h->so.sync_iters) h->so.sync_phases &= 63;   // barriers inside the Newton loop need lock-step iterations
+  if (h->so.sync_iters < best) h->so.sync_phases &= 63;   // block barriers inside the Newton loop need whole-block lock-step
   h->wpb = best;
   h->smem = best * per_env;
   CK(cudaFuncSetAttribute(step_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
@@ -512,6 +514,51 @@ int locosim_set_param_pool(locosim_t* h, const double* pool, int n_rows, int row
 }
 
 int locosim_kernels_per_step(const locosim_t* h) { return h->regroup ? 2 : 1; }
+
+// Measured non-tensor FP32 peak (the denominator of the FP32 utilisation bench.py reports next to the HBM roofline):
+// 8 independent FMA chains per thread, 2 x 256 threads per SM slot, all SMs, best of 5 launches.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters) {
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = 1.0f + 1e-3f * (float)(threadIdx.x + k);
+  const float b = 0.9999f, c = 1e-4f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[k] = fmaf(a[k], b, c);
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+int locosim_measure_fp32_peak(int device, double* tflops_out) {
+  if (!tflops_out) return 1;
+  if (cudaSetDevice(device) != cudaSuccess) return 1;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  float* out = nullptr;
+  if (cudaMalloc((void**)&out, (size_t)blocks * threads * 4) != cudaSuccess) return 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0);
+    fp32_peak_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return 1; }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+    if (rep > 0 && ms > 0) best = flops / (ms * 1e-3) / 1e12 > best ? flops / (ms * 1e-3) / 1e12 : best;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops_out = best;
+  return 0;
+}
 
 int locosim_launch_info(const locosim_t* h, int* wpb, int* smem, int* blocks) {
   if (wpb) *wpb = h->wpb;

@@ -45,8 +45,21 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define LS_LANE ((int)(threadIdx.x & 31))
 #define LS_FFS(x) __ffs((int)(x))
 #define LS_CLZ(x) __clz((int)(x))
-// block-wide OR that doubles as a barrier: keeps the warps of a block in the same solver iteration (flag = 0: plain predicate)
-#define BLOCK_ANY(flag, pred) ((flag) ? (__syncthreads_or((pred) ? 1 : 0) != 0) : (pred))
+// OR-reduction that doubles as a barrier: keeps warps in the same solver iteration (flag = 0: plain predicate).
+// flag = number of consecutive warps that iterate in lock-step (a GROUP): flag >= warps per block -> the whole block
+// (__syncthreads_or); smaller groups use one named barrier each (barrier.red with a thread count), so a group only waits
+// for the slowest of its own envs while all groups still execute the same (solver) code region.
+__device__ __forceinline__ bool group_any(int group_warps, bool pred) {
+  const int nw = (int)(blockDim.x >> 5);
+  if (group_warps >= nw) return __syncthreads_or(pred ? 1 : 0) != 0;
+  const int g = (int)(threadIdx.x >> 5) / group_warps;
+  const int first = g * group_warps, cnt = (first + group_warps <= nw ? group_warps : nw - first) * 32;
+  unsigned out, p = pred ? 1u : 0u, id = (unsigned)(1 + g), n = (unsigned)cnt;
+  asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbarrier.cta.red.or.pred q, %2, %3, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+               : "=r"(out) : "r"(p), "r"(id), "r"(n) : "memory");
+  return out != 0;
+}
+#define BLOCK_ANY(flag, pred) ((flag) ? group_any((flag), (pred)) : (pred))
 #define BLOCK_SYNC(flag) do { if (flag) __syncthreads(); } while (0)
 LS_DEV float warp_sum(float v) {
 #pragma unroll
@@ -109,7 +122,7 @@ struct SolverOpts {
   float ls_tolerance;  // relative line-search gradient tolerance
   int max_iter;        // Newton iterations cap
   int ls_iter;         // line-search evaluations cap
-  int sync_iters;      // 1: the warps of a block run the Newton iterations in lock-step (instruction-cache sharing)
+  int sync_iters;      // warps per lock-step group of the Newton iterations (0: none; >= warps per block: the whole block)
   int sync_phases;     // bit mask of extra block barriers at phase boundaries of forward()
 };
 

@@ -60,6 +60,8 @@ def load_library():
     lib.locosim_get_param_rows.argtypes = [vp, vp, vp]
     lib.locosim_kernels_per_step.restype = ip
     lib.locosim_kernels_per_step.argtypes = [vp]
+    lib.locosim_measure_fp32_peak.restype = ip
+    lib.locosim_measure_fp32_peak.argtypes = [ip, ctypes.POINTER(ctypes.c_double)]
     lib.locosim_launch_info.restype = ip
     lib.locosim_launch_info.argtypes = [vp, ctypes.POINTER(ip), ctypes.POINTER(ip), ctypes.POINTER(ip)]
     _LIB = lib
@@ -70,7 +72,15 @@ EXPORTED_SYMBOLS = ["locosim_create", "locosim_destroy", "locosim_last_error", "
                     "locosim_action_dim", "locosim_nq", "locosim_set_solver", "locosim_reset", "locosim_step",
                     "locosim_get_state", "locosim_set_state", "locosim_get_counters", "locosim_launch_info",
                     "locosim_param_pool_row_len", "locosim_set_param_pool", "locosim_get_param_rows",
-                    "locosim_kernels_per_step", "locosim_reset_rows", "locosim_set_goal"]
+                    "locosim_kernels_per_step", "locosim_reset_rows", "locosim_set_goal", "locosim_measure_fp32_peak"]
+
+
+def measure_fp32_peak(device=0):
+    """Measured non-tensor FP32 FMA peak of the device in TFLOP/s (include/locosim.h)."""
+    v = ctypes.c_double(0)
+    if load_library().locosim_measure_fp32_peak(int(device), ctypes.byref(v)) != 0:
+        raise RuntimeError("locosim_measure_fp32_peak failed")
+    return v.value
 
 
 def _ptr(t):
@@ -147,17 +157,31 @@ class CudaEngine:
         self.launches += 1
         return out
 
-    def step(self, action, auto_reset=True, want_next_obs=True):
-        """action: float32 cuda [n_envs, action_dim] (contiguous). Returns (obs, reward, done, next_obs) views."""
+    @property
+    def packed_bytes(self):
+        """Bytes of one step's (obs f32 [N, D] | reward f32 [N] | done u8 [N]) record."""
+        return self.n_envs * (4 * self.obs_dim + 5)
+
+    def step(self, action, auto_reset=True, want_next_obs=True, packed=None):
+        """action: float32 cuda [n_envs, action_dim] (contiguous). Returns (obs, reward, done, next_obs) views.
+        packed: optional uint8 cuda buffer of `packed_bytes` (16-byte aligned, e.g. one time slot of a rollout buffer)
+        the kernel writes this step's obs / reward / done into instead of the engine's own `packed_out`."""
         if action.dtype != self.torch.float32 or not action.is_contiguous() or action.device != self.device:
             raise ValueError("action must be a contiguous float32 tensor on %s" % self.device)
         if tuple(action.shape) != (self.n_envs, self.action_dim):
             raise ValueError("action shape %s != %s" % (tuple(action.shape), (self.n_envs, self.action_dim)))
-        self._check(self.lib.locosim_step(self.h, _ptr(action), _ptr(self.obs), _ptr(self.reward), _ptr(self.done),
+        if packed is None:
+            obs, reward, done = self.obs, self.reward, self.done
+        else:
+            if packed.dtype != self.torch.uint8 or packed.numel() != self.packed_bytes or not packed.is_contiguous() \
+                    or packed.data_ptr() % 4:
+                raise ValueError("packed must be a contiguous, 4-byte aligned uint8 buffer of %d bytes" % self.packed_bytes)
+            obs, reward, done = self.views_of(packed)
+        self._check(self.lib.locosim_step(self.h, _ptr(action), _ptr(obs), _ptr(reward), _ptr(done),
                                           _ptr(self.next_obs) if want_next_obs else None, int(bool(auto_reset)),
                                           self._stream()))
         self.launches += self.kernels_per_step
-        return self.obs, self.reward, self.done, self.next_obs
+        return obs, reward, done, self.next_obs
 
     def get_state(self):
         t = self.torch

@@ -320,11 +320,32 @@ class LocoEnv:
         if self._domain_rand is None:
             from ..domain_randomization import DomainRandomizationHandler
             if self._xml_handles[0] is None:
-                raise ValueError("domain randomisation needs the MJCF source (a loco_mujoco checkout), not bundled assets")
+                self._dr_pool = self._bundled_dr_pool()
+                self._domain_rand = "bundled"
+                return self._dr_pool
             self._domain_rand = DomainRandomizationHandler([self._xml_handles[0].copy()], self._domain_rand_config,
                                                            timestep=self._timestep)
             self._dr_pool = self._domain_rand.build_pool(self._domain_rand_pool_size)
         return self._dr_pool
+
+    def _bundled_dr_pool(self):
+        """Without the MJCF sources (bundled assets only, e.g. on the GPU box) the randomised recompilations cannot be
+        made; for the reference's shipped YAML configs a pre-built seeded pool is bundled (tools/build_dr_pools.py)."""
+        import json
+        task_id = getattr(self, "_task_id", None)
+        path = os.path.join(ASSET_DIR, "dr_pools", "%s.npz" % task_id)
+        if task_id is None or not os.path.exists(path):
+            raise ValueError("domain randomisation needs the MJCF source (a loco_mujoco checkout); no pre-built pool is "
+                             "bundled for %s" % task_id)
+        d = np.load(path, allow_pickle=False)
+        meta = json.loads(str(d["meta"]))
+        conf = self._domain_rand_config
+        ok = (isinstance(conf, str) and os.path.basename(conf) == meta["yaml"]) or conf == meta["config_used"] or \
+            conf == meta["config_shipped"]
+        if not ok:
+            raise ValueError("the bundled pool of %s was built for %s; other configs need the MJCF source"
+                             % (task_id, meta["yaml"]))
+        return np.asarray(d["pool"], dtype=np.float64)
 
     def model_pool(self):
         """[n_models, P] parameter pool of a multi-model env (one row per model incl. its user features)."""

@@ -116,6 +116,7 @@ class BaseRobotHumanoid(LocoEnv):
                 model = modelpack.from_npz_dict({k[6:]: asset[k] for k in asset.files if k.startswith("model_")})
             mdp = cls(reward_type=reward_type, reward_params=reward_params, compiled_model=model, **kwargs)
             mdp.load_trajectory(dict(processed={k[5:]: asset[k] for k in asset.files if k.startswith("traj_")}))
+        mdp._task_id = "%s.%s" % (cls.__name__, task)
         return mdp
 
 

@@ -45,6 +45,116 @@ def gather_rollout(obs, reward, done, group=None):
     return cat[:, :-2], cat[:, -2], cat[:, -1] > 0.5
 
 
+class RolloutGather:
+    """The one collective the path has: an all-gather of the rollout buffer for consumers that want the
+    global batch on every rank. Per-step records are latency bound (4096 envs x 153 B = 0.6 MB), so the engine writes
+    `chunk` consecutive steps straight into one time-major buffer [chunk, record_bytes] (no staging copies: `slot(t)` is
+    handed to `CudaEngine.step(packed=...)`), and ONE `all_gather_into_tensor` per chunk runs on a side stream while
+    the next chunk is being simulated into the second buffer (double buffering, event ordered, no host sync).
+
+        g = RolloutGather(record_bytes, chunk, device)
+        for k in range(steps):
+            eng.step(actions[k], packed=g.slot())      # writes step k of the current chunk
+            g.advance()                                 # after `chunk` steps: launches the gather of the full buffer
+        out = g.finish()                                # [world, chunk, record_bytes] of the last complete chunk
+    """
+
+    def __init__(self, record_bytes, chunk, device, group=None):
+        self.group, self.chunk, self.record_bytes = group, int(chunk), int(record_bytes)
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        pad = (-self.record_bytes) % 16                       # keep every time slot 16-byte aligned
+        self.stride = self.record_bytes + pad
+        self.local = [torch.zeros((self.chunk, self.stride), dtype=torch.uint8, device=device) for _ in range(2)]
+        self.glob = [torch.zeros((self.world, self.chunk, self.stride), dtype=torch.uint8, device=device) for _ in range(2)]
+        on_gpu = torch.device(device).type == "cuda"
+        self.side = torch.cuda.Stream(device=device) if on_gpu else None
+        self.filled = [torch.cuda.Event() for _ in range(2)] if on_gpu else None     # chunk written (compute stream)
+        self.gathered = [torch.cuda.Event() for _ in range(2)] if on_gpu else None   # gather done (side stream)
+        self.cur, self.t, self.n_gathers, self.last = 0, 0, 0, None
+        self._pending = [False, False]
+
+    def slot(self):
+        return self.local[self.cur][self.t, :self.record_bytes]
+
+    def bytes_received_per_chunk(self):
+        return (self.world - 1) * self.chunk * self.stride
+
+    def advance(self):
+        self.t += 1
+        if self.t < self.chunk:
+            return False
+        b = self.cur
+        if self.side is not None:
+            self.filled[b].record()                            # on the caller's (compute) stream
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.filled[b])
+                self._collective(b)
+                self.gathered[b].record()
+        else:
+            self._collective(b)
+        self._pending[b] = True
+        self.last, self.n_gathers = b, self.n_gathers + 1
+        self.cur, self.t = 1 - b, 0
+        if self.side is not None and self._pending[self.cur]:  # the buffer about to be rewritten must have been sent
+            torch.cuda.current_stream().wait_event(self.gathered[self.cur])
+            self._pending[self.cur] = False
+        return True
+
+    def _collective(self, b):
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.glob[b].view(-1), self.local[b].view(-1), group=self.group)
+        else:
+            self.glob[b][0].copy_(self.local[b])
+
+    def finish(self):
+        """Make the compute stream wait for every outstanding gather; returns the last gathered chunk (or None)."""
+        if self.side is not None:
+            for b in range(2):
+                if self._pending[b]:
+                    torch.cuda.current_stream().wait_event(self.gathered[b])
+                    self._pending[b] = False
+        return None if self.last is None else self.glob[self.last][:, :, :self.record_bytes]
+
+
+class MixedBatch:
+    """Heterogeneous batch on ONE GPU (BASELINE config 4: Atlas.walk + Talos.walk): the robots differ in nv, observation
+    size and integrator, i.e. in the step-kernel instantiation, so every member is its own homogeneous engine; the
+    members' kernels are launched on separate CUDA streams and share the SMs (each sub-batch alone does not fill them).
+
+        mb = MixedBatch([("Atlas.walk.real", 1024, {...}), ("Talos.walk.real", 1024, {...})], device="cuda:0", seed=0)
+        obs = mb.reset();  results = mb.step([a_atlas, a_talos])      # lists, one entry per member
+    """
+
+    def __init__(self, members, device="cuda:0", seed=0, env_id_offset=0, **common):
+        from . import LocoEnv
+        self.device = torch.device(device)
+        self.envs, off = [], int(env_id_offset)
+        for task_id, n, kw in members:
+            kw = dict(common, **(kw or {}))
+            self.envs.append(LocoEnv.make(task_id, num_envs=int(n), device=str(self.device), seed=seed, env_id_offset=off, **kw))
+            off += int(n)
+        self.engines = [e._get_engine() for e in self.envs]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.envs]
+        self.num_envs = sum(e.num_envs for e in self.envs)
+
+    def reset(self):
+        return [e.reset() for e in self.envs]
+
+    def step(self, actions, packed=None):
+        """actions: one [n_i, nu_i] tensor per member. All members are enqueued before anything is awaited."""
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        out = []
+        for i, (eng, st) in enumerate(zip(self.engines, self.streams)):
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                out.append(eng.step(actions[i], auto_reset=True, packed=None if packed is None else packed[i]))
+        for st in self.streams:
+            cur.wait_stream(st)
+        return out
+
+
 def aggregate_throughput(local_units, local_seconds, device=None, group=None):
     """Whole-job throughput = units of all ranks / max-over-ranks time (the bench contract)."""
     t = torch.tensor([float(local_seconds)], dtype=torch.float64, device=device)

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from loco_mujoco_b200.parallel import shard_range, gather_rollout, aggregate_throughput
+from loco_mujoco_b200.parallel import shard_range, gather_rollout, aggregate_throughput, RolloutGather
 
 
 def test_shard_range_partitions_the_env_axis():
@@ -32,8 +32,16 @@ def _worker(rank, world, port, n_total, out_dir):
     done = (ids.long() % 3) == 0
     g_obs, g_rew, g_done = gather_rollout(obs, rew, done)
     thr, tmax = aggregate_throughput(local_units=cnt * 7, local_seconds=1.0 + rank)
+    # chunked rollout gather: 7 steps, chunk 3 -> two complete chunks gathered, the last one returned by finish()
+    rec = 37
+    g = RolloutGather(rec, 3, "cpu")
+    n_g = 0
+    for k in range(7):
+        g.slot().copy_(torch.full((rec,), 16 * rank + k, dtype=torch.uint8))
+        n_g += int(g.advance())
+    chunk = g.finish()
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), obs=g_obs.numpy(), rew=g_rew.numpy(), done=g_done.numpy(),
-             thr=thr, tmax=tmax)
+             thr=thr, tmax=tmax, chunk=chunk.numpy(), n_g=n_g, stride=g.stride)
     dist.destroy_process_group()
 
 
@@ -51,3 +59,7 @@ def test_gather_and_throughput_world2(tmp_path):
         assert np.array_equal(d["rew"], ids * 0.5)
         assert np.array_equal(d["done"], (ids.astype(np.int64) % 3) == 0)
         assert d["tmax"] == pytest.approx(2.0) and d["thr"] == pytest.approx(n_total * 7 / 2.0)
+        assert int(d["n_g"]) == 2 and int(d["stride"]) == 48 and d["chunk"].shape == (world, 3, 37)
+        for src in range(world):                 # second chunk = steps 3, 4, 5 of every rank, in rank order
+            for t in range(3):
+                assert (d["chunk"][src, t] == 16 * src + 3 + t).all()
