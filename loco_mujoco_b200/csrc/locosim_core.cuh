@@ -28,6 +28,7 @@ struct alignas(16) float4 { float x, y, z, w; };
 #define SYNC() ((void)0)
 #define WARP_SUM(x) (x)
 #define WARP_MIN(x) (x)
+#define WARP_ARGMAX(v, i) ((void)0)
 #define LANE0
 #define LS_LANE 0
 #define LS_FFS(x) __builtin_ffs((int)(x))
@@ -66,6 +67,15 @@ LS_DEV float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// all lanes end up with the largest v and its index i; ties go to the smaller index (= the first maximum of a serial scan)
+#define WARP_ARGMAX(v, i)                                                                  \
+  do {                                                                                     \
+    _Pragma("unroll") for (int o_ = 16; o_ > 0; o_ >>= 1) {                                \
+      const float ov_ = __shfl_xor_sync(0xffffffffu, (v), o_);                             \
+      const int oi_ = __shfl_xor_sync(0xffffffffu, (i), o_);                               \
+      if (ov_ > (v) || (ov_ == (v) && oi_ < (i))) { (v) = ov_; (i) = oi_; }                \
+    }                                                                                      \
+  } while (0)
 #endif
 
 #define NOUNROLL _Pragma("unroll 1")
@@ -758,6 +768,205 @@ LS_FN int capsule_capsule(RawCon* c, float margin, const float* pos1, const floa
   return n;
 }
 
+
+// ----------------------------------------------------------------------------------------------------------
+// General convex pairs (mesh-mesh, box-mesh): mjc_Convex = libccd's Minkowski Portal Refinement, restated in
+// oracle/locosim_ref.c (ccd_mpr_penetration) where it is pinned by the reference goldens. Here: fp32, ONE pair at a
+// time by the whole warp -- the control flow is warp-uniform, the mesh support function (argmax of dir . vertex over
+// the hull vertices) is the parallel part: lanes stride over the vertices, then a warp argmax.
+// fp32: CCD_EPS -> FLT_EPSILON for the sign tests, relative tests where libccd compares areas with an absolute epsilon;
+// mpr_tolerance stays 1e-6 (the dot products it compares carry ~1e-8 of fp32 noise at these sizes).
+// ----------------------------------------------------------------------------------------------------------
+#define MPR_EPS 1.1920929e-7f
+#define MPR_TOL 1e-6f
+#define MPR_MAXIT 50
+struct MprSup { float v[3], v1[3], v2[3]; };
+struct MprGeom { int type, vadr, vnum; float pos[3], mat[9], size[3], margin; };
+LS_DEV bool mpr_is_zero(float x) { return fabsf(x) < MPR_EPS; }
+LS_DEV bool mpr_eq(float a, float b) {
+  float ab = fabsf(a - b);
+  if (ab < MPR_EPS) return true;
+  a = fabsf(a); b = fabsf(b);
+  return b > a ? ab < MPR_EPS * b : ab < MPR_EPS * a;
+}
+LS_DEV void mpr_normalize(float* d) { const float inv = rsqrtf(dot3(d, d)); d[0] *= inv; d[1] *= inv; d[2] *= inv; }
+
+// mjccd_support of one geom (inflated by margin) in the unit world direction dir; all lanes return the same point
+LS_DEV void mpr_support_geom(const float* __restrict__ mesh_vert, const MprGeom& g, const float* dir, float* res) {
+  float ld[3], r[3] = {0, 0, 0};
+  mulmatTvec3(ld, g.mat, dir);
+  if (g.type == LS_GEOM_MESH) {
+    const float* v = mesh_vert + 3 * g.vadr;
+    float mx = -3.0e38f;
+    int best = 0x7fffffff;
+    PAR_FOR(i, g.vnum) {
+      const float d = ld[0] * v[3 * i] + ld[1] * v[3 * i + 1] + ld[2] * v[3 * i + 2];
+      if (d > mx) { mx = d; best = i; }
+    }
+    WARP_ARGMAX(mx, best);
+    r[0] = v[3 * best]; r[1] = v[3 * best + 1]; r[2] = v[3 * best + 2];
+  } else if (g.type == LS_GEOM_BOX) {
+    for (int k = 0; k < 3; k++) r[k] = ld[k] >= 0 ? g.size[k] : -g.size[k];
+  }
+  mulmatvec3(res, g.mat, r);
+  for (int k = 0; k < 3; k++) res[k] += g.pos[k] + dir[k] * g.margin;
+}
+LS_DEV void mpr_support(const float* __restrict__ mv, const MprGeom& a, const MprGeom& b, const float* dir, MprSup& sp) {
+  const float nd[3] = {-dir[0], -dir[1], -dir[2]};
+  mpr_support_geom(mv, a, dir, sp.v1);
+  mpr_support_geom(mv, b, nd, sp.v2);
+  for (int k = 0; k < 3; k++) sp.v[k] = sp.v1[k] - sp.v2[k];
+#if defined(LS_EMULATE) && defined(LS_TRACE)
+  printf("    [f32] dir %.6f %.6f %.6f -> v %.7f %.7f %.7f\n", dir[0], dir[1], dir[2], sp.v[0], sp.v[1], sp.v[2]);
+#endif
+}
+LS_DEV void mpr_portal_dir(const MprSup* p, float* dir) {
+  float a[3], b[3];
+  for (int k = 0; k < 3; k++) { a[k] = p[2].v[k] - p[1].v[k]; b[k] = p[3].v[k] - p[1].v[k]; }
+  cross3(dir, a, b);
+  mpr_normalize(dir);
+}
+LS_DEV bool mpr_reach_tolerance(const MprSup* p, const MprSup& v4, const float* dir) {
+  const float dv4 = dot3(v4.v, dir);
+  const float d1 = fminf(fminf(dv4 - dot3(p[1].v, dir), dv4 - dot3(p[2].v, dir)), dv4 - dot3(p[3].v, dir));
+  return mpr_eq(d1, MPR_TOL) || d1 < MPR_TOL;
+}
+LS_DEV void mpr_expand_portal(MprSup* p, const MprSup& v4) {
+  float v4v0[3];
+  cross3(v4v0, v4.v, p[0].v);
+  if (dot3(p[1].v, v4v0) > 0) {
+    if (dot3(p[2].v, v4v0) > 0) p[1] = v4; else p[3] = v4;
+  } else {
+    if (dot3(p[3].v, v4v0) > 0) p[2] = v4; else p[1] = v4;
+  }
+}
+LS_DEV float mpr_point_seg_dist2(const float* x0, const float* b, float* wit) {      // distance of the origin
+  float d[3] = {b[0] - x0[0], b[1] - x0[1], b[2] - x0[2]};
+  const float t = -dot3(x0, d) / dot3(d, d);
+  if (t < 0 || mpr_is_zero(t)) { wit[0] = x0[0]; wit[1] = x0[1]; wit[2] = x0[2]; }
+  else if (t > 1 || mpr_eq(t, 1.0f)) { wit[0] = b[0]; wit[1] = b[1]; wit[2] = b[2]; }
+  else for (int k = 0; k < 3; k++) wit[k] = d[k] * t + x0[k];
+  return dot3(wit, wit);
+}
+LS_DEV float mpr_point_tri_dist2(const float* x0, const float* B, const float* C, float* wit) {
+  float d1[3], d2[3];
+  for (int k = 0; k < 3; k++) { d1[k] = B[k] - x0[k]; d2[k] = C[k] - x0[k]; }
+  const float v = dot3(d1, d1), w = dot3(d2, d2), pp = dot3(x0, d1), q = dot3(x0, d2), r = dot3(d1, d2);
+  const float d = w * v - r * r;
+  float s, t, dist;
+  // (libccd tests |d| < DBL_EPSILON; the portal triangle near the origin has edges of ~1e-3 m, so in fp32 the absolute
+  //  test would call every such triangle degenerate: relative test, sin^2 of the corner angle below fp32 resolution)
+  if (!(d > 1e-6f * w * v)) s = t = -1.0f;
+  else { s = (q * r - w * pp) / d; t = (-s * r - q) / w; }
+  if ((mpr_is_zero(s) || s > 0) && (mpr_eq(s, 1.0f) || s < 1) && (mpr_is_zero(t) || t > 0) && (mpr_eq(t, 1.0f) || t < 1) &&
+      (mpr_eq(t + s, 1.0f) || t + s < 1)) {
+    for (int k = 0; k < 3; k++) wit[k] = x0[k] + d1[k] * s + d2[k] * t;
+    dist = dot3(wit, wit);
+  } else {
+    float w2[3], dist2;
+    dist = mpr_point_seg_dist2(x0, B, wit);
+    dist2 = mpr_point_seg_dist2(x0, C, w2);
+    if (dist2 < dist) { dist = dist2; wit[0] = w2[0]; wit[1] = w2[1]; wit[2] = w2[2]; }
+    dist2 = mpr_point_seg_dist2(B, C, w2);
+    if (dist2 < dist) { dist = dist2; wit[0] = w2[0]; wit[1] = w2[1]; wit[2] = w2[2]; }
+  }
+  return dist;
+}
+LS_DEV void mpr_find_pos(const MprSup* p, float* pos) {
+  float dir[3], vec[3], b[4], sum;
+  mpr_portal_dir(p, dir);
+  cross3(vec, p[1].v, p[2].v); b[0] = dot3(vec, p[3].v);
+  cross3(vec, p[3].v, p[2].v); b[1] = dot3(vec, p[0].v);
+  cross3(vec, p[0].v, p[1].v); b[2] = dot3(vec, p[3].v);
+  cross3(vec, p[2].v, p[1].v); b[3] = dot3(vec, p[0].v);
+  sum = b[0] + b[1] + b[2] + b[3];
+  if (mpr_is_zero(sum) || sum < 0) {
+    b[0] = 0;
+    cross3(vec, p[2].v, p[3].v); b[1] = dot3(vec, dir);
+    cross3(vec, p[3].v, p[1].v); b[2] = dot3(vec, dir);
+    cross3(vec, p[1].v, p[2].v); b[3] = dot3(vec, dir);
+    sum = b[1] + b[2] + b[3];
+  }
+  const float inv = 1.0f / sum;
+  float p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+  for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) { p1[k] += p[i].v1[k] * b[i]; p2[k] += p[i].v2[k] * b[i]; }
+  for (int k = 0; k < 3; k++) pos[k] = (p1[k] * inv + p2[k] * inv) * 0.5f;
+}
+// ccdMPRPenetration: true and (depth, dir, pos) if the inflated geoms intersect
+LS_FN bool mpr_penetration(const float* __restrict__ mv, const MprGeom& o1, const MprGeom& o2, float* depth, float* pdir,
+                           float* pos) {
+  MprSup p[4], v4;
+  float dir[3], va[3], vb[3], dot;
+  // ---- discoverPortal ----
+  for (int k = 0; k < 3; k++) { p[0].v1[k] = o1.pos[k]; p[0].v2[k] = o2.pos[k]; p[0].v[k] = o1.pos[k] - o2.pos[k]; }
+  if (mpr_eq(p[0].v[0], 0.0f) && mpr_eq(p[0].v[1], 0.0f) && mpr_eq(p[0].v[2], 0.0f)) p[0].v[0] += MPR_EPS * 10.0f;
+  for (int k = 0; k < 3; k++) dir[k] = -p[0].v[k];
+  mpr_normalize(dir);
+  mpr_support(mv, o1, o2, dir, p[1]);
+  dot = dot3(p[1].v, dir);
+  if (mpr_is_zero(dot) || dot < 0) return false;
+  cross3(dir, p[0].v, p[1].v);
+  if (!(dot3(dir, dir) > 1e-10f * dot3(p[0].v, p[0].v) * dot3(p[1].v, p[1].v))) {      // origin on the segment v0-v1 (relative test)
+    for (int k = 0; k < 3; k++) { pos[k] = 0.5f * (p[1].v1[k] + p[1].v2[k]); pdir[k] = p[1].v[k]; }
+    *depth = sqrtf(dot3(pdir, pdir));
+    if (mpr_is_zero(*depth)) { pdir[0] = pdir[1] = pdir[2] = 0; *depth = 0; }      // touching contact: no normal
+    else mpr_normalize(pdir);
+    return true;
+  }
+  mpr_normalize(dir);
+  mpr_support(mv, o1, o2, dir, p[2]);
+  dot = dot3(p[2].v, dir);
+  if (mpr_is_zero(dot) || dot < 0) return false;
+  for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+  cross3(dir, va, vb);
+  mpr_normalize(dir);
+  if (dot3(dir, p[0].v) > 0) {
+    const MprSup t = p[1]; p[1] = p[2]; p[2] = t;
+    for (int k = 0; k < 3; k++) dir[k] = -dir[k];
+  }
+  NOUNROLL for (int guard = 0; guard < 4 * MPR_MAXIT; guard++) {
+    mpr_support(mv, o1, o2, dir, p[3]);
+    dot = dot3(p[3].v, dir);
+    if (mpr_is_zero(dot) || dot < 0) return false;
+    bool cont = false;
+    cross3(va, p[1].v, p[3].v);
+    dot = dot3(va, p[0].v);
+    if (dot < 0 && !mpr_is_zero(dot)) { p[2] = p[3]; cont = true; }
+    if (!cont) {
+      cross3(va, p[3].v, p[2].v);
+      dot = dot3(va, p[0].v);
+      if (dot < 0 && !mpr_is_zero(dot)) { p[1] = p[3]; cont = true; }
+    }
+    if (!cont) break;
+    for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+    cross3(dir, va, vb);
+    mpr_normalize(dir);
+  }
+  // ---- refinePortal ----
+  NOUNROLL for (int guard = 0;; guard++) {
+    mpr_portal_dir(p, dir);
+    dot = dot3(dir, p[1].v);
+    if (mpr_is_zero(dot) || dot > 0) break;
+    mpr_support(mv, o1, o2, dir, v4);
+    dot = dot3(v4.v, dir);
+    if (!(mpr_is_zero(dot) || dot > 0) || mpr_reach_tolerance(p, v4, dir) || guard > 4 * MPR_MAXIT) return false;
+    mpr_expand_portal(p, v4);
+  }
+  // ---- findPenetr ----
+  NOUNROLL for (int it = 0;; it++) {
+    mpr_portal_dir(p, dir);
+    mpr_support(mv, o1, o2, dir, v4);
+    if (mpr_reach_tolerance(p, v4, dir) || it > MPR_MAXIT) {
+      *depth = sqrtf(mpr_point_tri_dist2(p[1].v, p[2].v, p[3].v, pdir));
+      if (mpr_is_zero(*depth)) pdir[0] = pdir[1] = pdir[2] = 0;
+      else mpr_normalize(pdir);
+      mpr_find_pos(p, pos);
+      return true;
+    }
+    mpr_expand_portal(p, v4);
+  }
+}
+
 // mid-phase test for one candidate pair (see oracle/locosim_ref.c collision(): no margin in the filter)
 template <class C>
 LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p) {
@@ -771,7 +980,49 @@ LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p) {
     return dot3(d, n) <= m.geom_rbound[g2];
   }
   float bound = m.geom_rbound[g1] + m.geom_rbound[g2];
-  return dot3(d, d) <= bound * bound;
+  if (dot3(d, d) > bound * bound) return false;
+  if (m.geom_type[g2] != LS_GEOM_MESH) return true;
+  // Convex pair (box | mesh vs mesh). The first thing MPR does is a separating test along the centre line: with
+  // dir = (c2 - c1) / |c2 - c1| it stops if support1(dir) - support2(-dir) does not reach past the origin. The geoms'
+  // oriented boxes (geom_size = the mesh's AABB in its own frame) contain them, so their supports bound the mesh
+  // supports from above: if even the boxes are separated along dir, MPR would stop at that first test. (Conservative
+  // prefilter: it never rejects a pair MPR would accept; ~98 % of the humanoid's bone pairs end here.)
+  const float dn = sqrtf(dot3(d, d));
+  if (dn < 1e-9f) return true;
+  const float dir[3] = {d[0] / dn, d[1] / dn, d[2] / dn};
+  float m1[9], m2[9], l1[3], l2[3];
+  geom_mat(ms, e, g1, m1);
+  geom_mat(ms, e, g2, m2);
+  mulmatTvec3(l1, m1, dir);
+  mulmatTvec3(l2, m2, dir);
+  const float* s1 = m.geom_size + 3 * g1;
+  const float* s2 = m.geom_size + 3 * g2;
+  const float h = fabsf(l1[0]) * s1[0] + fabsf(l1[1]) * s1[1] + fabsf(l1[2]) * s1[2] + fabsf(l2[0]) * s2[0] +
+                  fabsf(l2[1]) * s2[1] + fabsf(l2[2]) * s2[2] + fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
+  return h * (1.0f + 1e-5f) + 1e-6f >= dn;
+}
+
+// warp-cooperative narrow phase of one convex pair (mjc_Convex): at most one contact
+template <class C>
+LS_FN int convex_narrow(const int ms, const EnvS<C>& e, int p, RawCon* raw) {
+  const DevModel& m = c_models[ms];
+  const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+  const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
+  MprGeom a, b;
+  a.type = m.geom_type[g1]; a.vadr = m.geom_meshadr[g1]; a.vnum = m.geom_meshnum[g1]; a.margin = 0.5f * margin;
+  b.type = m.geom_type[g2]; b.vadr = m.geom_meshadr[g2]; b.vnum = m.geom_meshnum[g2]; b.margin = 0.5f * margin;
+  for (int k = 0; k < 3; k++) {
+    a.pos[k] = e.gxpos[g1][k]; b.pos[k] = e.gxpos[g2][k];
+    a.size[k] = m.geom_size[3 * g1 + k]; b.size[k] = m.geom_size[3 * g2 + k];
+  }
+  geom_mat(ms, e, g1, a.mat);
+  geom_mat(ms, e, g2, b.mat);
+  float depth, dir[3], pos[3];
+  if (!mpr_penetration(m.mesh_vert, a, b, &depth, dir, pos)) return 0;
+  if (dir[0] == 0.0f && dir[1] == 0.0f && dir[2] == 0.0f) return 0;      // contact found but normal undefined
+  raw->dist = margin - depth;
+  for (int k = 0; k < 3; k++) { raw->pos[k] = pos[k]; raw->frame[k] = dir[k]; raw->frame[3 + k] = 0; }
+  return 1;
 }
 
 // contact parameters (mj_contactParam), frame completion (mju_makeFrame) and storage of one raw contact
@@ -873,7 +1124,8 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
     if (!pair_filter(ms, e, p)) continue;
     RawCon raw[4];
     int g1, g2; float margin;
-    const int n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
+    int n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
+    if (m.geom_type[g2] == LS_GEOM_MESH && m.geom_type[g1] >= LS_GEOM_BOX) n = convex_narrow(ms, e, p, raw);
     const float incl = pair_incl(m, g1, g2, margin);
     for (int k = 0; k < n; k++)
       if (raw[k].dist < incl && e.ncon < EnvS<C>::MAXCON) fill_contact(ms, e, e.ncon++, g1, g2, incl, raw + k);
@@ -889,8 +1141,17 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
     RawCon raw[4];
     int g1 = 0, g2 = 0, n = 0, nact = 0;
     float margin = 0, incl = 0;
+    if (hit) n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
+    // convex pairs (box | mesh vs mesh) that survived the prefilter: one at a time, by the whole warp
+    unsigned cm = __ballot_sync(0xffffffffu, hit && m.geom_type[g2] == LS_GEOM_MESH && m.geom_type[g1] >= LS_GEOM_BOX);
+    while (cm) {
+      const int src = __ffs(cm) - 1;
+      cm &= cm - 1;
+      RawCon rc;
+      const int nn = convex_narrow(ms, e, base + src, &rc);
+      if (lane == src) { n = nn; raw[0] = rc; }
+    }
     if (hit) {
-      n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
       incl = pair_incl(m, g1, g2, margin);
       for (int k = 0; k < 4; k++) if (k < n && raw[k].dist < incl) nact++;
     }

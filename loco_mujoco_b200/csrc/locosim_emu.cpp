@@ -55,6 +55,7 @@ struct EmuT : EmuBase {
     o[0] = e.con_g1[k]; o[1] = e.con_g2[k]; o[2] = e.con_dim[k]; o[3] = e.con_dist[k];
     int r0 = e.nunit + e.con_row[k], dim = e.con_dim[k];
     for (int j = 0; j < 8; j++) o[4 + j] = (j < (C::CONE == 1 || dim == 1 ? dim : 2 * (dim - 1))) ? e.r_force[r0 + j] : 0.0;
+    for (int j = 0; j < 3; j++) { o[12 + j] = e.con_frame[k][j]; o[15 + j] = e.con_pos[k][j]; }
   }
   void grf(double* o, int clear) override { for (int k = 0; k < 3 * LS_MAX_GRF; k++) { o[k] = e.grf[k]; if (clear) e.grf[k] = 0; } }
   void bind_prm() override { e.prm = hm.default_row.data(); c_models[0] = m; init_workspace(0, e); }

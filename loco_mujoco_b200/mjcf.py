@@ -777,9 +777,12 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64, fuse_stati
                 continue
             ta, tb = m.geom_type[a], m.geom_type[b]
             supported = (ta == GEOM_PLANE and tb in (GEOM_SPHERE, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH)) or \
-                        (ta, tb) in ((GEOM_SPHERE, GEOM_SPHERE), (GEOM_SPHERE, GEOM_CAPSULE), (GEOM_CAPSULE, GEOM_CAPSULE))
+                        (ta, tb) in ((GEOM_SPHERE, GEOM_SPHERE), (GEOM_SPHERE, GEOM_CAPSULE), (GEOM_CAPSULE, GEOM_CAPSULE),
+                                     (GEOM_MESH, GEOM_MESH), (GEOM_BOX, GEOM_MESH))      # the last two: mjc_Convex (MPR)
             if not supported:
-                dropped.append((a, b))      # box/cylinder/mesh vs non-plane (mjc_Convex / mjc_BoxBox): not built yet
+                # mjc_BoxBox / mjc_CapsuleBox / mjc_SphereBox (dedicated routines) and convex pairs with a smooth geom
+                # (sphere / capsule / cylinder vs cylinder / mesh): not built
+                dropped.append((a, b))
                 continue
             pairs.append((a, b))
     m.npair = len(pairs)
@@ -839,39 +842,24 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64, fuse_stati
 
 def _mesh_prepare(v, f, max_verts=None):
     """
-    Convex hull + recentring of a mesh, like MuJoCo's mesh compile step: the mesh is expressed in the frame of
-    its own centre of mass / principal axes (computed here from the convex hull, uniform density), and geoms
-    referencing it get that transform composed in. Returns (hull_vertices_local, center, quat, aabb_halfsizes).
+    Convex hull + recentring of a mesh, like MuJoCo's mesh compile step (user_mesh.cc, 2.3.7 default
+    inertia="legacy"): the mesh is expressed in the frame of the centre of mass / principal axes of the ORIGINAL
+    triangle mesh under the legacy volume rule (`mesh_legacy_inertia`), and geoms referencing it get that transform
+    composed in. The frame origin is the geom centre libccd's MPR starts from (mjccd_center), so it has to be
+    MuJoCo's; the collision vertices are those of the convex hull. Returns (hull_vertices_local, center, quat,
+    aabb_halfsizes).
     """
     from scipy.spatial import ConvexHull
     hull = ConvexHull(v)
     hv = v[hull.vertices]
-    # volume properties of the hull (signed tetrahedra w.r.t. hull centroid)
-    c0 = hv.mean(axis=0)
-    vol, com = 0.0, np.zeros(3)
-    P = np.zeros((3, 3))
-    tris = []
-    for simplex, eq in zip(hull.simplices, hull.equations):
-        a, b, c = v[simplex] - c0
-        if np.dot(np.cross(b - a, c - a), eq[:3]) < 0:
-            b, c = c, b
-        tris.append((a, b, c))
-        vt = np.dot(a, np.cross(b, c)) / 6.0
-        vol += vt
-        com += vt * (a + b + c) / 4.0
-    com /= vol
-    for a, b, c in tris:
-        a, b, c = a - com, b - com, c - com
-        vt = np.dot(a, np.cross(b, c)) / 6.0
-        S = np.outer(a, a) + np.outer(b, b) + np.outer(c, c)
-        s = a + b + c
-        P += vt / 20.0 * (S + np.outer(s, s))
-    I = np.trace(P) * np.eye(3) - P
+    _, center, I = mesh_legacy_inertia(v, f)
     w, q = _eig_inertia([I[0, 0], I[1, 1], I[2, 2], I[0, 1], I[0, 2], I[1, 2]])
-    center = c0 + com
     R = quat_to_mat(q)
-    local = (hv - center) @ R
-    aabb = np.abs(local).max(axis=0)
+    # MuJoCo stores mesh vertices as float32 AFTER the transformation into this frame (mjModel.mesh_vert is float*);
+    # rounding here the same way reproduces its vertex positions (the rounding is indifferent to the sign / order
+    # conventions of the principal axes)
+    local = ((hv - center) @ R).astype(np.float32).astype(np.float64)
+    aabb = np.abs(((v - center) @ R).astype(np.float32).astype(np.float64)).max(axis=0)
     return local, center, q, aabb
 
 

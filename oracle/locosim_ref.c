@@ -594,6 +594,244 @@ static int capsule_capsule(RawCon* c, double margin, const double* pos1, const d
   return n;
 }
 
+
+/* ---------------------------------------------------------------------------------------------------- */
+/* mjc_Convex: general convex pair = libccd's Minkowski Portal Refinement (ccdMPRPenetration, libccd 2.1 as   */
+/* vendored by MuJoCo 2.3.7; engine_collision_convex.c: mjccd_center / mjccd_support / mjc_MPRIteration).     */
+/* Neither source is under /root/reference (third party): restated from the published algorithm (G. Snethen,  */
+/* "XenoCollide", Game Programming Gems 7; libccd src/mpr.c, src/vec3.c), pinned by the tails of the           */
+/* reference goldens that contain bone-bone contacts (tests/test_oracle_golden.py).                            */
+/* Each object is inflated by margin/2 in the support direction; dist = margin - depth.                        */
+/* ---------------------------------------------------------------------------------------------------- */
+#define CCD_EPS 2.220446049250313e-16
+typedef struct { double v[3], v1[3], v2[3]; } CcdSup;
+typedef struct { const RefSim* s; int g; double margin; } CcdObj;
+static inline int ccd_is_zero(double x) { return fabs(x) < CCD_EPS; }
+static inline int ccd_eq(double a, double b) {
+  double ab = fabs(a - b);
+  if (ab < CCD_EPS) return 1;
+  a = fabs(a); b = fabs(b);
+  return b > a ? ab < CCD_EPS * b : ab < CCD_EPS * a;
+}
+static inline int ccd_vec_eq(const double* a, const double* b) { return ccd_eq(a[0], b[0]) && ccd_eq(a[1], b[1]) && ccd_eq(a[2], b[2]); }
+static inline void ccd_normalize(double* d) { double inv = 1.0 / sqrt(dot3(d, d)); d[0] *= inv; d[1] *= inv; d[2] *= inv; }
+
+/* mjccd_support: farthest point of geom g (inflated by margin) in world direction dir (unit) */
+static void ccd_support_geom(const CcdObj* o, const double* dir, double* res) {
+  const Model* m = &o->s->m;
+  const int g = o->g;
+  const double* mat = o->s->gxmat[g];
+  const double* size = m->geom_size + 3 * g;
+  double ld[3], r[3] = {0, 0, 0};
+  mulmatTvec3(ld, mat, dir);
+  switch (m->geom_type[g]) {
+    case LS_GEOM_SPHERE: for (int k = 0; k < 3; k++) r[k] = ld[k] * size[0]; break;
+    case LS_GEOM_CAPSULE:
+      for (int k = 0; k < 3; k++) r[k] = ld[k] * size[0];
+      r[2] += (ld[2] >= 0 ? 1.0 : -1.0) * size[1];
+      break;
+    case LS_GEOM_CYLINDER: {
+      double t = sqrt(ld[0] * ld[0] + ld[1] * ld[1]);
+      if (t > mjMINVAL) { r[0] = ld[0] / t * size[0]; r[1] = ld[1] / t * size[0]; }
+      r[2] = (ld[2] >= 0 ? 1.0 : -1.0) * size[1];
+      break;
+    }
+    case LS_GEOM_BOX: for (int k = 0; k < 3; k++) r[k] = (ld[k] >= 0 ? 1.0 : -1.0) * size[k]; break;
+    case LS_GEOM_MESH: {
+      const double* v = m->mesh_vert + 3 * m->geom_meshadr[g];
+      int n = m->geom_meshnum[g], best = 0;
+      double mx = -1e300;
+      for (int i = 0; i < n; i++) { double d = dot3(ld, v + 3 * i); if (d > mx) { mx = d; best = i; } }
+      memcpy(r, v + 3 * best, sizeof(r));
+      break;
+    }
+    default: break;
+  }
+  mulmatvec3(res, mat, r);
+  for (int k = 0; k < 3; k++) res[k] += o->s->gxpos[g][k] + dir[k] * o->margin;
+}
+static long g_convex_support;
+static int g_ccd_trace = 0;
+void ref_debug_trace(int on) { g_ccd_trace = on; }
+static void ccd_support(const CcdObj* o1, const CcdObj* o2, const double* dir, CcdSup* sp) {
+  g_convex_support++;
+  double nd[3] = {-dir[0], -dir[1], -dir[2]};
+  ccd_support_geom(o1, dir, sp->v1);
+  ccd_support_geom(o2, nd, sp->v2);
+  for (int k = 0; k < 3; k++) sp->v[k] = sp->v1[k] - sp->v2[k];
+  if (g_ccd_trace) printf("    [f64] g%d-g%d dir %.6f %.6f %.6f -> v %.7f %.7f %.7f\n", o1->g, o2->g, dir[0], dir[1], dir[2], sp->v[0], sp->v[1], sp->v[2]);
+}
+static void ccd_portal_dir(const CcdSup* p, double* dir) {
+  double a[3], b[3];
+  for (int k = 0; k < 3; k++) { a[k] = p[2].v[k] - p[1].v[k]; b[k] = p[3].v[k] - p[1].v[k]; }
+  cross3(dir, a, b);
+  ccd_normalize(dir);
+}
+static int ccd_reach_tolerance(const CcdSup* p, const CcdSup* v4, const double* dir, double tol) {
+  double dv1 = dot3(p[1].v, dir), dv2 = dot3(p[2].v, dir), dv3 = dot3(p[3].v, dir), dv4 = dot3(v4->v, dir);
+  double d1 = dv4 - dv1, d2 = dv4 - dv2, d3 = dv4 - dv3;
+  d1 = d1 < d2 ? d1 : d2;
+  d1 = d1 < d3 ? d1 : d3;
+  return ccd_eq(d1, tol) || d1 < tol;
+}
+static void ccd_expand_portal(CcdSup* p, const CcdSup* v4) {
+  double v4v0[3];
+  cross3(v4v0, v4->v, p[0].v);
+  if (dot3(p[1].v, v4v0) > 0) {
+    if (dot3(p[2].v, v4v0) > 0) p[1] = *v4; else p[3] = *v4;
+  } else {
+    if (dot3(p[3].v, v4v0) > 0) p[2] = *v4; else p[1] = *v4;
+  }
+}
+static double ccd_point_seg_dist2(const double* P, const double* x0, const double* b, double* wit) {
+  double d[3], a[3];
+  for (int k = 0; k < 3; k++) { d[k] = b[k] - x0[k]; a[k] = x0[k] - P[k]; }
+  double t = -dot3(a, d) / dot3(d, d);
+  if (t < 0 || ccd_is_zero(t)) memcpy(wit, x0, 3 * sizeof(double));
+  else if (t > 1 || ccd_eq(t, 1.0)) memcpy(wit, b, 3 * sizeof(double));
+  else for (int k = 0; k < 3; k++) wit[k] = d[k] * t + x0[k];
+  double e[3] = {wit[0] - P[0], wit[1] - P[1], wit[2] - P[2]};
+  return dot3(e, e);
+}
+static double ccd_point_tri_dist2(const double* P, const double* x0, const double* B, const double* C, double* wit) {
+  double d1[3], d2[3], a[3];
+  for (int k = 0; k < 3; k++) { d1[k] = B[k] - x0[k]; d2[k] = C[k] - x0[k]; a[k] = x0[k] - P[k]; }
+  double v = dot3(d1, d1), w = dot3(d2, d2), p = dot3(a, d1), q = dot3(a, d2), r = dot3(d1, d2);
+  double d = w * v - r * r, s, t, dist;
+  if (ccd_is_zero(d)) s = t = -1.0;
+  else { s = (q * r - w * p) / d; t = (-s * r - q) / w; }
+  if ((ccd_is_zero(s) || s > 0) && (ccd_eq(s, 1.0) || s < 1) && (ccd_is_zero(t) || t > 0) && (ccd_eq(t, 1.0) || t < 1) &&
+      (ccd_eq(t + s, 1.0) || t + s < 1)) {
+    for (int k = 0; k < 3; k++) wit[k] = x0[k] + d1[k] * s + d2[k] * t;
+    double e[3] = {wit[0] - P[0], wit[1] - P[1], wit[2] - P[2]};
+    dist = dot3(e, e);
+  } else {
+    double w2[3], dist2;
+    dist = ccd_point_seg_dist2(P, x0, B, wit);
+    dist2 = ccd_point_seg_dist2(P, x0, C, w2);
+    if (dist2 < dist) { dist = dist2; memcpy(wit, w2, sizeof(w2)); }
+    dist2 = ccd_point_seg_dist2(P, B, C, w2);
+    if (dist2 < dist) { dist = dist2; memcpy(wit, w2, sizeof(w2)); }
+  }
+  return dist;
+}
+static void ccd_find_pos(const CcdSup* p, double* pos) {
+  double dir[3], vec[3], b[4], sum;
+  ccd_portal_dir(p, dir);
+  cross3(vec, p[1].v, p[2].v); b[0] = dot3(vec, p[3].v);
+  cross3(vec, p[3].v, p[2].v); b[1] = dot3(vec, p[0].v);
+  cross3(vec, p[0].v, p[1].v); b[2] = dot3(vec, p[3].v);
+  cross3(vec, p[2].v, p[1].v); b[3] = dot3(vec, p[0].v);
+  sum = b[0] + b[1] + b[2] + b[3];
+  if (ccd_is_zero(sum) || sum < 0) {
+    b[0] = 0;
+    cross3(vec, p[2].v, p[3].v); b[1] = dot3(vec, dir);
+    cross3(vec, p[3].v, p[1].v); b[2] = dot3(vec, dir);
+    cross3(vec, p[1].v, p[2].v); b[3] = dot3(vec, dir);
+    sum = b[1] + b[2] + b[3];
+  }
+  double inv = 1.0 / sum, p1[3] = {0, 0, 0}, p2[3] = {0, 0, 0};
+  for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) { p1[k] += p[i].v1[k] * b[i]; p2[k] += p[i].v2[k] * b[i]; }
+  for (int k = 0; k < 3; k++) pos[k] = (p1[k] * inv + p2[k] * inv) * 0.5;
+}
+/* returns 0 and (depth, dir, pos) if the inflated objects intersect, -1 otherwise */
+static int ccd_mpr_penetration(const CcdObj* o1, const CcdObj* o2, double tol, int max_iter, double* depth, double* pdir,
+                               double* pos) {
+  static const double origin[3] = {0, 0, 0};
+  CcdSup p[4], v4;
+  double dir[3], va[3], vb[3], dot;
+  /* ---- discoverPortal ---- */
+  for (int k = 0; k < 3; k++) {
+    p[0].v1[k] = o1->s->gxpos[o1->g][k]; p[0].v2[k] = o2->s->gxpos[o2->g][k]; p[0].v[k] = p[0].v1[k] - p[0].v2[k];
+  }
+  if (ccd_vec_eq(p[0].v, origin)) p[0].v[0] += CCD_EPS * 10.0;
+  for (int k = 0; k < 3; k++) dir[k] = -p[0].v[k];
+  ccd_normalize(dir);
+  ccd_support(o1, o2, dir, &p[1]);
+  dot = dot3(p[1].v, dir);
+  if (ccd_is_zero(dot) || dot < 0) return -1;
+  cross3(dir, p[0].v, p[1].v);
+  if (ccd_is_zero(dot3(dir, dir))) {
+    if (ccd_vec_eq(p[1].v, origin)) {           /* findPenetrTouch */
+      *depth = 0; pdir[0] = pdir[1] = pdir[2] = 0;
+      for (int k = 0; k < 3; k++) pos[k] = 0.5 * (p[1].v1[k] + p[1].v2[k]);
+    } else {                                    /* findPenetrSegment */
+      for (int k = 0; k < 3; k++) { pos[k] = 0.5 * (p[1].v1[k] + p[1].v2[k]); pdir[k] = p[1].v[k]; }
+      *depth = sqrt(dot3(pdir, pdir));
+      ccd_normalize(pdir);
+    }
+    return 0;
+  }
+  ccd_normalize(dir);
+  ccd_support(o1, o2, dir, &p[2]);
+  dot = dot3(p[2].v, dir);
+  if (ccd_is_zero(dot) || dot < 0) return -1;
+  for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+  cross3(dir, va, vb);
+  ccd_normalize(dir);
+  if (dot3(dir, p[0].v) > 0) {
+    CcdSup t = p[1]; p[1] = p[2]; p[2] = t;
+    for (int k = 0; k < 3; k++) dir[k] = -dir[k];
+  }
+  for (;;) {
+    ccd_support(o1, o2, dir, &p[3]);
+    dot = dot3(p[3].v, dir);
+    if (ccd_is_zero(dot) || dot < 0) return -1;
+    int cont = 0;
+    cross3(va, p[1].v, p[3].v);
+    dot = dot3(va, p[0].v);
+    if (dot < 0 && !ccd_is_zero(dot)) { p[2] = p[3]; cont = 1; }
+    if (!cont) {
+      cross3(va, p[3].v, p[2].v);
+      dot = dot3(va, p[0].v);
+      if (dot < 0 && !ccd_is_zero(dot)) { p[1] = p[3]; cont = 1; }
+    }
+    if (!cont) break;
+    for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+    cross3(dir, va, vb);
+    ccd_normalize(dir);
+  }
+  /* ---- refinePortal ---- */
+  for (;;) {
+    ccd_portal_dir(p, dir);
+    dot = dot3(dir, p[1].v);
+    if (ccd_is_zero(dot) || dot > 0) break;                       /* portal encapsules the origin */
+    ccd_support(o1, o2, dir, &v4);
+    dot = dot3(v4.v, dir);
+    if (!(ccd_is_zero(dot) || dot > 0) || ccd_reach_tolerance(p, &v4, dir, tol)) return -1;
+    ccd_expand_portal(p, &v4);
+  }
+  /* ---- findPenetr ---- */
+  for (int iterations = 0;; iterations++) {
+    ccd_portal_dir(p, dir);
+    ccd_support(o1, o2, dir, &v4);
+    if (ccd_reach_tolerance(p, &v4, dir, tol) || iterations > max_iter) {
+      *depth = sqrt(ccd_point_tri_dist2(origin, p[1].v, p[2].v, p[3].v, pdir));
+      if (ccd_is_zero(*depth)) pdir[0] = pdir[1] = pdir[2] = 0;
+      else ccd_normalize(pdir);
+      ccd_find_pos(p, pos);
+      return 0;
+    }
+    ccd_expand_portal(p, &v4);
+  }
+}
+static long g_convex_calls = 0, g_convex_hits = 0;
+long ref_debug_convex(int k) { return k == 0 ? g_convex_calls : (k == 1 ? g_convex_hits : g_convex_support); }
+static int convex_pair(RawCon* c, const RefSim* s, int g1, int g2, double margin) {
+  g_convex_calls++;
+  CcdObj o1 = {s, g1, 0.5 * margin}, o2 = {s, g2, 0.5 * margin};
+  static const double origin[3] = {0, 0, 0};
+  double depth, dir[3], pos[3];
+  if (ccd_mpr_penetration(&o1, &o2, 1e-6, 50, &depth, dir, pos) != 0) return 0;      /* opt.mpr_tolerance / mpr_iterations */
+  if (ccd_vec_eq(dir, origin)) return 0;
+  g_convex_hits++;
+  c->dist = margin - depth;
+  memset(c->frame, 0, sizeof(c->frame));
+  memcpy(c->frame, dir, sizeof(dir));
+  memcpy(c->pos, pos, sizeof(pos));
+  return 1;
+}
+
 static void make_frame(double* f) {
   /* mju_makeFrame: normal given in f[0:3]; tangent f[3:6] optional */
   normalize3(f);
@@ -676,7 +914,9 @@ static void collision(RefSim* s) {
     } else if (t1 == LS_GEOM_CAPSULE && t2 == LS_GEOM_CAPSULE) {
       n = capsule_capsule(raw, margin, pos1, mat1, size1, pos2, mat2, size2);
     } else {
-      n = 0; /* box/cylinder/mesh vs non-plane: mjc_Convex (libccd MPR) / mjc_BoxBox -- see DESIGN.md "not yet" */
+      /* every other pair the compiler lets through (mesh-mesh, box-mesh, ...): mjc_Convex, one contact. (mjc_BoxBox,
+         mjc_CapsuleBox, mjc_SphereBox have their own routines in MuJoCo: those pairs are dropped at compile time.) */
+      n = convex_pair(raw, s, g1, g2, margin);
     }
     for (int k = 0; k < n && s->ncon < MAXCON; k++) {
       Contact* c = &s->con[s->ncon++];

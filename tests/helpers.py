@@ -10,25 +10,32 @@ GOLDEN_TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "Hum
     ["HumanoidTorque4Ages.%s.%s" % (t, m) for t in ("run", "walk") for m in "1234"]
 
 
-# HumanoidTorque.walk: from row 20 on the reference rollout contains a convex mesh-mesh self-contact (fixed arm/hand
-# bones against the leg, mjc_Convex / libccd MPR in MuJoCo) that the engines do not implement yet (DESIGN.md "gaps");
-# rows 0..19 (190 RK4 steps = 760 dynamics evaluations) are pinned.
+# Convex mesh-mesh contacts (HumanoidTorque.walk rows >= 20, HumanoidTorque4Ages run.3 / walk.2-4, UnitreeG1.walk last rows:
+# bone against bone, mjc_Convex = libccd MPR) are built since round 2 (oracle: ccd_mpr_penetration; engine:
+# mpr_penetration): those goldens are reproduced over the WHOLE episode, same length, to <= 2.6e-6. That residual is the
+# MPR tolerance itself (opt.mpr_tolerance = 1e-6: the penetration depth depends at that level on which hull vertices the
+# portal visits; scipy's Qhull and MuJoCo's own qhull run do not enumerate identical vertex sets), hence atol 1e-5 below.
 # UnitreeH1: the feet are convex MESHES; MuJoCo's plane-mesh routine picks its (up to 3) contact vertices by walking the
 # qhull vertex graph of the mesh from the support vertex, an order that cannot be reproduced without MuJoCo's own qhull
 # run (the sole has ~30 exactly coplanar hull vertices). The engines use the deepest-vertices rule instead, so only the
 # rows before the first foot strike of the golden (10 rows = 90 steps of free flight incl. joint limits) are pinned.
-# UnitreeG1.walk: the feet are spheres (pinned exactly), but in the last two rows of the golden a convex-mesh body part
-# touches something (same unbuilt mesh narrow phase as HumanoidTorque.walk): rows 0..25 pinned (1e-13).
-# HumanoidTorque4Ages (one scaling per env): run.1 / run.2 / run.4 / walk.1 are reproduced completely; the others up to the
-# first convex-mesh contact of the episode (same gap as HumanoidTorque.walk).
-PINNED_ROWS = {"HumanoidTorque.walk": 20, "UnitreeH1.run": 10, "UnitreeG1.walk": 26, "HumanoidTorque4Ages.run.3": 39,
-               "HumanoidTorque4Ages.walk.2": 36, "HumanoidTorque4Ages.walk.3": 19, "HumanoidTorque4Ages.walk.4": 20}
+PINNED_ROWS = {"UnitreeH1.run": 10}
+
+# Rows of the golden that the FP32 engine is compared on (tests of the CUDA path and of its serial emulation build); the fp64
+# oracle is pinned on the whole episodes. MPR's answer is piecewise constant in its inputs (the contact normal is the normal of
+# the Minkowski-difference facet the centre ray leaves through): for a shallow, just-touching bone-bone contact an fp32-sized
+# difference of the geom poses can select the neighbouring facet (normal a few degrees off), after which an fp32 and an
+# fp64 rollout are two different - equally valid - trajectories. In the two longest bone-contact episodes that happens at
+# rows 38 / 27 (measured on the emulation build: |obs - golden| jumps from <1e-3 to >1e-2 there); all other goldens are
+# followed by the fp32 core over their whole length.
+FP32_ROWS = dict(PINNED_ROWS, **{"HumanoidTorque4Ages.walk.2": 36, "HumanoidTorque4Ages.walk.3": 24})
 
 
 # Talos.carry: the oracle follows the golden to 2.0e-7 over the whole episode (same episode length / done timing); a few
 # near-zero velocity entries miss np.allclose's default atol of 1e-8 (Talos.walk: 5e-8, inside). The residual comes from
 # Talos' mesh-derived inertias (float32 STL vertices -> equivalent inertia boxes), not from the dynamics.
-GOLDEN_ATOL = {"Talos.carry": 1e-6}
+GOLDEN_ATOL = {"Talos.carry": 1e-6, "HumanoidTorque.walk": 1e-5, "UnitreeG1.walk": 1e-5, "HumanoidTorque4Ages.run.3": 1e-5,
+               "HumanoidTorque4Ages.walk.2": 1e-5, "HumanoidTorque4Ages.walk.3": 1e-5, "HumanoidTorque4Ages.walk.4": 1e-5}
 
 
 def golden(task):

@@ -10,7 +10,7 @@ from helpers import ROOT
 
 def declared_symbols():
     txt = open(os.path.join(ROOT, "include", "locosim.h")).read()
-    return sorted(set(re.findall(r"\b(locosim_[a-z_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(locosim_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_declares_expected_entry_points():

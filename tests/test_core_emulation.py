@@ -13,9 +13,9 @@ import subprocess
 import numpy as np
 import pytest
 
-from helpers import ROOT, PINNED_ROWS, golden, make_env
+from helpers import ROOT, FP32_ROWS, golden, make_env
 
-TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "Atlas.walk", "Talos.walk", "UnitreeG1.run",
+TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "HumanoidTorque.walk", "Atlas.walk", "Talos.walk", "UnitreeG1.run", "UnitreeG1.walk", "HumanoidTorque4Ages.walk.3",
          "HumanoidTorque4Ages.run.1"]
 
 
@@ -48,7 +48,7 @@ def test_fp32_core_tracks_reference_golden(emu, bundled_only, task):
     from loco_mujoco_b200 import modelpack
     env = make_env(task)
     m, spec, g = env._model, env.task_spec(), golden(task)
-    n = PINNED_ROWS.get(task, len(g))
+    n = FP32_ROWS.get(task, len(g))
     ints, reals = modelpack.pack(m)
     sim = emu.emu_create(_p(ints), len(ints), _p(reals), len(reals))
     assert sim
