@@ -69,6 +69,20 @@ int locosim_step(locosim_t* h, const float* d_action, float* d_obs, float* d_rew
 int locosim_get_state(locosim_t* h, float* d_qpos, float* d_qvel, float* d_qacc_warmstart, void* stream);
 int locosim_set_state(locosim_t* h, const float* d_qpos, const float* d_qvel, const float* d_qacc_warmstart, void* stream);
 
+/* setup_random_rot in the drop-in single-env mode (unitreeA1.py:270-285: angle = np.random.uniform(0, 2 pi) from the legacy
+ * numpy stream): rotation angles for the NEXT locosim_reset* call only, d_angle fp32 [n_envs] (NULL: the engine's own
+ * counter-based draw, which is also what in-kernel auto-resets use). Requires a TaskSpec with TKI_ROT_* set. */
+int locosim_set_reset_rotation(locosim_t* h, const float* d_angle);
+
+/* Trajectory cursor of every env (traj * traj_len + sample; LS_REWARD_TRACKING, include/locosim_task.h). int32 [n_envs]. */
+int locosim_get_cursor(locosim_t* h, int32_t* d_out, void* stream);
+
+/* Replaces LocoEnv.create_dataset() (base.py:278-312 -> utils/trajectory.py:104-151) on the device: consecutive samples of
+ * every trajectory of the reset table in observation layout. d_states / d_next_states fp32 [locosim_dataset_rows, obs_dim],
+ * d_last fp32 [locosim_dataset_rows] (may be NULL); absorbing is all zero in the reference and is not materialised. */
+int locosim_dataset_rows(const locosim_t* h);
+int locosim_create_dataset(locosim_t* h, float* d_states, float* d_next_states, float* d_last, void* stream);
+
 /* Per-episode goal features (UnitreeA1: cos / sin of the goal direction and the goal speed, GoalDirectionVelocity set in
  * setup() unitreeA1.py:287-291); normally loaded from the reset table, settable for reset(obs=...) (base.py:217-218,633-654).
  * d_goal fp32 [n_envs, 4]. */

@@ -20,7 +20,7 @@
 #define LOCOSIM_TASK_H
 
 #define LOCOSIM_TASK_MAGIC 0x5441534B
-#define LOCOSIM_TASK_VERSION 3
+#define LOCOSIM_TASK_VERSION 4
 
 enum {
   TKI_MAGIC = 0, TKI_VERSION, TKI_OBS_DIM, TKI_N_DONE, TKI_REWARD_TYPE, TKI_N_SUBSTEPS, TKI_N_TRAJ, TKI_TRAJ_LEN,
@@ -28,8 +28,11 @@ enum {
   TKI_USE_ABSORBING,
   TKI_N_GRF,      /* number of foot-force groups (0: use_foot_forces off) */
   TKI_N_GRF_GEOM, /* length of the grf_group array (= ngeom of the compiled model, 0 if n_grf == 0) */
-  TKI_RESERVED0, TKI_RESERVED1,
-  TKI_HEADER_LEN = 20
+  TKI_ROT_Q,      /* setup_random_rot (unitreeA1.py:270-285, utils/math.py:5-31): qpos index of the yaw joint, -1 = off */
+  TKI_ROT_VX,     /*   dof index of the root x velocity */
+  TKI_ROT_VY,     /*   dof index of the root y velocity: at every reset yaw += a (wrapped to [-pi,pi)), (vx,vy) rotated by a ~ U[0,2pi) */
+  TKI_RESERVED1, TKI_RESERVED2, TKI_RESERVED3,
+  TKI_HEADER_LEN = 24
 };
 /* int arrays after the header: obs_src_type[obs_dim], obs_src_idx[obs_dim], done_obs_idx[n_done],
  *                                  act_idx[nu]  (data.ctrl[act_idx[k]] = action[k]*act_delta[k] + act_mean[k]; mushroom's
@@ -37,7 +40,9 @@ enum {
  *                                  grf_group[n_grf_geom]: per geom -1 = none, k < n_grf = member of foot group k,
  *                                  LS_GRF_FLOOR = floor (collision_groups of the env; base.py:667-679, unitreeA1.py:223-227,551-562) */
 
-enum { TKR_REWARD_P0 = 0, TKR_REWARD_P1, TKR_HEADER_LEN = 8 };
+enum { TKR_REWARD_P0 = 0, TKR_REWARD_P1,
+       TKR_TRACK_WP, TKR_TRACK_KP, TKR_TRACK_WV, TKR_TRACK_KV,   /* LS_REWARD_TRACKING weights / scales */
+       TKR_HEADER_LEN = 8 };
 /* real arrays after the header: act_mean[nu], act_delta[nu], done_lo[n_done], done_hi[n_done],
  *                               traj_table[n_traj][traj_len][nq + nv + n_goal]                      */
 
@@ -57,7 +62,15 @@ enum {
   LS_REWARD_NONE = 0,            /* NoReward :34 */
   LS_REWARD_TARGET_VELOCITY = 1, /* TargetVelocityReward :66   exp(-(prev_obs[i0]-p0)^2) */
   LS_REWARD_VELOCITY_VECTOR = 2, /* VelocityVectorReward :100  exp(-5*|v_xy - goal*[cos,sin]|), i0=x i1=y i2=cos idx i3=goal idx */
-  LS_REWARD_POS = 3              /* PosReward :44  prev_obs[i0] */
+  LS_REWARD_POS = 3,             /* PosReward :44  prev_obs[i0] */
+  /* Mocap-tracking reward (BASELINE config 3 "imitation reward vs mocap dataset"). NOT in the reference (none of its six
+   * rewards reads the trajectory): this package's own spec, DeepMimic-style. Every env carries a trajectory
+   * cursor (traj, sample), set by each (auto-)reset to the sampled reset row and advanced by one sample per control
+   * step (clamped at the last sample). With P / V = the observation entries gathered from qpos / qvel,
+   *   r = wp * exp(-kp * sum_{k in P} (obs[k] - ref[k])^2) + wv * exp(-kv * sum_{k in V} (obs[k] - ref[k])^2),
+   * evaluated on the observation AFTER the step against the table row at the advanced cursor (the reward of the step
+   * that reached it; the observation's root x / y are not part of it). */
+  LS_REWARD_TRACKING = 4
 };
 
 #endif

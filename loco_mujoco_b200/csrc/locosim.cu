@@ -24,6 +24,8 @@ struct EngineState {
   int* counters;                    // [N,8]
   int* dr_row;                      // [N] row of the parameter pool used by the env's current episode
   int* perm;                        // [N] env handled by warp slot i (regrouped every step by solver effort)
+  int* cursor;                      // [N] trajectory cursor traj * traj_len + sample (LS_REWARD_TRACKING)
+  const float* rot_angle;           // [N] rotation angles pinned for the next reset (setup_random_rot, drop-in mode) or NULL
   const float* pool;                // [K, P] parameter pool (domain randomisation); K = 1: the model's own values
   int pool_K;
 };
@@ -40,6 +42,12 @@ __device__ __forceinline__ void draw_reset(uint64_t seed, int64_t genv, int epis
   uint64_t r = mix64(seed ^ mix64((uint64_t)genv * 0x100000001B3ULL + (uint64_t)(uint32_t)episode));
   *traj = (int)((r & 0xffffffffULL) % (uint64_t)n_traj);
   *step = (int)((r >> 32) % (uint64_t)traj_len);
+}
+
+// setup_random_rot: rotation angle ~ U[0, 2 pi) of reset number `episode` of global env `genv`
+__device__ __forceinline__ float draw_rot_angle(uint64_t seed, int64_t genv, int episode) {
+  uint64_t r = mix64((seed + 0x2545F4914F6CDD1DULL) ^ mix64((uint64_t)genv * 0x100000001B3ULL + (uint64_t)(uint32_t)episode));
+  return (float)(r >> 40) * (6.283185307179586f / 16777216.0f);
 }
 
 __device__ __forceinline__ int draw_pool_row(uint64_t seed, int64_t genv, int episode, int K) {
@@ -68,11 +76,11 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
   const float* row = t.table + ((size_t)tr * t.traj_len + sp) * ncol;
   int prow = draw_pool_row(seed, env_off + env, ep, st.pool_K);     // the model of this episode (base.py:187-191)
   if (pool_row) prow = min(max(pool_row[env], 0), st.pool_K - 1);
+  float angle = 0.0f;
+  if (t.rot[0] >= 0) angle = st.rot_angle ? st.rot_angle[env] : draw_rot_angle(seed, env_off + env, ep);
   for (int i = lane; i < nv; i += 32) {
-    float q = row[i];
-    if (i == t.recenter0 || i == t.recenter1) q = 0;
-    st.qpos[(size_t)env * nv + i] = q;
-    st.qvel[(size_t)env * nv + i] = row[nv + i];
+    st.qpos[(size_t)env * nv + i] = reset_value(t, row, nv, LS_OBS_QPOS, i, angle);
+    st.qvel[(size_t)env * nv + i] = reset_value(t, row, nv, LS_OBS_QVEL, i, angle);
     st.ws[(size_t)env * nv + i] = 0;
   }
   for (int k = lane; k < t.n_goal; k += 32) st.goal[(size_t)env * 4 + k] = row[2 * nv + k];
@@ -80,8 +88,7 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
     for (int k = lane; k < t.obs_dim; k += 32) {
       int idx = t.obs_src_idx[k], ty = t.obs_src_type[k];
       float v;
-      if (ty == LS_OBS_QPOS) v = (idx == t.recenter0 || idx == t.recenter1) ? 0.0f : row[idx];
-      else if (ty == LS_OBS_QVEL) v = row[nv + idx];
+      if (ty == LS_OBS_QPOS || ty == LS_OBS_QVEL) v = reset_value(t, row, nv, ty, idx, angle);
       else if (ty == LS_OBS_GRF) v = 0.0f;           // the running mean of the foot forces is reset with the episode
       else if (ty == LS_OBS_PARAM) v = st.pool[(size_t)prow * m.pool_P + t.po_user + idx];
       else v = row[2 * nv + idx];
@@ -91,6 +98,7 @@ __global__ void reset_kernel(int ms, DevTask t, EngineState st, const uint8_t* m
   if (lane == 0) {
     st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1;
     st.dr_row[env] = prow;
+    st.cursor[env] = tr * t.traj_len + sp;
   }
 }
 
@@ -159,6 +167,25 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
   bad = __any_sync(0xffffffffu, bad);
   fallen = __any_sync(0xffffffffu, fallen) && t.use_absorbing;
   const bool is_done = fallen || bad;
+  if (t.reward_type == LS_REWARD_TRACKING) {
+    // mocap-tracking reward (include/locosim_task.h): the cursor advances one sample, the observation reached by this step
+    // is compared with the table row at the advanced cursor
+    int cur = st.cursor[env];
+    const int tj = cur / t.traj_len;
+    int sp = cur - tj * t.traj_len;
+    sp = sp + 1 < t.traj_len ? sp + 1 : t.traj_len - 1;
+    cur = tj * t.traj_len + sp;
+    const float* ref = t.table + (size_t)cur * (2 * nv + t.n_goal);
+    float ep = 0, ev = 0;
+    for (int k = lane; k < D; k += 32) {
+      const int ty = t.obs_src_type[k], idx = t.obs_src_idx[k];
+      if (ty == LS_OBS_QPOS) { const float d = e.qpos[idx] - ref[idx]; ep += d * d; }
+      else if (ty == LS_OBS_QVEL) { const float d = e.qvel[idx] - ref[nv + idx]; ev += d * d; }
+    }
+    ep = warp_sum(ep); ev = warp_sum(ev);
+    rew = bad ? 0.0f : t.track[0] * expf(-t.track[1] * ep) + t.track[2] * expf(-t.track[3] * ev);
+    if (lane == 0) st.cursor[env] = cur;
+  }
   for (int k = lane; k < D; k += 32) {
     float v = obs_value(t, e, k);
     if (bad) v = 0.0f;
@@ -190,11 +217,12 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
     int tr, sp;
     draw_reset(seed, env_off + env, ep, t.n_traj, t.traj_len, &tr, &sp);
     __syncwarp();
-    reset_env(ms, t, e, tr, sp);
+    reset_env(ms, t, e, tr, sp, t.rot[0] >= 0 ? draw_rot_angle(seed, env_off + env, ep) : 0.0f);
     if (lane == 0) {
       const int prow = draw_pool_row(seed, env_off + env, ep, st.pool_K);
       st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1;
       st.dr_row[env] = prow;
+      st.cursor[env] = tr * t.traj_len + sp;
       e.prm = st.pool + (size_t)prow * m.pool_P;      // the next episode's model (LS_OBS_PARAM entries of next_obs)
     }
     __syncwarp();
@@ -373,11 +401,13 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
        cudaMalloc((void**)&h->st.ws, N * nv * 4) == cudaSuccess && cudaMalloc((void**)&h->st.goal, N * 4 * 4) == cudaSuccess &&
        cudaMalloc((void**)&h->st.episode, N * 4) == cudaSuccess && cudaMalloc((void**)&h->st.counters, N * 32) == cudaSuccess &&
        cudaMalloc((void**)&h->st.dr_row, N * 4) == cudaSuccess && cudaMalloc((void**)&h->st.perm, N * 4) == cudaSuccess &&
+       cudaMalloc((void**)&h->st.cursor, N * 4) == cudaSuccess &&
        up((void**)&h->d_pool, h->hm.default_row.data(), h->hm.default_row.size() * 4);
   if (!ok) { std::string m = std::string("device allocation failed: ") + cudaGetErrorString(cudaGetLastError()); locosim_destroy(h); g_create_error = m; return 1; }
   cudaMemset(h->st.qpos, 0, N * nv * 4); cudaMemset(h->st.qvel, 0, N * nv * 4); cudaMemset(h->st.ws, 0, N * nv * 4);
   cudaMemset(h->st.goal, 0, N * 16); cudaMemset(h->st.episode, 0, N * 4); cudaMemset(h->st.counters, 0, N * 32);
-  cudaMemset(h->st.dr_row, 0, N * 4);
+  cudaMemset(h->st.dr_row, 0, N * 4); cudaMemset(h->st.cursor, 0, N * 4);
+  h->st.rot_angle = nullptr;
   { std::vector<int> id(N); for (size_t i = 0; i < N; i++) id[i] = (int)i; cudaMemcpy(h->st.perm, id.data(), N * 4, cudaMemcpyHostToDevice); }
   h->st.pool = h->d_pool; h->st.pool_K = 1;
   bind_model(h->dm, h->hm, h->d_mints, h->d_mreals);
@@ -405,7 +435,7 @@ void locosim_destroy(locosim_t* h) {
   if (h->slot >= 0) g_slot_used[h->slot] = false;
   cudaFree(h->d_mints); cudaFree(h->d_mreals); cudaFree(h->d_tints); cudaFree(h->d_treals);
   cudaFree(h->st.qpos); cudaFree(h->st.qvel); cudaFree(h->st.ws); cudaFree(h->st.goal); cudaFree(h->st.episode);
-  cudaFree(h->st.counters); cudaFree(h->st.dr_row); cudaFree(h->st.perm); cudaFree(h->d_pool);
+  cudaFree(h->st.counters); cudaFree(h->st.dr_row); cudaFree(h->st.perm); cudaFree(h->st.cursor); cudaFree(h->d_pool);
   delete h;
 }
 
@@ -426,6 +456,43 @@ int locosim_reset_rows(locosim_t* h, const uint8_t* d_mask, const int32_t* d_tra
   int threads = 128, blocks = (h->n_envs * 32 + threads - 1) / threads;
   reset_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(h->slot, h->dt, h->st, d_mask, d_traj, d_step, d_pool_row, d_obs,
                                                              h->n_envs, h->seed, h->env_off);
+  h->st.rot_angle = nullptr;        // pinned rotation angles apply to one reset call
+  CK(cudaGetLastError());
+  return 0;
+}
+int locosim_set_reset_rotation(locosim_t* h, const float* d_angle) { h->st.rot_angle = d_angle; return 0; }
+int locosim_get_cursor(locosim_t* h, int32_t* d_out, void* stream) {
+  CK(cudaMemcpyAsync(d_out, h->st.cursor, (size_t)h->n_envs * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+// create_dataset() on the device (base.py:278-312 -> Trajectory.create_dataset utils/trajectory.py:104-151): states /
+// next_states = the observation layout of consecutive samples of every trajectory of the reset table (already in HBM),
+// last = 1 on the final transition of each trajectory; absorbing is all zero in the reference and is not materialised.
+__global__ void dataset_kernel(int ms, DevTask t, float* __restrict__ states, float* __restrict__ next_states,
+                               float* __restrict__ last) {
+  const DevModel& m = c_models[ms];
+  const int nv = m.nv, ncol = 2 * nv + t.n_goal, D = t.obs_dim, per = t.traj_len - 1;
+  const long n_rows = (long)t.n_traj * per;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * D; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / D;
+    const int k = (int)(i - r * D), tj = (int)(r / per), sp = (int)(r - (long)tj * per);
+    const float* row = t.table + ((size_t)tj * t.traj_len + sp) * ncol;
+    const int ty = t.obs_src_type[k], idx = t.obs_src_idx[k];
+    float a, b;
+    if (ty == LS_OBS_QPOS) { a = row[idx]; b = row[ncol + idx]; }
+    else if (ty == LS_OBS_QVEL) { a = row[nv + idx]; b = row[ncol + nv + idx]; }
+    else if (ty == LS_OBS_GOAL) { a = row[2 * nv + idx]; b = row[ncol + 2 * nv + idx]; }
+    else { a = 0.0f; b = 0.0f; }                      // foot forces / per-model features are not trajectory data
+    states[i] = a; next_states[i] = b;
+    if (k == 0 && last) last[r] = sp == per - 1 ? 1.0f : 0.0f;
+  }
+}
+int locosim_dataset_rows(const locosim_t* h) { return h->ht.n_traj * (h->ht.traj_len - 1); }
+int locosim_create_dataset(locosim_t* h, float* d_states, float* d_next_states, float* d_last, void* stream) {
+  if (!d_states || !d_next_states) { h->err = "null buffer"; return 1; }
+  CK(cudaSetDevice(h->device));
+  dataset_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(h->slot, h->dt, d_states, d_next_states, d_last);
   CK(cudaGetLastError());
   return 0;
 }

@@ -113,7 +113,9 @@ struct DevTask {
   int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter0, recenter1, ri[4], use_absorbing;
   int n_grf;                      // foot-force groups (use_foot_forces), 0 = off
   int po_user;                    // offset of the user features inside a parameter-pool row (LS_OBS_PARAM)
+  int rot[3];                     // setup_random_rot: qpos index of the yaw, dof indices of root vx / vy (-1: off)
   float rp[2];
+  float track[4];                 // LS_REWARD_TRACKING: w_pose, k_pose, w_vel, k_vel
   const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx, *grf_group;
   const float *act_mean, *act_delta, *done_lo, *done_hi, *table;
 };
@@ -780,6 +782,9 @@ LS_FN int capsule_capsule(RawCon* c, float margin, const float* pos1, const floa
 #define MPR_EPS 1.1920929e-7f
 #define MPR_TOL 1e-6f
 #define MPR_MAXIT 50
+#if defined(LS_EMULATE)
+static long g_mpr_supports = 0, g_mpr_calls = 0, g_mpr_candidates = 0, g_forward_evals = 0;
+#endif
 struct MprSup { float v[3], v1[3], v2[3]; };
 struct MprGeom { int type, vadr, vnum; float pos[3], mat[9], size[3], margin; };
 LS_DEV bool mpr_is_zero(float x) { return fabsf(x) < MPR_EPS; }
@@ -799,11 +804,28 @@ LS_DEV void mpr_support_geom(const float* __restrict__ mesh_vert, const MprGeom&
     const float* v = mesh_vert + 3 * g.vadr;
     float mx = -3.0e38f;
     int best = 0x7fffffff;
-    PAR_FOR(i, g.vnum) {
+#ifdef LS_EMULATE
+    for (int i = 0; i < g.vnum; i++) {
       const float d = ld[0] * v[3 * i] + ld[1] * v[3 * i + 1] + ld[2] * v[3 * i + 2];
       if (d > mx) { mx = d; best = i; }
     }
+#else
+    // 4 vertices per lane and trip: 12 independent loads in flight (the scan is bound by L2 latency, not by arithmetic);
+    // indices past the end are clamped to the last vertex (a duplicate candidate never wins the tie-break)
+    const int last = g.vnum - 1;
+    NOUNROLL for (int i0 = LS_LANE; i0 <= last; i0 += 128) {
+      const int i1 = min(i0 + 32, last), i2 = min(i0 + 64, last), i3 = min(i0 + 96, last);
+      const float d0 = ld[0] * v[3 * i0] + ld[1] * v[3 * i0 + 1] + ld[2] * v[3 * i0 + 2];
+      const float d1 = ld[0] * v[3 * i1] + ld[1] * v[3 * i1 + 1] + ld[2] * v[3 * i1 + 2];
+      const float d2 = ld[0] * v[3 * i2] + ld[1] * v[3 * i2 + 1] + ld[2] * v[3 * i2 + 2];
+      const float d3 = ld[0] * v[3 * i3] + ld[1] * v[3 * i3 + 1] + ld[2] * v[3 * i3 + 2];
+      if (d0 > mx) { mx = d0; best = i0; }
+      if (d1 > mx) { mx = d1; best = i1; }
+      if (d2 > mx) { mx = d2; best = i2; }
+      if (d3 > mx) { mx = d3; best = i3; }
+    }
     WARP_ARGMAX(mx, best);
+#endif
     r[0] = v[3 * best]; r[1] = v[3 * best + 1]; r[2] = v[3 * best + 2];
   } else if (g.type == LS_GEOM_BOX) {
     for (int k = 0; k < 3; k++) r[k] = ld[k] >= 0 ? g.size[k] : -g.size[k];
@@ -816,8 +838,11 @@ LS_DEV void mpr_support(const float* __restrict__ mv, const MprGeom& a, const Mp
   mpr_support_geom(mv, a, dir, sp.v1);
   mpr_support_geom(mv, b, nd, sp.v2);
   for (int k = 0; k < 3; k++) sp.v[k] = sp.v1[k] - sp.v2[k];
-#if defined(LS_EMULATE) && defined(LS_TRACE)
+#if defined(LS_EMULATE)
+  g_mpr_supports++;
+#if defined(LS_TRACE)
   printf("    [f32] dir %.6f %.6f %.6f -> v %.7f %.7f %.7f\n", dir[0], dir[1], dir[2], sp.v[0], sp.v[1], sp.v[2]);
+#endif
 #endif
 }
 LS_DEV void mpr_portal_dir(const MprSup* p, float* dir) {
@@ -982,24 +1007,41 @@ LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p) {
   float bound = m.geom_rbound[g1] + m.geom_rbound[g2];
   if (dot3(d, d) > bound * bound) return false;
   if (m.geom_type[g2] != LS_GEOM_MESH) return true;
-  // Convex pair (box | mesh vs mesh). The first thing MPR does is a separating test along the centre line: with
-  // dir = (c2 - c1) / |c2 - c1| it stops if support1(dir) - support2(-dir) does not reach past the origin. The geoms'
-  // oriented boxes (geom_size = the mesh's AABB in its own frame) contain them, so their supports bound the mesh
-  // supports from above: if even the boxes are separated along dir, MPR would stop at that first test. (Conservative
-  // prefilter: it never rejects a pair MPR would accept; ~98 % of the humanoid's bone pairs end here.)
-  const float dn = sqrtf(dot3(d, d));
-  if (dn < 1e-9f) return true;
-  const float dir[3] = {d[0] / dn, d[1] / dn, d[2] / dn};
-  float m1[9], m2[9], l1[3], l2[3];
-  geom_mat(ms, e, g1, m1);
-  geom_mat(ms, e, g2, m2);
-  mulmatTvec3(l1, m1, dir);
-  mulmatTvec3(l2, m2, dir);
-  const float* s1 = m.geom_size + 3 * g1;
-  const float* s2 = m.geom_size + 3 * g2;
-  const float h = fabsf(l1[0]) * s1[0] + fabsf(l1[1]) * s1[1] + fabsf(l1[2]) * s1[2] + fabsf(l2[0]) * s2[0] +
-                  fabsf(l2[1]) * s2[1] + fabsf(l2[2]) * s2[2] + fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
-  return h * (1.0f + 1e-5f) + 1e-6f >= dn;
+#if defined(LS_EMULATE)
+  g_mpr_candidates++;
+#endif
+  // Convex pair (box | mesh vs mesh): MPR reports a contact only if the (margin-inflated) geoms intersect. Their oriented
+  // boxes (geom_size = the mesh's AABB in its own principal frame) contain them, so disjoint boxes mean no contact:
+  // 15-axis separating-axis test of the two boxes (conservative prefilter: it never rejects an intersecting pair;
+  // measured on the humanoid: of ~60 bone pairs per evaluation that pass the bounding spheres, ~N survive).
+  float RA[9], RB[9];
+  geom_mat(ms, e, g1, RA);
+  geom_mat(ms, e, g2, RB);
+  const float mg = 0.5f * fmaxf(m.geom_margin[g1], m.geom_margin[g2]) + 1e-6f;
+  const float a[3] = {m.geom_size[3 * g1] + mg, m.geom_size[3 * g1 + 1] + mg, m.geom_size[3 * g1 + 2] + mg};
+  const float b[3] = {m.geom_size[3 * g2] + mg, m.geom_size[3 * g2 + 1] + mg, m.geom_size[3 * g2 + 2] + mg};
+  float R[3][3], AR[3][3], t[3];
+  for (int i = 0; i < 3; i++) {
+    t[i] = RA[i] * d[0] + RA[3 + i] * d[1] + RA[6 + i] * d[2];                     // d in A's frame
+    for (int j = 0; j < 3; j++) {
+      R[i][j] = RA[i] * RB[j] + RA[3 + i] * RB[3 + j] + RA[6 + i] * RB[6 + j];     // A_i . B_j
+      AR[i][j] = fabsf(R[i][j]) + 1e-6f;
+    }
+  }
+  for (int i = 0; i < 3; i++)
+    if (fabsf(t[i]) > a[i] + b[0] * AR[i][0] + b[1] * AR[i][1] + b[2] * AR[i][2]) return false;
+  for (int j = 0; j < 3; j++)
+    if (fabsf(t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j]) > b[j] + a[0] * AR[0][j] + a[1] * AR[1][j] + a[2] * AR[2][j])
+      return false;
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const float ra = a[i1] * AR[i2][j] + a[i2] * AR[i1][j], rb = b[j1] * AR[i][j2] + b[j2] * AR[i][j1];
+      if (fabsf(t[i2] * R[i1][j] - t[i1] * R[i2][j]) > ra + rb) return false;
+    }
+  }
+  return true;
 }
 
 // warp-cooperative narrow phase of one convex pair (mjc_Convex): at most one contact
@@ -1018,6 +1060,9 @@ LS_FN int convex_narrow(const int ms, const EnvS<C>& e, int p, RawCon* raw) {
   geom_mat(ms, e, g1, a.mat);
   geom_mat(ms, e, g2, b.mat);
   float depth, dir[3], pos[3];
+#if defined(LS_EMULATE)
+  g_mpr_calls++;
+#endif
   if (!mpr_penetration(m.mesh_vert, a, b, &depth, dir, pos)) return 0;
   if (dir[0] == 0.0f && dir[1] == 0.0f && dir[2] == 0.0f) return 0;      // contact found but normal undefined
   raw->dist = margin - depth;
@@ -2057,6 +2102,9 @@ template <class C>
 LS_FN void forward(const int ms, EnvS<C>& e, const SolverOpts so) {
   const DevModel& m = c_models[ms];
   BLOCK_SYNC(so.sync_phases & 1);
+#if defined(LS_EMULATE)
+  g_forward_evals++;
+#endif
   kinematics(ms, e);
   BLOCK_SYNC(so.sync_phases & 2);
   com_pos(ms, e);
@@ -2190,15 +2238,38 @@ LS_DEV float obs_value(const DevTask& t, const EnvS<C>& e, int k) {
   return ty == LS_OBS_QPOS ? e.qpos[idx] : (ty == LS_OBS_QVEL ? e.qvel[idx] : e.goal[idx]);
 }
 
+// value `kind` (LS_OBS_QPOS / LS_OBS_QVEL) number idx of a reset row: recentred root x / y, and -- setup_random_rot,
+// unitreeA1.py:270-285 -> utils/math.py rotate_obs -- yaw + angle wrapped to [-pi, pi), root (vx, vy) rotated by angle
+LS_DEV float reset_value(const DevTask& t, const float* row, int nv, int kind, int idx, float angle) {
+  if (kind == LS_OBS_QPOS) {
+    if (idx == t.recenter0 || idx == t.recenter1) return 0.0f;
+    float q = row[idx];
+    if (idx == t.rot[0]) {
+      const float two_pi = 6.283185307179586f;
+      q = q + angle + 3.14159265358979f;
+      q = q - two_pi * floorf(q / two_pi) - 3.14159265358979f;
+    }
+    return q;
+  }
+  float v = row[nv + idx];
+  if (t.rot[0] >= 0 && (idx == t.rot[1] || idx == t.rot[2])) {
+    float sn, cs;
+    sincosf(angle, &sn, &cs);
+    const float vx = row[nv + t.rot[1]], vy = row[nv + t.rot[2]];
+    v = idx == t.rot[1] ? cs * vx - sn * vy : sn * vx + cs * vy;
+  }
+  return v;
+}
+
 template <class C>
-LS_FN void reset_env(const int ms, const DevTask& t, EnvS<C>& e, int traj_no, int step_no) {
+LS_FN void reset_env(const int ms, const DevTask& t, EnvS<C>& e, int traj_no, int step_no, float angle) {
   const DevModel& m = c_models[ms];
   const int nv = m.nv, ncol = 2 * nv + t.n_goal;
   const float* row = t.table + ((size_t)traj_no * t.traj_len + step_no) * ncol;
   PAR_FOR(i, nv) {
-    float q = row[i];
-    if (i == t.recenter0 || i == t.recenter1) q = 0;
-    e.qpos[i] = q; e.qvel[i] = row[nv + i]; e.qacc_ws[i] = 0; e.qacc[i] = 0;
+    e.qpos[i] = reset_value(t, row, nv, LS_OBS_QPOS, i, angle);
+    e.qvel[i] = reset_value(t, row, nv, LS_OBS_QVEL, i, angle);
+    e.qacc_ws[i] = 0; e.qacc[i] = 0;
   }
   PAR_FOR(k, t.n_goal) e.goal[k] = row[2 * nv + k];
   PAR_FOR(k, 3 * LS_MAX_GRF) e.grf[k] = 0;     // mean_grf is reset with the episode (reset observation: zeros)

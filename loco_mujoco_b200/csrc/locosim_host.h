@@ -138,7 +138,9 @@ struct HostTask {
   std::vector<float> reals;
   int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter0, recenter1, ri[4], use_absorbing;
   int n_grf = 0, n_grf_geom = 0;
+  int rot[3] = {-1, -1, -1};
   float rp[2];
+  float track[4] = {0, 0, 0, 0};
 };
 
 static inline std::string parse_task(HostTask& t, int nu, int nv, int ng, const int* ti, int nti, const double* tr, int ntr) {
@@ -152,6 +154,9 @@ static inline std::string parse_task(HostTask& t, int nu, int nv, int ng, const 
   t.n_grf = ti[TKI_N_GRF]; t.n_grf_geom = ti[TKI_N_GRF_GEOM];
   if (t.n_grf < 0 || t.n_grf > LS_MAX_GRF) return "n_grf out of range";
   t.rp[0] = (float)tr[TKR_REWARD_P0]; t.rp[1] = (float)tr[TKR_REWARD_P1];
+  for (int k = 0; k < 3; k++) t.rot[k] = ti[TKI_ROT_Q + k];
+  for (int k = 0; k < 4; k++) t.track[k] = (float)tr[TKR_TRACK_WP + k];
+  if (t.rot[0] >= nv || t.rot[1] >= nv || t.rot[2] >= nv) return "random-rotation index out of range";
   size_t ni = 2 * (size_t)t.obs_dim + t.n_done + (size_t)nu + (size_t)t.n_grf_geom;
   size_t nr = 2 * (size_t)nu + 2 * (size_t)t.n_done + (size_t)t.n_traj * t.traj_len * (2 * nv + t.n_goal);
   if ((size_t)nti != TKI_HEADER_LEN + ni || (size_t)ntr != TKR_HEADER_LEN + nr) return "TaskSpec size mismatch";
@@ -168,6 +173,8 @@ static inline void bind_task(DevTask& d, const HostTask& t, int nu, const int* i
   d.n_traj = t.n_traj; d.traj_len = t.traj_len; d.n_goal = t.n_goal; d.recenter0 = t.recenter0; d.recenter1 = t.recenter1;
   for (int k = 0; k < 4; k++) d.ri[k] = t.ri[k];
   d.use_absorbing = t.use_absorbing; d.rp[0] = t.rp[0]; d.rp[1] = t.rp[1]; d.n_grf = t.n_grf;
+  for (int k = 0; k < 3; k++) d.rot[k] = t.rot[k];
+  for (int k = 0; k < 4; k++) d.track[k] = t.track[k];
   const int* ip = ibase;
   d.obs_src_type = ip; ip += t.obs_dim; d.obs_src_idx = ip; ip += t.obs_dim; d.done_obs_idx = ip; ip += t.n_done; d.act_idx = ip; ip += nu;
   d.grf_group = ip;

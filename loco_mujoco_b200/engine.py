@@ -48,6 +48,14 @@ def load_library():
     lib.locosim_get_state.argtypes = [vp, vp, vp, vp, vp]
     lib.locosim_set_state.restype = ip
     lib.locosim_set_state.argtypes = [vp, vp, vp, vp, vp]
+    lib.locosim_set_reset_rotation.restype = ip
+    lib.locosim_set_reset_rotation.argtypes = [vp, vp]
+    lib.locosim_get_cursor.restype = ip
+    lib.locosim_get_cursor.argtypes = [vp, vp, vp]
+    lib.locosim_dataset_rows.restype = ip
+    lib.locosim_dataset_rows.argtypes = [vp]
+    lib.locosim_create_dataset.restype = ip
+    lib.locosim_create_dataset.argtypes = [vp, vp, vp, vp, vp]
     lib.locosim_set_goal.restype = ip
     lib.locosim_set_goal.argtypes = [vp, vp, vp]
     lib.locosim_get_counters.restype = ip
@@ -72,7 +80,8 @@ EXPORTED_SYMBOLS = ["locosim_create", "locosim_destroy", "locosim_last_error", "
                     "locosim_action_dim", "locosim_nq", "locosim_set_solver", "locosim_reset", "locosim_step",
                     "locosim_get_state", "locosim_set_state", "locosim_get_counters", "locosim_launch_info",
                     "locosim_param_pool_row_len", "locosim_set_param_pool", "locosim_get_param_rows",
-                    "locosim_kernels_per_step", "locosim_reset_rows", "locosim_set_goal", "locosim_measure_fp32_peak"]
+                    "locosim_kernels_per_step", "locosim_reset_rows", "locosim_set_goal", "locosim_measure_fp32_peak",
+                    "locosim_set_reset_rotation", "locosim_get_cursor", "locosim_dataset_rows", "locosim_create_dataset"]
 
 
 def measure_fp32_peak(device=0):
@@ -150,8 +159,11 @@ class CudaEngine:
     def set_solver(self, tolerance=1e-5, ls_tolerance=0.1, max_iter=20, ls_iter=16):
         self._check(self.lib.locosim_set_solver(self.h, tolerance, ls_tolerance, max_iter, ls_iter))
 
-    def reset(self, mask=None, traj_no=None, step_no=None, out=None, pool_row=None):
+    def reset(self, mask=None, traj_no=None, step_no=None, out=None, pool_row=None, rot_angle=None):
+        """rot_angle: float32 cuda [n_envs], rotation angles of this reset (setup_random_rot with host-drawn angles)."""
         out = self.next_obs if out is None else out
+        if rot_angle is not None:
+            self._check(self.lib.locosim_set_reset_rotation(self.h, _ptr(rot_angle)))
         self._check(self.lib.locosim_reset_rows(self.h, _ptr(mask), _ptr(traj_no), _ptr(step_no), _ptr(pool_row), _ptr(out),
                                                 self._stream()))
         self.launches += 1
@@ -196,6 +208,23 @@ class CudaEngine:
             if x is not None and (x.dtype != self.torch.float32 or not x.is_contiguous()):
                 raise ValueError("state tensors must be contiguous float32")
         self._check(self.lib.locosim_set_state(self.h, _ptr(qpos), _ptr(qvel), _ptr(qacc_warmstart), self._stream()))
+
+    def cursor(self):
+        t = self.torch
+        c = t.empty((self.n_envs,), dtype=t.int32, device=self.device)
+        self._check(self.lib.locosim_get_cursor(self.h, _ptr(c), self._stream()))
+        return c
+
+    def create_dataset(self):
+        """(states, next_states, last) of the reset table in observation layout, built on the device."""
+        t = self.torch
+        n = self.lib.locosim_dataset_rows(self.h)
+        states = t.empty((n, self.obs_dim), dtype=t.float32, device=self.device)
+        nxt = t.empty_like(states)
+        last = t.empty((n,), dtype=t.float32, device=self.device)
+        self._check(self.lib.locosim_create_dataset(self.h, _ptr(states), _ptr(nxt), _ptr(last), self._stream()))
+        self.launches += 1
+        return states, nxt, last
 
     def set_goal(self, goal):
         """goal: float32 cuda [n_envs, 4] per-episode goal features (A1: cos, sin, speed)."""

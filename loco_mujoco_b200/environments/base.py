@@ -24,7 +24,7 @@ import numpy as np
 
 from .. import mjcf, modelpack
 from ..task import (TaskSpec, OBS_QPOS, OBS_QVEL, OBS_GOAL, OBS_GRF, OBS_PARAM, GRF_FLOOR, REWARD_NONE, REWARD_TARGET_VELOCITY,
-                    REWARD_POS)
+                    REWARD_POS, REWARD_TRACKING)
 from ..trajectory import Trajectory
 from ..utils.reward import NoReward, CustomReward, TargetVelocityReward, PosReward
 
@@ -272,6 +272,8 @@ class LocoEnv:
             return REWARD_POS, [self.get_obs_idx("q_pelvis_tx")[0]], []
         if rt == "custom":
             return REWARD_NONE, [], []      # evaluated on the host from the returned tensors
+        if rt == "tracking":
+            return REWARD_TRACKING, [], []  # weights travel in TaskSpec.tracking
         raise NotImplementedError(rt)
 
     def _reset_table(self):
@@ -313,7 +315,22 @@ class LocoEnv:
         idxs += list(range(n_user))
         return TaskSpec(types, idxs, done_terms, rtype, rints, rparams, self.norm_act_mean, self.norm_act_delta,
                         self._n_substeps, self._reset_table(), self._n_goal(), recenter, self._use_absorbing_states,
-                        act_idx=self._action_indices, n_grf=n_grf, grf_group=grf_group)
+                        act_idx=self._action_indices, n_grf=n_grf, grf_group=grf_group, random_rot=self._random_rot_spec(),
+                        tracking=self._tracking_params())
+
+    TRACKING_DEFAULTS = dict(w_pose=0.7, k_pose=2.0, w_vel=0.3, k_vel=0.1)
+
+    def _tracking_params(self):
+        """(w_pose, k_pose, w_vel, k_vel) of reward_type="tracking" (this package's mocap-tracking reward, see
+        include/locosim_task.h LS_REWARD_TRACKING; the reference has no reward that reads the trajectory)."""
+        if self._reward_type != "tracking":
+            return None
+        prm = dict(self.TRACKING_DEFAULTS, **(self._reward_params or {}))
+        return [prm["w_pose"], prm["k_pose"], prm["w_vel"], prm["k_vel"]]
+
+    def _random_rot_spec(self):
+        """None, or (qpos index of the yaw joint, dof indices of the root x / y velocity): setup_random_rot."""
+        return None
 
     def domain_randomization_pool(self):
         """[K, P] parameter pool: K consecutive randomised recompilations of the model (see domain_randomization.py)."""
@@ -440,8 +457,9 @@ class LocoEnv:
             t = torch.tensor([traj_no], dtype=torch.int32, device=eng.device)
             s = torch.tensor([step_no], dtype=torch.int32, device=eng.device)
             r = torch.tensor([model_no], dtype=torch.int32, device=eng.device) if len(self._models) > 1 else None
-            out = eng.reset(traj_no=t, step_no=s, pool_row=r)
-            out = self._post_reset_single(eng, sample, out)
+            ang = self._reset_rotation_angle()
+            ang = None if ang is None else torch.tensor([ang], dtype=torch.float32, device=eng.device)
+            out = eng.reset(traj_no=t, step_no=s, pool_row=r, rot_angle=ang)
             self._obs = out[0].double().cpu().numpy()
             return self._obs.copy()
         if obs is not None:
@@ -451,9 +469,9 @@ class LocoEnv:
         self._obs = out.clone() if self._copy_outputs else out
         return self._obs
 
-    def _post_reset_single(self, eng, sample, out):
-        """Hook of the drop-in single-env reset, after the engine has loaded the trajectory sample (A1: random rotation)."""
-        return out
+    def _reset_rotation_angle(self):
+        """Drop-in single-env reset: host-drawn rotation angle of setup_random_rot envs (None: env has no such option)."""
+        return None
 
     def step(self, action):
         eng = self._get_engine()
@@ -612,13 +630,21 @@ class LocoEnv:
             idx = self.get_obs_idx("q_pelvis_tx")
             assert len(idx) == 1
             return PosReward(pos_idx=idx[0])
-        if reward_type is None:
+        if reward_type is None or reward_type == "tracking":      # tracking: evaluated in the kernel only (no host functor)
             return NoReward()
         raise NotImplementedError("The specified reward has not been implemented: %s" % reward_type)
 
     # ---------------------------------------------------------------------------------------------------
     # datasets / replay (reference: base.py:278-386)
     # ---------------------------------------------------------------------------------------------------
+    def create_dataset_device(self):
+        """`create_dataset()` built ON the device from the reset table that already lives in HBM: dict of torch.cuda float32
+        tensors (states / next_states [n, obs_dim] in observation layout, absorbing / last [n]); same content as the host
+        `create_dataset()` with the env's default ignore keys (reference: base.py:278-312, utils/trajectory.py:104-151)."""
+        import torch
+        states, nxt, last = self._get_engine().create_dataset()
+        return dict(states=states, next_states=nxt, absorbing=torch.zeros_like(last), last=last)
+
     def create_dataset(self, ignore_keys=None):
         if self._dataset is None:
             if self.trajectories is None:

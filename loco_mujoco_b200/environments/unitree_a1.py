@@ -29,8 +29,6 @@ class UnitreeA1(LocoEnv):
                  **kwargs):
         if action_mode != "torque":
             raise NotImplementedError("only action_mode='torque' is built (position control models are out of scope)")
-        if setup_random_rot:
-            raise NotImplementedError("setup_random_rot")
         self._action_mode = action_mode
         action_spec = self._get_action_specification()
         observation_spec = self._get_observation_specification()
@@ -74,6 +72,20 @@ class UnitreeA1(LocoEnv):
 
     def _n_goal(self):
         return 3
+
+    def _random_rot_spec(self):
+        # setup_random_rot (unitreeA1.py:270-285): yaw and root (vx, vy) of every reset sample are rotated by a ~ U[0, 2 pi);
+        # the goal direction is NOT rotated in the reference (it is read from the un-rotated dir_arrow), kept that way
+        if not self.setup_random_rot:
+            return None
+        return (self._model.joint_id("trunk_rotation"), self._model.joint_id("trunk_tx"), self._model.joint_id("trunk_ty"))
+
+    def _reset_rotation_angle(self):
+        # drop-in single-env mode: the reference draws the angle from the legacy numpy stream right after the trajectory
+        # sample (unitreeA1.py:269-272, 282-285; only for random_start / the first-sample start, not for init_step_no)
+        if self.setup_random_rot and (self._random_start or self._init_step_no is None):
+            return np.random.uniform(0, 2 * np.pi)
+        return 0.0 if self.setup_random_rot else None
 
     def _goal_features(self, sample):
         rot_mat = self.trajectories.get_from_sample(sample, "dir_arrow")

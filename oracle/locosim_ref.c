@@ -1614,8 +1614,8 @@ void ref_step(RefSim* s, const double* ctrl, int nsub) {
 /* ---------------------------------------------------------------------------------------------------- */
 typedef struct {
   int obs_dim, n_done, reward_type, n_substeps, n_traj, traj_len, n_goal, recenter[2], ri[4], use_absorbing;
-  int n_grf, n_grf_geom;
-  double rp[2];
+  int n_grf, n_grf_geom, rot[3];
+  double rp[2], track[4];
   int *ibuf; double* rbuf;
   const int *obs_src_type, *obs_src_idx, *done_obs_idx, *act_idx, *grf_group;
   const double *act_mean, *act_delta, *done_lo, *done_hi, *table;
@@ -1633,6 +1633,8 @@ static int task_load(Task* t, int nu, int nv, const int* ti, int nti, const doub
   t->n_grf = ti[TKI_N_GRF]; t->n_grf_geom = ti[TKI_N_GRF_GEOM];
   if (t->n_grf < 0 || t->n_grf > LS_MAX_GRF) return -3;
   t->rp[0] = tr[TKR_REWARD_P0]; t->rp[1] = tr[TKR_REWARD_P1];
+  for (int k = 0; k < 3; k++) t->rot[k] = ti[TKI_ROT_Q + k];
+  for (int k = 0; k < 4; k++) t->track[k] = tr[TKR_TRACK_WP + k];
   const int* ip = t->ibuf + TKI_HEADER_LEN;
   t->obs_src_type = ip; ip += t->obs_dim; t->obs_src_idx = ip; ip += t->obs_dim; t->done_obs_idx = ip; ip += t->n_done;
   t->act_idx = ip; ip += nu;
@@ -1644,7 +1646,8 @@ static int task_load(Task* t, int nu, int nv, const int* ti, int nti, const doub
   return 0;
 }
 
-struct RefEnv { RefSim* sim; Task task; double goal[8]; double obs[128]; double grf[3 * LS_MAX_GRF]; double user[LS_POOL_USER]; };
+struct RefEnv { RefSim* sim; Task task; double goal[8]; double obs[128]; double grf[3 * LS_MAX_GRF]; double user[LS_POOL_USER];
+                int cursor; double rot_angle; };
 
 RefEnv* refenv_create(const int* ints, int n_ints, const double* reals, int n_reals, const int* ti, int nti,
                       const double* tr, int ntr) {
@@ -1658,6 +1661,8 @@ RefEnv* refenv_create(const int* ints, int n_ints, const double* reals, int n_re
 void refenv_destroy(RefEnv* e) { if (e) { ref_destroy(e->sim); free(e->task.ibuf); free(e->task.rbuf); free(e); } }
 int refenv_obs_dim(const RefEnv* e) { return e->task.obs_dim; }
 void refenv_set_user(RefEnv* e, const double* user) { memcpy(e->user, user, sizeof(e->user)); }
+void refenv_set_rotation(RefEnv* e, double angle) { e->rot_angle = angle; }
+int refenv_cursor(const RefEnv* e) { return e->cursor; }
 RefSim* refenv_sim(RefEnv* e) { return e->sim; }
 
 static void build_obs(const RefEnv* e, double* obs) {
@@ -1697,11 +1702,21 @@ void refenv_reset_to(RefEnv* e, int traj_no, int step_no, double* obs) {
   const Task* t = &e->task;
   int nv = e->sim->m.nv, ncol = 2 * nv + t->n_goal;
   const double* row = t->table + ((long)traj_no * t->traj_len + step_no) * ncol;
-  double qpos[MAXNV];
+  double qpos[MAXNV], qvel[MAXNV];
   memcpy(qpos, row, sizeof(double) * nv);
+  memcpy(qvel, row + nv, sizeof(double) * nv);
   if (t->recenter[0] >= 0) qpos[t->recenter[0]] = 0;
   if (t->recenter[1] >= 0) qpos[t->recenter[1]] = 0;
-  ref_reset(e->sim, qpos, row + nv);
+  if (t->rot[0] >= 0) {
+    /* setup_random_rot (unitreeA1.py:270-285 -> utils/math.py:5-31 rotate_obs): yaw + angle wrapped to [-pi, pi), root
+       (vx, vy) rotated; the angle comes from the caller (refenv_set_rotation), 0 otherwise */
+    double a = e->rot_angle, vx = qvel[t->rot[1]], vy = qvel[t->rot[2]];
+    qpos[t->rot[0]] = fmod(fmod(qpos[t->rot[0]] + a + M_PI, 2 * M_PI) + 2 * M_PI, 2 * M_PI) - M_PI;
+    qvel[t->rot[1]] = cos(a) * vx - sin(a) * vy;
+    qvel[t->rot[2]] = sin(a) * vx + cos(a) * vy;
+  }
+  e->cursor = traj_no * t->traj_len + step_no;
+  ref_reset(e->sim, qpos, qvel);
   for (int k = 0; k < t->n_goal; k++) e->goal[k] = row[2 * nv + k];
   memset(e->grf, 0, sizeof(e->grf));   /* RunningAveragedWindow reset with the episode */
   build_obs(e, e->obs);
@@ -1734,7 +1749,21 @@ void refenv_step(RefEnv* e, const double* action, double* obs, double* reward, i
   }
   build_obs(e, cur);
   int ab = t->use_absorbing ? has_fallen(t, cur) : 0;
-  if (reward) *reward = reward_fn(t, e->obs);
+  if (t->reward_type == LS_REWARD_TRACKING) {
+    /* this package's mocap-tracking reward (include/locosim_task.h): cursor + 1 (clamped), post-step observation
+       against that table row */
+    int nv = e->sim->m.nv, tj = e->cursor / t->traj_len, sp = e->cursor % t->traj_len;
+    sp = sp + 1 < t->traj_len ? sp + 1 : t->traj_len - 1;
+    e->cursor = tj * t->traj_len + sp;
+    const double* ref = t->table + (long)e->cursor * (2 * nv + t->n_goal);
+    double ep = 0, ev = 0;
+    for (int k = 0; k < t->obs_dim; k++) {
+      int idx = t->obs_src_idx[k];
+      if (t->obs_src_type[k] == LS_OBS_QPOS) { double d = e->sim->qpos[idx] - ref[idx]; ep += d * d; }
+      else if (t->obs_src_type[k] == LS_OBS_QVEL) { double d = e->sim->qvel[idx] - ref[nv + idx]; ev += d * d; }
+    }
+    if (reward) *reward = t->track[0] * exp(-t->track[1] * ep) + t->track[2] * exp(-t->track[3] * ev);
+  } else if (reward) *reward = reward_fn(t, e->obs);
   if (absorbing) *absorbing = ab;
   memcpy(e->obs, cur, sizeof(double) * t->obs_dim);
   if (obs) memcpy(obs, cur, sizeof(double) * t->obs_dim);

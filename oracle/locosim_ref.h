@@ -71,6 +71,10 @@ void refenv_destroy(RefEnv* e);
 int refenv_obs_dim(const RefEnv* e);
 /* user features observed through LS_OBS_PARAM (multi-model envs: the carried weight's mass) */
 void refenv_set_user(RefEnv* e, const double* user);
+/* setup_random_rot: rotation angle applied by the following refenv_reset_to calls (0 by default) */
+void refenv_set_rotation(RefEnv* e, double angle);
+/* trajectory cursor (traj * traj_len + sample) of the tracking reward */
+int refenv_cursor(const RefEnv* e);
 void refenv_reset_to(RefEnv* e, int traj_no, int step_no, double* obs);
 void refenv_step(RefEnv* e, const double* action, double* obs, double* reward, int* absorbing);
 RefSim* refenv_sim(RefEnv* e);

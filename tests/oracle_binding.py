@@ -20,6 +20,8 @@ class Oracle:
         lib.refenv_sim.argtypes = [vp]
         lib.refenv_set_user.restype = None
         lib.refenv_set_user.argtypes = [vp, vp]
+        lib.refenv_set_rotation.restype = None
+        lib.refenv_set_rotation.argtypes = [vp, ctypes.c_double]
         lib.refenv_obs_dim.restype = ip
         lib.refenv_obs_dim.argtypes = [vp]
         for f, args in [("ref_destroy", [vp]), ("refenv_destroy", [vp]), ("ref_reset", [vp, vp, vp]),
@@ -63,6 +65,9 @@ class OracleEnv:
         u = np.zeros(4)
         u[:len(user)] = user
         self.lib.refenv_set_user(self.h, _p(u))
+
+    def set_rotation(self, angle):
+        self.lib.refenv_set_rotation(self.h, float(angle))
 
     def reset_to(self, traj_no, step_no):
         obs = np.zeros(self.obs_dim)

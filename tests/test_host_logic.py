@@ -100,16 +100,17 @@ def test_bundled_assets_match_live_compile():
         assert np.array_equal(a[k], b[k]), k
 
 
-def test_taskspec_v3_layout_and_feature_sources(bundled_only):
-    """Wire format of the task description (include/locosim_task.h, version 3): header fields and array lengths."""
+def test_taskspec_layout_and_feature_sources(bundled_only):
+    """Wire format of the task description (include/locosim_task.h, version 4): header fields and array lengths."""
     from loco_mujoco_b200 import task as T
     env = make_env("UnitreeA1.simple", use_foot_forces=True)
     spec = env.task_spec()
     ints, reals = spec.pack()
-    assert ints[0] == T.MAGIC and ints[1] == T.VERSION == 3 and ints[2] == spec.obs_dim == 49
+    assert ints[0] == T.MAGIC and ints[1] == T.VERSION == 4 and ints[2] == spec.obs_dim == 49
     assert ints[16] == 4 and ints[17] == env._model.ngeom                      # TKI_N_GRF, TKI_N_GRF_GEOM
     nu = len(spec.act_idx)
-    assert len(ints) == 20 + 2 * spec.obs_dim + len(spec.done_terms) + nu + env._model.ngeom
+    assert list(ints[18:21]) == [-1, -1, -1]                                      # TKI_ROT_*: setup_random_rot off
+    assert len(ints) == 24 + 2 * spec.obs_dim + len(spec.done_terms) + nu + env._model.ngeom
     n_traj, T_len, ncol = spec.table.shape
     assert len(reals) == 8 + 2 * nu + 2 * len(spec.done_terms) + n_traj * T_len * ncol
     assert list(spec.obs_src_type[-12:]) == [T.OBS_GRF] * 12 and list(spec.obs_src_idx[-12:]) == list(range(12))
@@ -170,3 +171,33 @@ def test_unitree_h1_carry_builds(bundled_only):
     env = make_env("UnitreeH1.carry")
     assert len(env._models) == 4 and env.info.observation_space.shape == (33,)
     assert [u[0] for u in env._model_user_features] == [0.1, 1.0, 5.0, 10.0]
+
+
+def test_tracking_reward_spec_on_the_oracle(oracle, bundled_only):
+    """reward_type="tracking" (include/locosim_task.h LS_REWARD_TRACKING): the oracle's reward equals the formula evaluated
+    in numpy on its own post-step observation and the table row at the advanced cursor; TaskSpec v4 carries the weights."""
+    from helpers import make_env, blobs
+    env = make_env("HumanoidTorque.run", reward_type="tracking", reward_params=dict(k_pose=1.5))
+    spec = env.task_spec()
+    assert spec.reward_type == 4 and spec.tracking == [0.7, 1.5, 0.3, 0.1] and spec.random_rot == [-1, -1, -1]
+    ints, reals = spec.pack()
+    assert ints[1] == 4 and list(reals[2:6]) == spec.tracking
+    oe = oracle.env(*blobs(env))
+    oe.reset_to(0, 10)
+    nq = env._model.nq
+    rng = np.random.RandomState(0)
+    for k in range(5):
+        obs, r, done = oe.step(rng.uniform(-1, 1, env._model.nu))
+        row = spec.table[0, min(10 + k + 1, spec.table.shape[1] - 1)]
+        ep = sum((obs[j] - row[i]) ** 2 for j, (t, i) in enumerate(zip(spec.obs_src_type, spec.obs_src_idx)) if t == 0)
+        ev = sum((obs[j] - row[nq + i]) ** 2 for j, (t, i) in enumerate(zip(spec.obs_src_type, spec.obs_src_idx)) if t == 1)
+        assert abs(r - (0.7 * np.exp(-1.5 * ep) + 0.3 * np.exp(-0.1 * ev))) < 1e-12
+    oe.close()
+
+
+def test_random_rotation_spec(bundled_only):
+    from helpers import make_env
+    env = make_env("UnitreeA1.simple", setup_random_rot=True)
+    m = env._model
+    assert env.task_spec().random_rot == [m.joint_id("trunk_rotation"), m.joint_id("trunk_tx"), m.joint_id("trunk_ty")]
+    assert make_env("UnitreeA1.simple").task_spec().random_rot == [-1, -1, -1]
