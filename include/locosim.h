@@ -111,6 +111,10 @@ int locosim_kernels_per_step(const locosim_t* h);
  * FMA-chain kernel on all SMs (best of 5). Not part of the simulation path. */
 int locosim_measure_fp32_peak(int device, double* tflops_out);
 
+/* Diagnostics of the convex (MPR) narrow phase, process-wide, only counted when the library was created with the environment
+ * variable LOCOSIM_DEBUG having bit 8 set: out8[0] = MPR runs, [1] = support calls, [3] = runs that hit the iteration cap. */
+int locosim_debug_counters(unsigned long long* out8);
+
 /* Launch geometry chosen for this handle: warps(envs) per block, dynamic shared memory bytes per block, blocks. */
 int locosim_launch_info(const locosim_t* h, int* warps_per_block, int* smem_bytes, int* n_blocks);
 

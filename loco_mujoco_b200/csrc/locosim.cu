@@ -110,9 +110,31 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
                                                     const float* __restrict__ action, float* __restrict__ obs,
                                                     float* __restrict__ reward, uint8_t* __restrict__ done,
                                                     float* __restrict__ next_obs, int n_envs, int auto_reset,
-                                                    uint64_t seed, int64_t env_off, int sync_substeps, int key_mode) {
+                                                    uint64_t seed, int64_t env_off, int sync_substeps, int key_mode,
+                                                    const unsigned char* __restrict__ stage_src, int stage_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (stage_bytes > 0) {
+    // Optional (LOCOSIM_STAGE=1): the hot geom tables of the shared model are staged once per block into the shared memory
+    // behind the per-env working sets by ONE TMA bulk copy (cp.async.bulk global -> shared::cta, completion on an
+    // mbarrier); c_models[ms].geom_* then point into the shared window (locosim_create probes its generic address).
+    unsigned char* dst = smem_raw + (size_t)(blockDim.x >> 5) * sizeof(EnvS<C>);
+    const unsigned dst_a = (unsigned)__cvta_generic_to_shared(dst);
+    const unsigned bar_a = dst_a + (unsigned)stage_bytes;
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((unsigned)stage_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+                   "l"(stage_src), "r"((unsigned)stage_bytes), "r"(bar_a)
+                   : "memory");
+    }
+    __syncthreads();                                    // (the barrier object is initialised before anybody polls it)
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar_a) : "memory");
+  }
   // warps past the last env shadow it (same barriers, no stores): the block-wide barriers inside the solver have
   // data-dependent counts, so every warp of a block has to run the physics
   const int slot_raw = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -202,7 +224,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
       int key = e.iter_sum;
       if (key_mode == 1) key = (cnt[5] + e.iter_sum + 1) >> 1;
       else if (key_mode == 2) key = e.solver_iter * 8;
-      else if (key_mode == 3) key = e.iter_sum + (e.nefc >> 1);
+      else if (key_mode == 3) key = e.iter_sum + (e.nefc >> 1) + 4 * min(e.mpr_calls, 64);   // (an MPR run costs about as much as 4 Newton iterations)
       else if (key_mode == 4) key = (3 * cnt[5] + e.iter_sum + 2) >> 2;
       else if (key_mode == 5) key = e.iter_sum + 4 * e.solver_iter;
       else if (key_mode == 6) key = e.iter_sum + e.nefc;
@@ -236,6 +258,13 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
     st.qvel[(size_t)env * nv + i] = e.qvel[i];
     st.ws[(size_t)env * nv + i] = e.qacc_ws[i];
   }
+}
+
+// generic address of the first byte of dynamic shared memory (the shared window is mapped at the same generic address in
+// every block of the context; used once at create time to point the staged model tables into it)
+__global__ void smem_probe_kernel(unsigned long long* out) {
+  extern __shared__ __align__(16) unsigned char smem_probe[];
+  if (threadIdx.x == 0) *out = (unsigned long long)(uintptr_t)smem_probe;
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -283,6 +312,7 @@ struct locosim_handle {
   EngineState st;
   int* d_mints = nullptr; float* d_mreals = nullptr; int* d_tints = nullptr; float* d_treals = nullptr;
   float* d_pool = nullptr;
+  unsigned char* d_stage = nullptr; int stage_bytes = 0;
   std::string err;
 };
 static std::string g_create_error;
@@ -297,8 +327,19 @@ static bool g_slot_used[LS_MAX_SLOTS] = {false};
     }                                                                                 \
   } while (0)
 
+static bool has_convex_pairs(const HostModel& hm) {
+  const int* ip = hm.ints.data();
+  // (pair_geom / geom_type live in the int blob in LOCOSIM_MP_INT_FIELDS order; resolve through a bound view)
+  DevModel v;
+  bind_model(v, hm, hm.ints.data(), hm.reals.data());
+  (void)ip;
+  for (int p = 0; p < hm.np; p++)
+    if (v.geom_type[v.pair_geom[2 * p + 1]] == LS_GEOM_MESH && v.geom_type[v.pair_geom[2 * p]] >= LS_GEOM_BOX) return true;
+  return false;
+}
 template <class C>
 static bool cfg_fits(const HostModel& hm, const HostTask& ht) {
+  if (!C::CONVEX && has_convex_pairs(hm)) return false;
   return hm.nv <= C::NV && hm.nb <= C::NB && hm.ng <= C::NG && ht.obs_dim <= C::MAXOBS && hm.cone == (int)C::CONE &&
          hm.integrator == (int)C::RK4;
 }
@@ -310,8 +351,9 @@ static int launch_step(locosim_handle* h, const float* a, float* o, float* r, ui
                        cudaStream_t s) {
   int blocks = (h->n_envs + h->wpb - 1) / h->wpb;
   if (h->regroup) rank_kernel<<<1, 1024, 0, s>>>(h->st.counters, h->st.perm, h->n_envs, h->key_shift);
-  step_kernel<C><<<blocks, h->wpb * 32, h->smem, s>>>(h->slot, h->dt, h->so, h->st, a, o, r, d, no, h->n_envs, auto_reset,
-                                                      h->seed, h->env_off, h->sync_substeps, h->key_mode);
+  step_kernel<C><<<blocks, h->wpb * 32, h->smem + (h->stage_bytes ? h->stage_bytes + 16 : 0), s>>>(
+      h->slot, h->dt, h->so, h->st, a, o, r, d, no, h->n_envs, auto_reset, h->seed, h->env_off, h->sync_substeps, h->key_mode,
+      h->d_stage, h->stage_bytes);
   CK(cudaGetLastError());
   return 0;
 }
@@ -354,7 +396,38 @@ static int setup_cfg(locosim_handle* h) {
   if (h->so.sync_iters < best) h->so.sync_phases &= 63;   // block barriers inside the Newton loop need whole-block lock-step
   h->wpb = best;
   h->smem = best * per_env;
-  CK(cudaFuncSetAttribute(step_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem));
+  { int dbg = getenv("LOCOSIM_DEBUG") ? atoi(getenv("LOCOSIM_DEBUG")) : 0; CK(cudaMemcpyToSymbol(c_debug, &dbg, sizeof(int))); }
+  // ---- optional TMA staging of the hot geom tables (LOCOSIM_STAGE=1; measured, see profiles/README.md) ----
+  if (getenv("LOCOSIM_STAGE") && atoi(getenv("LOCOSIM_STAGE")) > 0) {
+    const int ng = h->hm.ng;
+    const int words = 11 * ng;                                   // size 3, quat 4, rbound 1, margin 1, type 1, bodyid 1
+    const int bytes = (words * 4 + 15) & ~15;
+    if (h->smem + bytes + 16 <= dev_max) {
+      CK(cudaMalloc((void**)&h->d_stage, bytes));
+      CK(cudaMemset(h->d_stage, 0, bytes));
+      float* f = (float*)h->d_stage;
+      CK(cudaMemcpy(f, h->dm.geom_size, 12 * ng, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(f + 3 * ng, h->dm.geom_quat, 16 * ng, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(f + 7 * ng, h->dm.geom_rbound, 4 * ng, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(f + 8 * ng, h->dm.geom_margin, 4 * ng, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(f + 9 * ng, h->dm.geom_type, 4 * ng, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(f + 10 * ng, h->dm.geom_bodyid, 4 * ng, cudaMemcpyDeviceToDevice));
+      unsigned long long* d_base = nullptr;
+      unsigned long long base = 0;
+      CK(cudaMalloc((void**)&d_base, 8));
+      CK(cudaFuncSetAttribute(smem_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem + bytes + 16));
+      smem_probe_kernel<<<1, 32, h->smem + bytes + 16>>>(d_base);
+      CK(cudaMemcpy(&base, d_base, 8, cudaMemcpyDeviceToHost));
+      cudaFree(d_base);
+      const float* sf = (const float*)(uintptr_t)(base + (unsigned long long)h->smem);
+      h->dm.geom_size = sf; h->dm.geom_quat = sf + 3 * ng; h->dm.geom_rbound = sf + 7 * ng; h->dm.geom_margin = sf + 8 * ng;
+      h->dm.geom_type = (const int*)(sf + 9 * ng); h->dm.geom_bodyid = (const int*)(sf + 10 * ng);
+      CK(cudaMemcpyToSymbol(c_models, &h->dm, sizeof(DevModel), sizeof(DevModel) * h->slot));
+      h->stage_bytes = bytes;
+    }
+  }
+  CK(cudaFuncSetAttribute(step_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          h->smem + (h->stage_bytes ? h->stage_bytes + 16 : 0)));
   return 0;
 }
 
@@ -436,6 +509,7 @@ void locosim_destroy(locosim_t* h) {
   cudaFree(h->d_mints); cudaFree(h->d_mreals); cudaFree(h->d_tints); cudaFree(h->d_treals);
   cudaFree(h->st.qpos); cudaFree(h->st.qvel); cudaFree(h->st.ws); cudaFree(h->st.goal); cudaFree(h->st.episode);
   cudaFree(h->st.counters); cudaFree(h->st.dr_row); cudaFree(h->st.perm); cudaFree(h->st.cursor); cudaFree(h->d_pool);
+  cudaFree(h->d_stage);
   delete h;
 }
 
@@ -581,6 +655,9 @@ int locosim_set_param_pool(locosim_t* h, const double* pool, int n_rows, int row
 }
 
 int locosim_kernels_per_step(const locosim_t* h) { return h->regroup ? 2 : 1; }
+int locosim_debug_counters(unsigned long long* out8) {
+  return cudaMemcpyFromSymbol(out8, g_dbg, 64) == cudaSuccess ? 0 : 1;
+}
 
 // Measured non-tensor FP32 peak (the denominator of the FP32 utilisation bench.py reports next to the HBM roofline):
 // 8 independent FMA chains per thread, 2 x 256 threads per SM slot, all SMs, best of 5 launches.

@@ -104,6 +104,8 @@ struct DevModel {
   const int* body_dofmask;   // [nb] bit d set if dof d is on the path root..body
   const int* dof_frow;       // [nv] index of the frictionloss row of dof d, or -1
   const int* tri_ij;         // [nv(nv+1)/2] packed (i << 8) | j of the lower triangle, row major
+  const int* pair_packed;    // [np] g1 | g2 << 12 | flags << 24 (1: plane pair, 2: convex pair) of candidate pair p
+  const float* pair_bound;   // [np] bound of the bounding-sphere / plane mid-phase test of pair p
   // per-env parameter pool (domain randomisation): float offsets of each field inside one pool row
   int po_dof_damping, po_dof_frictionloss, po_dof_armature, po_jnt_stiffness, po_dof_invweight0, po_body_mass,
       po_body_inertia, po_body_ipos, po_body_iquat, po_geom_friction, po_geom_invweight0, po_meaninertia, po_user, pool_P;
@@ -125,8 +127,12 @@ struct DevTask {
 #define LS_MAX_SLOTS 8
 #ifdef LS_EMULATE
 static DevModel c_models[LS_MAX_SLOTS];
+static int c_debug = 0;
 #else
 __constant__ DevModel c_models[LS_MAX_SLOTS];
+__constant__ int c_debug;      // diagnostic switches (LOCOSIM_DEBUG): 1 skip MPR, 2 skip the OBB filter, 4 drop convex pairs,
+                               // 8 count MPR runs / support calls (locosim_debug_counters), 16 no separating-direction cache
+__device__ unsigned long long g_dbg[8];      // (LOCOSIM_DEBUG & 8) MPR statistics: calls, support pairs, hits, cap exits
 #endif
 
 struct SolverOpts {
@@ -144,7 +150,7 @@ struct SolverOpts {
 template <class C>
 struct alignas(16) EnvS {
   enum { NV = C::NV, NB = C::NB, NG = C::NG, NVP = C::NV + 1, JS = (C::NV + 3) & ~3, MAXCON = C::MAXCON, MAXROW = C::MAXROW,
-         MAXUNIT = 2 * C::NV, MAXEFC = 2 * C::NV + C::MAXROW, NRK = C::RK4 ? C::NV : 1 };
+         MAXUNIT = 2 * C::NV, MAXEFC = 2 * C::NV + C::MAXROW, NRK = C::RK4 ? C::NV : 1, NSEP = C::CONVEX ? 4 : 1 };
   // state + per-sub-step vectors
   float qpos[NV], qvel[NV], qacc[NV], qacc_ws[NV], ctrl[NV];
   float qfrc_smooth[NV], qacc_smooth[NV];
@@ -156,7 +162,7 @@ struct alignas(16) EnvS {
   float cdof[NV][6];
   float M[NV][NVP], H[NV][NVP];                              // H: chol(M) during smooth_forces, then the Newton Hessian factor
   // contacts
-  int ncon, nunit, nrow, nefc, solver_iter, iter_sum, pad1, pad2;   // iter_sum: Newton iterations of this control step
+  int ncon, nunit, nrow, nefc, solver_iter, iter_sum, sep_next, mpr_calls;   // iter_sum / mpr_calls: Newton iterations / MPR runs of this control step
   float con_dist[MAXCON], con_pos[MAXCON][3], con_frame[MAXCON][9], con_fri[MAXCON][5], con_imp[MAXCON], con_K[MAXCON],
       con_B[MAXCON], con_incl[MAXCON], con_mu[MAXCON];
   int con_dim[MAXCON], con_g1[MAXCON], con_g2[MAXCON], con_row[MAXCON];
@@ -181,6 +187,9 @@ struct alignas(16) EnvS {
 #ifdef LS_EMULATE
   float Y[6][NV];
 #endif
+  // convex pairs: separating directions found by earlier evaluations of this control step (pair index, unit direction)
+  int sep_pair[NSEP];
+  float sep_dir[NSEP][3];
   // task
   float goal[4];
   float grf[3 * LS_MAX_GRF];   // use_foot_forces: per foot group, contact-frame force summed over the sub-steps
@@ -290,6 +299,8 @@ LS_FN void init_workspace(const int ms, EnvS<C>& e) {
     int i = idx / EnvS<C>::NVP, j = idx - i * EnvS<C>::NVP;
     (&e.M[0][0])[idx] = (i == j && i >= m.nv) ? 1.0f : 0.0f;
   }
+  PAR_FOR(k, EnvS<C>::NSEP) e.sep_pair[k] = -1;
+  LANE0 { e.sep_next = 0; e.mpr_calls = 0; }
   // entries [nv, NV) of the solver vectors are never written by the phases (they loop to nv): keep them 0
   PAR_FOR(i, EnvS<C>::NV) {
     if (i >= m.nv) {
@@ -783,10 +794,10 @@ LS_FN int capsule_capsule(RawCon* c, float margin, const float* pos1, const floa
 #define MPR_TOL 1e-6f
 #define MPR_MAXIT 50
 #if defined(LS_EMULATE)
-static long g_mpr_supports = 0, g_mpr_calls = 0, g_mpr_candidates = 0, g_forward_evals = 0;
+static long g_mpr_supports = 0, g_mpr_calls = 0, g_mpr_candidates = 0, g_forward_evals = 0, g_sep_found = 0, g_sep_ok = 0, g_mpr_nohit = 0, g_obb_pass = 0;
 #endif
 struct MprSup { float v[3], v1[3], v2[3]; };
-struct MprGeom { int type, vadr, vnum; float pos[3], mat[9], size[3], margin; };
+struct MprGeom { int type, vnum; const float* verts; float pos[3], mat[9], size[3], margin; };
 LS_DEV bool mpr_is_zero(float x) { return fabsf(x) < MPR_EPS; }
 LS_DEV bool mpr_eq(float a, float b) {
   float ab = fabsf(a - b);
@@ -796,12 +807,19 @@ LS_DEV bool mpr_eq(float a, float b) {
 }
 LS_DEV void mpr_normalize(float* d) { const float inv = rsqrtf(dot3(d, d)); d[0] *= inv; d[1] *= inv; d[2] *= inv; }
 
-// mjccd_support of one geom (inflated by margin) in the unit world direction dir; all lanes return the same point
-LS_DEV void mpr_support_geom(const float* __restrict__ mesh_vert, const MprGeom& g, const float* dir, float* res) {
+// Per-warp MPR scratch in shared memory (it lives in the contact-Jacobian storage, free until make_constraint): the two
+// geoms and the result of the last support call. Keeping them in shared memory (not in structs handed by reference to
+// __noinline__ functions, which the ABI places in local memory) and the portal in registers is what makes a lone warp's
+// MPR call fast: its lock-step block waits for it.
+struct MprScratch { MprGeom g[2]; float out[12]; };
+
+// mjccd_support of geom g (inflated by margin) in the unit world direction (dx, dy, dz); all lanes compute the same point
+LS_DEV void mpr_support_geom(const MprGeom& g, float dx, float dy, float dz, float* res) {
+  const float dir[3] = {dx, dy, dz};
   float ld[3], r[3] = {0, 0, 0};
   mulmatTvec3(ld, g.mat, dir);
   if (g.type == LS_GEOM_MESH) {
-    const float* v = mesh_vert + 3 * g.vadr;
+    const float* v = g.verts;
     float mx = -3.0e38f;
     int best = 0x7fffffff;
 #ifdef LS_EMULATE
@@ -810,21 +828,19 @@ LS_DEV void mpr_support_geom(const float* __restrict__ mesh_vert, const MprGeom&
       if (d > mx) { mx = d; best = i; }
     }
 #else
-    // 4 vertices per lane and trip: 12 independent loads in flight (the scan is bound by L2 latency, not by arithmetic);
-    // indices past the end are clamped to the last vertex (a duplicate candidate never wins the tie-break)
-    const int last = g.vnum - 1;
-    NOUNROLL for (int i0 = LS_LANE; i0 <= last; i0 += 128) {
-      const int i1 = min(i0 + 32, last), i2 = min(i0 + 64, last), i3 = min(i0 + 96, last);
-      const float d0 = ld[0] * v[3 * i0] + ld[1] * v[3 * i0 + 1] + ld[2] * v[3 * i0 + 2];
-      const float d1 = ld[0] * v[3 * i1] + ld[1] * v[3 * i1 + 1] + ld[2] * v[3 * i1 + 2];
-      const float d2 = ld[0] * v[3 * i2] + ld[1] * v[3 * i2 + 1] + ld[2] * v[3 * i2 + 2];
-      const float d3 = ld[0] * v[3 * i3] + ld[1] * v[3 * i3 + 1] + ld[2] * v[3 * i3 + 2];
-      if (d0 > mx) { mx = d0; best = i0; }
-      if (d1 > mx) { mx = d1; best = i1; }
-      if (d2 > mx) { mx = d2; best = i2; }
-      if (d3 > mx) { mx = d3; best = i3; }
+    const int n = g.vnum;
+#pragma unroll 4
+    for (int i = LS_LANE; i < n; i += 32) {
+      const float d = ld[0] * v[3 * i] + ld[1] * v[3 * i + 1] + ld[2] * v[3 * i + 2];
+      if (d > mx) { mx = d; best = i; }
     }
-    WARP_ARGMAX(mx, best);
+    // warp argmax in two redux instructions instead of a 5-round shuffle butterfly (this sits on the critical path of a
+    // lone warp): max of the order-preserving integer image of the dot product, then the smallest index among the
+    // lanes that hold it (= the first maximum of a serial scan)
+    unsigned key = __float_as_uint(mx);
+    key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);
+    const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+    best = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (unsigned)best : 0x7fffffffu);
 #endif
     r[0] = v[3 * best]; r[1] = v[3 * best + 1]; r[2] = v[3 * best + 2];
   } else if (g.type == LS_GEOM_BOX) {
@@ -833,17 +849,29 @@ LS_DEV void mpr_support_geom(const float* __restrict__ mesh_vert, const MprGeom&
   mulmatvec3(res, g.mat, r);
   for (int k = 0; k < 3; k++) res[k] += g.pos[k] + dir[k] * g.margin;
 }
-LS_DEV void mpr_support(const float* __restrict__ mv, const MprGeom& a, const MprGeom& b, const float* dir, MprSup& sp) {
-  const float nd[3] = {-dir[0], -dir[1], -dir[2]};
-  mpr_support_geom(mv, a, dir, sp.v1);
-  mpr_support_geom(mv, b, nd, sp.v2);
-  for (int k = 0; k < 3; k++) sp.v[k] = sp.v1[k] - sp.v2[k];
-#if defined(LS_EMULATE)
+// support point of the Minkowski difference: sc->out = {v = v1 - v2, v1, v2}. ONE out-of-line copy (the vertex scan is
+// the bulk of the MPR code and has 6 call sites).
+LS_FN void mpr_support_call(MprScratch* sc, float dx, float dy, float dz) {
+  float v1[3], v2[3];
+  mpr_support_geom(sc->g[0], dx, dy, dz, v1);
+  mpr_support_geom(sc->g[1], -dx, -dy, -dz, v2);
+  LANE0 {
+    for (int k = 0; k < 3; k++) { sc->out[k] = v1[k] - v2[k]; sc->out[3 + k] = v1[k]; sc->out[6 + k] = v2[k]; }
+  }
+  SYNC();
+#if !defined(LS_EMULATE)
+  if ((c_debug & 8) && LS_LANE == 0) atomicAdd(&g_dbg[1], 1ULL);
+#else
   g_mpr_supports++;
 #if defined(LS_TRACE)
-  printf("    [f32] dir %.6f %.6f %.6f -> v %.7f %.7f %.7f\n", dir[0], dir[1], dir[2], sp.v[0], sp.v[1], sp.v[2]);
+  printf("    [f32] dir %.6f %.6f %.6f -> v %.7f %.7f %.7f\n", dx, dy, dz, sc->out[0], sc->out[1], sc->out[2]);
 #endif
 #endif
+}
+LS_DEV void mpr_support(MprScratch* sc, const float* dir, MprSup& sp) {
+  mpr_support_call(sc, dir[0], dir[1], dir[2]);
+  for (int k = 0; k < 3; k++) { sp.v[k] = sc->out[k]; sp.v1[k] = sc->out[3 + k]; sp.v2[k] = sc->out[6 + k]; }
+  SYNC();                                    // (everybody has read `out` before the next call rewrites it)
 }
 LS_DEV void mpr_portal_dir(const MprSup* p, float* dir) {
   float a[3], b[3];
@@ -918,8 +946,11 @@ LS_DEV void mpr_find_pos(const MprSup* p, float* pos) {
   for (int k = 0; k < 3; k++) pos[k] = (p1[k] * inv + p2[k] * inv) * 0.5f;
 }
 // ccdMPRPenetration: true and (depth, dir, pos) if the inflated geoms intersect
-LS_FN bool mpr_penetration(const float* __restrict__ mv, const MprGeom& o1, const MprGeom& o2, float* depth, float* pdir,
-                           float* pos) {
+// returns false if the geoms do not intersect; `sep` then holds the last direction tested (a separating direction whenever
+// the search stopped because a support point did not reach past the origin)
+LS_FN bool mpr_penetration(MprScratch* sc, float* depth, float* pdir, float* pos, float* sep) {
+  const MprGeom& o1 = sc->g[0];
+  const MprGeom& o2 = sc->g[1];
   MprSup p[4], v4;
   float dir[3], va[3], vb[3], dot;
   // ---- discoverPortal ----
@@ -927,8 +958,9 @@ LS_FN bool mpr_penetration(const float* __restrict__ mv, const MprGeom& o1, cons
   if (mpr_eq(p[0].v[0], 0.0f) && mpr_eq(p[0].v[1], 0.0f) && mpr_eq(p[0].v[2], 0.0f)) p[0].v[0] += MPR_EPS * 10.0f;
   for (int k = 0; k < 3; k++) dir[k] = -p[0].v[k];
   mpr_normalize(dir);
-  mpr_support(mv, o1, o2, dir, p[1]);
+  mpr_support(sc, dir, p[1]);
   dot = dot3(p[1].v, dir);
+  sep[0] = dir[0]; sep[1] = dir[1]; sep[2] = dir[2];
   if (mpr_is_zero(dot) || dot < 0) return false;
   cross3(dir, p[0].v, p[1].v);
   if (!(dot3(dir, dir) > 1e-10f * dot3(p[0].v, p[0].v) * dot3(p[1].v, p[1].v))) {      // origin on the segment v0-v1 (relative test)
@@ -939,8 +971,9 @@ LS_FN bool mpr_penetration(const float* __restrict__ mv, const MprGeom& o1, cons
     return true;
   }
   mpr_normalize(dir);
-  mpr_support(mv, o1, o2, dir, p[2]);
+  mpr_support(sc, dir, p[2]);
   dot = dot3(p[2].v, dir);
+  sep[0] = dir[0]; sep[1] = dir[1]; sep[2] = dir[2];
   if (mpr_is_zero(dot) || dot < 0) return false;
   for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
   cross3(dir, va, vb);
@@ -950,8 +983,9 @@ LS_FN bool mpr_penetration(const float* __restrict__ mv, const MprGeom& o1, cons
     for (int k = 0; k < 3; k++) dir[k] = -dir[k];
   }
   NOUNROLL for (int guard = 0; guard < 4 * MPR_MAXIT; guard++) {
-    mpr_support(mv, o1, o2, dir, p[3]);
+    mpr_support(sc, dir, p[3]);
     dot = dot3(p[3].v, dir);
+    sep[0] = dir[0]; sep[1] = dir[1]; sep[2] = dir[2];
     if (mpr_is_zero(dot) || dot < 0) return false;
     bool cont = false;
     cross3(va, p[1].v, p[3].v);
@@ -972,15 +1006,20 @@ LS_FN bool mpr_penetration(const float* __restrict__ mv, const MprGeom& o1, cons
     mpr_portal_dir(p, dir);
     dot = dot3(dir, p[1].v);
     if (mpr_is_zero(dot) || dot > 0) break;
-    mpr_support(mv, o1, o2, dir, v4);
+    mpr_support(sc, dir, v4);
     dot = dot3(v4.v, dir);
+    sep[0] = dir[0]; sep[1] = dir[1]; sep[2] = dir[2];
     if (!(mpr_is_zero(dot) || dot > 0) || mpr_reach_tolerance(p, v4, dir) || guard > 4 * MPR_MAXIT) return false;
     mpr_expand_portal(p, v4);
   }
   // ---- findPenetr ----
   NOUNROLL for (int it = 0;; it++) {
     mpr_portal_dir(p, dir);
-    mpr_support(mv, o1, o2, dir, v4);
+    mpr_support(sc, dir, v4);
+#if !defined(LS_EMULATE)
+    if ((c_debug & 8) && LS_LANE == 0 && it > MPR_MAXIT) atomicAdd(&g_dbg[3], 1ULL);
+    if ((c_debug & 8) && LS_LANE == 0 && !(dir[0] == dir[0])) atomicAdd(&g_dbg[4], 1ULL);
+#endif
     if (mpr_reach_tolerance(p, v4, dir) || it > MPR_MAXIT) {
       *depth = sqrtf(mpr_point_tri_dist2(p[1].v, p[2].v, p[3].v, pdir));
       if (mpr_is_zero(*depth)) pdir[0] = pdir[1] = pdir[2] = 0;
@@ -992,28 +1031,35 @@ LS_FN bool mpr_penetration(const float* __restrict__ mv, const MprGeom& o1, cons
   }
 }
 
-// mid-phase test for one candidate pair (see oracle/locosim_ref.c collision(): no margin in the filter)
+// mid-phase test for one candidate pair (see oracle/locosim_ref.c collision(): no margin in the filter); pk = pair_packed[p]
 template <class C>
-LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p) {
+LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p, int pk) {
   const DevModel& m = c_models[ms];
-  int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
-  float d[3] = {e.gxpos[g2][0] - e.gxpos[g1][0], e.gxpos[g2][1] - e.gxpos[g1][1], e.gxpos[g2][2] - e.gxpos[g1][2]};
-  if (m.geom_type[g1] == LS_GEOM_PLANE) {
+  const int g1 = pk & 0xfff, g2 = (pk >> 12) & 0xfff;
+  const float d[3] = {e.gxpos[g2][0] - e.gxpos[g1][0], e.gxpos[g2][1] - e.gxpos[g1][1], e.gxpos[g2][2] - e.gxpos[g1][2]};
+  const float bound = m.pair_bound[p];
+  if (pk & (1 << 24)) {
     float mat1[9];
     geom_mat(ms, e, g1, mat1);
-    float n[3] = {mat1[2], mat1[5], mat1[8]};
-    return dot3(d, n) <= m.geom_rbound[g2];
+    const float n[3] = {mat1[2], mat1[5], mat1[8]};
+    return dot3(d, n) <= bound;
   }
-  float bound = m.geom_rbound[g1] + m.geom_rbound[g2];
-  if (dot3(d, d) > bound * bound) return false;
-  if (m.geom_type[g2] != LS_GEOM_MESH) return true;
+  return dot3(d, d) <= bound * bound;
+}
+
+// second filter of a convex pair (box | mesh vs mesh) that passed the bounding spheres
+template <class C>
+LS_FN bool convex_obb_filter(const int ms, const EnvS<C>& e, int p) {
+  const DevModel& m = c_models[ms];
+  const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+  const float d[3] = {e.gxpos[g2][0] - e.gxpos[g1][0], e.gxpos[g2][1] - e.gxpos[g1][1], e.gxpos[g2][2] - e.gxpos[g1][2]};
 #if defined(LS_EMULATE)
   g_mpr_candidates++;
 #endif
   // Convex pair (box | mesh vs mesh): MPR reports a contact only if the (margin-inflated) geoms intersect. Their oriented
   // boxes (geom_size = the mesh's AABB in its own principal frame) contain them, so disjoint boxes mean no contact:
   // 15-axis separating-axis test of the two boxes (conservative prefilter: it never rejects an intersecting pair;
-  // measured on the humanoid: of ~60 bone pairs per evaluation that pass the bounding spheres, ~N survive).
+  // measured on the humanoid: of ~60 bone pairs per evaluation that pass the bounding spheres, 1.2 survive).
   float RA[9], RB[9];
   geom_mat(ms, e, g1, RA);
   geom_mat(ms, e, g2, RB);
@@ -1046,24 +1092,77 @@ LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p) {
 
 // warp-cooperative narrow phase of one convex pair (mjc_Convex): at most one contact
 template <class C>
-LS_FN int convex_narrow(const int ms, const EnvS<C>& e, int p, RawCon* raw) {
+LS_FN int convex_narrow(const int ms, EnvS<C>& e, int p, RawCon* raw) {
   const DevModel& m = c_models[ms];
   const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
   const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
-  MprGeom a, b;
-  a.type = m.geom_type[g1]; a.vadr = m.geom_meshadr[g1]; a.vnum = m.geom_meshnum[g1]; a.margin = 0.5f * margin;
-  b.type = m.geom_type[g2]; b.vadr = m.geom_meshadr[g2]; b.vnum = m.geom_meshnum[g2]; b.margin = 0.5f * margin;
-  for (int k = 0; k < 3; k++) {
-    a.pos[k] = e.gxpos[g1][k]; b.pos[k] = e.gxpos[g2][k];
-    a.size[k] = m.geom_size[3 * g1 + k]; b.size[k] = m.geom_size[3 * g2 + k];
+  // scratch + staged vertices live in the contact-Jacobian storage (nobody uses it before make_constraint)
+  constexpr int SCR = (int)((sizeof(MprScratch) + 15) / 16 * 4);                  // floats taken by the scratch block
+  MprScratch* sc = reinterpret_cast<MprScratch*>(&e.J[0][0]);
+  float* buf = &e.J[0][0] + SCR;
+  const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+  const int n1 = t1 == LS_GEOM_MESH ? 3 * m.geom_meshnum[g1] : 0, n2 = t2 == LS_GEOM_MESH ? 3 * m.geom_meshnum[g2] : 0;
+  const float* s1 = m.mesh_vert + 3 * m.geom_meshadr[g1];
+  const float* s2 = m.mesh_vert + 3 * m.geom_meshadr[g2];
+  // An MPR call scans the two vertex sets ~10 times each, one after the other: the vertices of both meshes are copied once
+  // (coalesced, all loads in flight) into shared memory whenever they fit (~400 vertices; larger pairs scan global memory)
+  const bool staged = n1 + n2 <= EnvS<C>::MAXROW * EnvS<C>::JS - SCR;
+  if (staged) {
+#ifdef LS_EMULATE
+    for (int i = 0; i < n1; i++) buf[i] = s1[i];
+    for (int i = 0; i < n2; i++) buf[n1 + i] = s2[i];
+#else
+#pragma unroll 4
+    for (int i = LS_LANE; i < n1; i += 32) buf[i] = s1[i];
+#pragma unroll 4
+    for (int i = LS_LANE; i < n2; i += 32) buf[n1 + i] = s2[i];
+#endif
   }
-  geom_mat(ms, e, g1, a.mat);
-  geom_mat(ms, e, g2, b.mat);
-  float depth, dir[3], pos[3];
+  {
+    float m1[9], m2[9];
+    geom_mat(ms, e, g1, m1);
+    geom_mat(ms, e, g2, m2);
+    LANE0 {
+      MprGeom& a = sc->g[0];
+      MprGeom& b = sc->g[1];
+      a.type = t1; a.vnum = m.geom_meshnum[g1]; a.margin = 0.5f * margin; a.verts = staged ? buf : s1;
+      b.type = t2; b.vnum = m.geom_meshnum[g2]; b.margin = 0.5f * margin; b.verts = staged ? buf + n1 : s2;
+      for (int k = 0; k < 3; k++) {
+        a.pos[k] = e.gxpos[g1][k]; b.pos[k] = e.gxpos[g2][k];
+        a.size[k] = m.geom_size[3 * g1 + k]; b.size[k] = m.geom_size[3 * g2 + k];
+      }
+      for (int k = 0; k < 9; k++) { a.mat[k] = m1[k]; b.mat[k] = m2[k]; }
+    }
+  }
+  SYNC();
+  float depth, dir[3], pos[3], sep[3] = {0, 0, 0};
+  // A direction that separated this pair in an earlier evaluation of the control step is tried first (ONE support pair;
+  // strict separation of the inflated geoms along it means MPR would not report a contact either); if it fails the full
+  // MPR runs and its last test direction refreshes the cache.
+  int slot = -1;
+  for (int k = 0; k < EnvS<C>::NSEP; k++) if (e.sep_pair[k] == p) slot = k;
+  if (slot >= 0 && !(c_debug & 16)) {
+    MprSup sp;
+    const float cd[3] = {e.sep_dir[slot][0], e.sep_dir[slot][1], e.sep_dir[slot][2]};
+    mpr_support(sc, cd, sp);
+    if (dot3(sp.v, cd) < -1e-7f) return 0;
+  }
 #if defined(LS_EMULATE)
   g_mpr_calls++;
+#else
+  if ((c_debug & 8) && LS_LANE == 0) atomicAdd(&g_dbg[0], 1ULL);
 #endif
-  if (!mpr_penetration(m.mesh_vert, a, b, &depth, dir, pos)) return 0;
+  LANE0 { e.mpr_calls += 1; }
+  if (!mpr_penetration(sc, &depth, dir, pos, sep)) {
+    if (slot < 0) { slot = e.sep_next & (EnvS<C>::NSEP - 1); }
+    SYNC();
+    LANE0 {
+      if (e.sep_pair[slot] != p) e.sep_next = e.sep_next + 1;
+      e.sep_pair[slot] = p; e.sep_dir[slot][0] = sep[0]; e.sep_dir[slot][1] = sep[1]; e.sep_dir[slot][2] = sep[2];
+    }
+    SYNC();
+    return 0;
+  }
   if (dir[0] == 0.0f && dir[1] == 0.0f && dir[2] == 0.0f) return 0;      // contact found but normal undefined
   raw->dist = margin - depth;
   for (int k = 0; k < 3; k++) { raw->pos[k] = pos[k]; raw->frame[k] = dir[k]; raw->frame[3 + k] = 0; }
@@ -1164,16 +1263,34 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
   const DevModel& m = c_models[ms];
   LANE0 { e.ncon = 0; }
   SYNC();
+  // Convex pairs (box | mesh vs mesh, mjc_Convex) that pass the bounding spheres are only COLLECTED in the pair loop
+  // (compacted list in the constraint-row storage, which is free until make_constraint) and handled afterwards: the
+  // oriented-box test runs on the compacted list (full lanes instead of a few lanes in every round of 32 pairs) and the
+  // survivors go through the warp-cooperative MPR one by one. Their contacts therefore FOLLOW the primitive contacts in
+  // the list (ordered by pair among themselves); the order of constraint rows has no influence on the solution.
+  unsigned short* cand = reinterpret_cast<unsigned short*>(e.r_D);
+  const int cand_max = (int)(5 * EnvS<C>::MAXEFC * sizeof(float) / sizeof(unsigned short));
+  int ncand = 0;
 #ifdef LS_EMULATE
   for (int p = 0; p < m.np; p++) {
-    if (!pair_filter(ms, e, p)) continue;
+    const int pk = m.pair_packed[p];
+    if (!pair_filter(ms, e, p, pk)) continue;
+    if (pk & (2 << 24)) { if (ncand < cand_max) cand[ncand++] = (unsigned short)p; continue; }
     RawCon raw[4];
     int g1, g2; float margin;
-    int n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
-    if (m.geom_type[g2] == LS_GEOM_MESH && m.geom_type[g1] >= LS_GEOM_BOX) n = convex_narrow(ms, e, p, raw);
+    const int n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
     const float incl = pair_incl(m, g1, g2, margin);
     for (int k = 0; k < n; k++)
       if (raw[k].dist < incl && e.ncon < EnvS<C>::MAXCON) fill_contact(ms, e, e.ncon++, g1, g2, incl, raw + k);
+  }
+  for (int k = 0; k < ncand; k++) {
+    const int p = cand[k];
+    if (!convex_obb_filter(ms, e, p)) continue;
+    RawCon rc;
+    if (!convex_narrow(ms, e, p, &rc)) continue;
+    const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+    const float incl = pair_incl(m, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]));
+    if (rc.dist < incl && e.ncon < EnvS<C>::MAXCON) fill_contact(ms, e, e.ncon++, g1, g2, incl, &rc);
   }
 #else
   // 32 candidate pairs at a time: every lane filters its pair, the lanes that hit run the narrow phase in parallel,
@@ -1182,21 +1299,25 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
   const int lane = LS_LANE;
   for (int base = 0; base < m.np; base += 32) {
     const int p = base + lane;
-    const bool hit = (p < m.np) && pair_filter(ms, e, p);
+    const int pk = p < m.np ? m.pair_packed[p] : 0;
+    bool hit = (p < m.np) && pair_filter(ms, e, p, pk);
+    if (!__any_sync(0xffffffffu, hit)) continue;        // (most rounds of 32 pairs have no candidate at all)
+    if (C::CONVEX) {                                   // (configurations whose models carry convex pairs)
+      const bool conv = hit && (pk & (2 << 24));
+      const unsigned cmask = (c_debug & 4) ? 0u : __ballot_sync(0xffffffffu, conv);
+      if (cmask) {
+        const int slot = ncand + __popc(cmask & ((1u << lane) - 1u));
+        if (conv && slot < cand_max) cand[slot] = (unsigned short)p;
+        ncand += __popc(cmask);
+        if (conv) hit = false;
+        if (!__any_sync(0xffffffffu, hit)) continue;
+      }
+    }
     RawCon raw[4];
     int g1 = 0, g2 = 0, n = 0, nact = 0;
     float margin = 0, incl = 0;
-    if (hit) n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
-    // convex pairs (box | mesh vs mesh) that survived the prefilter: one at a time, by the whole warp
-    unsigned cm = __ballot_sync(0xffffffffu, hit && m.geom_type[g2] == LS_GEOM_MESH && m.geom_type[g1] >= LS_GEOM_BOX);
-    while (cm) {
-      const int src = __ffs(cm) - 1;
-      cm &= cm - 1;
-      RawCon rc;
-      const int nn = convex_narrow(ms, e, base + src, &rc);
-      if (lane == src) { n = nn; raw[0] = rc; }
-    }
     if (hit) {
+      n = pair_narrow(ms, e, p, raw, &g1, &g2, &margin);
       incl = pair_incl(m, g1, g2, margin);
       for (int k = 0; k < 4; k++) if (k < n && raw[k].dist < incl) nact++;
     }
@@ -1221,6 +1342,28 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
     __syncwarp();
     LANE0 { const int nc = e.ncon + total; e.ncon = nc < EnvS<C>::MAXCON ? nc : EnvS<C>::MAXCON; }
     __syncwarp();
+  }
+  if (C::CONVEX && ncand > 0) {
+    if (ncand > cand_max) ncand = cand_max;
+    __syncwarp();
+    NOUNROLL for (int base = 0; base < ncand; base += 32) {
+      const int p = base + lane < ncand ? (int)cand[base + lane] : -1;
+      unsigned pm = __ballot_sync(0xffffffffu, p >= 0 && ((c_debug & 2) || convex_obb_filter(ms, e, p)));
+      while (pm) {
+        const int src = __ffs(pm) - 1;
+        pm &= pm - 1;
+        const int pp = __shfl_sync(0xffffffffu, p, src);
+        RawCon rc;
+        const int nn = (c_debug & 1) ? 0 : convex_narrow(ms, e, pp, &rc);   // warp-cooperative; every lane holds the result
+        const int g1 = m.pair_geom[2 * pp], g2 = m.pair_geom[2 * pp + 1];
+        const float incl = pair_incl(m, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]));
+        const int ci = e.ncon;
+        if (nn > 0 && rc.dist < incl && ci < EnvS<C>::MAXCON) {
+          LANE0 { fill_contact(ms, e, ci, g1, g2, incl, &rc); e.ncon = ci + 1; }
+          __syncwarp();
+        }
+      }
+    }
   }
 #endif
   SYNC();

@@ -89,7 +89,7 @@ void emu_get_state(EmuBase* s, double* qpos, double* qvel) { s->get(qpos, qvel, 
 void emu_get_qacc(EmuBase* s, double* qacc) { s->get(nullptr, nullptr, qacc, nullptr); }
 void emu_get_ws(EmuBase* s, double* w) { s->get(nullptr, nullptr, nullptr, w); }
 void emu_set_ws(EmuBase* s, const double* w) { s->set_ws(w); }
-long emu_mpr_stat(int k) { return k == 0 ? g_forward_evals : (k == 1 ? g_mpr_candidates : (k == 2 ? g_mpr_calls : g_mpr_supports)); }
+long emu_mpr_stat(int k) { long v[8] = {g_forward_evals, g_mpr_candidates, g_mpr_calls, g_mpr_supports, g_sep_found, g_sep_ok, g_mpr_nohit, 0}; return v[k]; }
 long emu_ls_evals() { return g_ls_evals; }
 long emu_ls_searches() { return g_ls_searches; }
 int emu_ncon(EmuBase* s) { return s->info(0); }

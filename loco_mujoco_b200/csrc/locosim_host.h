@@ -2,6 +2,7 @@
 // parse the ModelPack / TaskSpec wire blobs (include/*.h), convert reals to fp32, derive the engine-only tables,
 // and bind DevModel / DevTask pointer views onto a (host or device) base address.
 #pragma once
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -41,18 +42,21 @@ static inline std::string parse_model(HostModel& h, const int* ints, int n_ints,
   for (size_t i = 0; i < nr; i++) h.reals[i] = (float)reals[MPR_HEADER_LEN + i];
   // locate the arrays we need for the derived tables
   const int* ip = h.ints.data();
-  const int *body_parentid = 0, *body_lastdof = 0, *dof_parentid = 0, *geom_condim = 0;
+  const int *body_parentid = 0, *body_lastdof = 0, *dof_parentid = 0, *geom_condim = 0, *pair_geom = 0, *geom_type = 0;
 #define X(name, cnt) if (std::string(#name) == "body_parentid") body_parentid = ip; \
                      if (std::string(#name) == "body_lastdof") body_lastdof = ip;   \
                      if (std::string(#name) == "dof_parentid") dof_parentid = ip;   \
                      if (std::string(#name) == "geom_condim") geom_condim = ip;     \
+                     if (std::string(#name) == "pair_geom") pair_geom = ip;         \
+                     if (std::string(#name) == "geom_type") geom_type = ip;         \
                      ip += (cnt);
   LOCOSIM_MP_INT_FIELDS(X)
 #undef X
   const float* rp = h.reals.data();
-  const float *dof_frictionloss = 0, *dof_damping = 0;
+  const float *dof_frictionloss = 0, *dof_damping = 0, *geom_rbound = 0;
 #define X(name, cnt) if (std::string(#name) == "dof_frictionloss") dof_frictionloss = rp; \
                      if (std::string(#name) == "dof_damping") dof_damping = rp;           \
+                     if (std::string(#name) == "geom_rbound") geom_rbound = rp;           \
                      rp += (cnt);
   LOCOSIM_MP_REAL_FIELDS(X)
 #undef X
@@ -79,6 +83,23 @@ static inline std::string parse_model(HostModel& h, const int* ints, int n_ints,
   h.ints.insert(h.ints.end(), mask.begin(), mask.end());
   h.ints.insert(h.ints.end(), frow.begin(), frow.end());
   for (int i = 0; i < 32; i++) for (int j = 0; j <= i; j++) h.ints.push_back((i << 8) | j);   // row-major lower triangle, n <= 32
+  // packed candidate-pair table of the mid-phase: g1 | g2 << 12 | flags << 24 (1: g1 is a plane, 2: convex pair = box | mesh
+  // vs mesh) and, as float bits, the bound of the bounding-sphere test (rbound[g2] for planes, else rbound[g1] + rbound[g2])
+  if (ng >= 4096) return "more than 4095 geoms";
+  for (int p = 0; p < np; p++) {
+    const int g1 = pair_geom[2 * p], g2 = pair_geom[2 * p + 1];
+    int flags = 0;
+    if (geom_type[g1] == LS_GEOM_PLANE) flags |= 1;
+    if (geom_type[g2] == LS_GEOM_MESH && geom_type[g1] >= LS_GEOM_BOX) flags |= 2;
+    h.ints.push_back(g1 | (g2 << 12) | (flags << 24));
+  }
+  for (int p = 0; p < np; p++) {
+    const int g1 = pair_geom[2 * p], g2 = pair_geom[2 * p + 1];
+    const float b = geom_type[g1] == LS_GEOM_PLANE ? geom_rbound[g2] : geom_rbound[g1] + geom_rbound[g2];
+    int bits;
+    memcpy(&bits, &b, 4);
+    h.ints.push_back(bits);
+  }
   // ---- parameter pool layout: POOL_FIELDS of loco_mujoco_b200/domain_randomization.py, meaninertia, LS_POOL_USER user
   //      features, padded to 4
   {
@@ -126,11 +147,13 @@ static inline void bind_model(DevModel& m, const HostModel& h, const int* ibase,
   m.body_dofmask = ip; ip += nb;
   m.dof_frow = ip; ip += nv;
   m.tri_ij = ip; ip += 32 * 33 / 2;
+  m.pair_packed = ip; ip += np;
+  m.pair_bound = reinterpret_cast<const float*>(ip); ip += np;
   m.po_dof_damping = h.po[0]; m.po_dof_frictionloss = h.po[1]; m.po_dof_armature = h.po[2]; m.po_jnt_stiffness = h.po[3];
   m.po_dof_invweight0 = h.po[4]; m.po_body_mass = h.po[5]; m.po_body_inertia = h.po[6]; m.po_body_ipos = h.po[7];
   m.po_body_iquat = h.po[8]; m.po_geom_friction = h.po[9]; m.po_geom_invweight0 = h.po[10]; m.po_meaninertia = h.po[11]; m.po_user = h.po[12];
   m.pool_P = h.pool_P;
-  (void)nu; (void)np; (void)nm; (void)ng;
+  (void)nu; (void)nm; (void)ng;
 }
 
 struct HostTask {

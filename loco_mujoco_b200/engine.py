@@ -81,7 +81,8 @@ EXPORTED_SYMBOLS = ["locosim_create", "locosim_destroy", "locosim_last_error", "
                     "locosim_get_state", "locosim_set_state", "locosim_get_counters", "locosim_launch_info",
                     "locosim_param_pool_row_len", "locosim_set_param_pool", "locosim_get_param_rows",
                     "locosim_kernels_per_step", "locosim_reset_rows", "locosim_set_goal", "locosim_measure_fp32_peak",
-                    "locosim_set_reset_rotation", "locosim_get_cursor", "locosim_dataset_rows", "locosim_create_dataset"]
+                    "locosim_set_reset_rotation", "locosim_get_cursor", "locosim_dataset_rows", "locosim_create_dataset",
+                    "locosim_debug_counters"]
 
 
 def measure_fp32_peak(device=0):

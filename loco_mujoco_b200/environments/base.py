@@ -137,7 +137,7 @@ class LocoEnv:
                  init_step_no=None, timestep=0.001, use_foot_forces=False, default_camera_mode="follow",
                  use_absorbing_states=True, domain_randomization_config=None, parallel_dom_rand=True,
                  N_worker_per_xml_dom_rand=4, num_envs=None, device="cuda:0", seed=0, env_id_offset=0,
-                 compiled_model=None, copy_outputs=True, **viewer_params):
+                 compiled_model=None, copy_outputs=True, convex_collisions=True, **viewer_params):
         if type(xml_handles) != list:
             xml_handles = [xml_handles]
         self._xml_handles = xml_handles
@@ -198,6 +198,9 @@ class LocoEnv:
         # caller private copies (two device-to-device copies per step), so that appending them to a rollout buffer is safe;
         # copy_outputs=False returns views that are only valid until the next step()/reset() (zero-copy, benchmark use).
         self._copy_outputs = bool(copy_outputs)
+        # convex_collisions=False drops the mesh-mesh / box-mesh candidate pairs (bone against bone: mjc_Convex / MPR) from the
+        # engine's pair table: faster (HumanoidTorque: ~3x), but not what the reference simulates. Default: on.
+        self._convex_collisions = bool(convex_collisions)
         self._engine = None
         self._obs = None
 
@@ -374,7 +377,8 @@ class LocoEnv:
             from ..engine import CudaEngine
             import torch
             dev = torch.device(self._device)
-            self._engine = CudaEngine(modelpack.pack(self._model), self.task_spec().pack(), self.num_envs,
+            self._engine = CudaEngine(modelpack.pack(self._model, convex_pairs=self._convex_collisions),
+                                      self.task_spec().pack(), self.num_envs,
                                       device=dev.index or 0, seed=self._seed, env_id_offset=self._env_id_offset)
             if self._domain_rand_config is not None:
                 self._engine.set_param_pool(self.domain_randomization_pool())

@@ -228,7 +228,7 @@ class UnitreeA1(LocoEnv):
         if dataset_type != "real":
             raise NotImplementedError("perfect datasets are not shipped (network download in the reference)")
         if "reward_type" in kwargs:
-            reward_type, reward_params = kwargs.pop("reward_type"), kwargs.pop("reward_params")
+            reward_type, reward_params = kwargs.pop("reward_type"), kwargs.pop("reward_params", dict())
         else:
             reward_type, reward_params = "velocity_vector", dict()
         fname = "walk_straight.npz" if task == "simple" else "walk_8_dir.npz"

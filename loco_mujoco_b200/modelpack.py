@@ -28,15 +28,30 @@ EXTRA_ARRAYS = ["opt_gravity", "body_weldid", "body_dofadr", "body_dofnum", "dof
                 "geom_conaffinity", "site_bodyid", "site_pos", "site_quat"]
 
 
-def pack(m):
-    """Model -> (ints int32[], reals float64[])"""
+GEOM_BOX, GEOM_MESH = 6, 7
+
+
+def convex_pair_mask(m):
+    """True for the candidate pairs that go through the general convex routine (mjc_Convex / MPR): box | mesh vs mesh."""
+    pg = np.asarray(m.pair_geom).reshape(-1, 2)
+    t = np.asarray(m.geom_type)
+    return (t[pg[:, 1]] == GEOM_MESH) & (t[pg[:, 0]] >= GEOM_BOX) if len(pg) else np.zeros(0, dtype=bool)
+
+
+def pack(m, convex_pairs=True):
+    """Model -> (ints int32[], reals float64[]). convex_pairs=False leaves the mesh-mesh / box-mesh candidate pairs out of
+    the pair table (LocoEnv kwarg `convex_collisions=False`: the round-1 feature set, without bone-bone contacts)."""
+    pair_geom = np.asarray(m.pair_geom).reshape(-1, 2)
+    if not convex_pairs:
+        pair_geom = pair_geom[~convex_pair_mask(m)]
     ih = np.zeros(16, dtype=np.int32)
-    ih[:11] = [MAGIC, VERSION, m.nbody, m.nv, m.ngeom, m.nu, m.npair, len(m.mesh_vert), m.opt_integrator,
+    ih[:11] = [MAGIC, VERSION, m.nbody, m.nv, m.ngeom, m.nu, len(pair_geom), len(m.mesh_vert), m.opt_integrator,
                m.opt_cone, m.opt_iterations]
     rh = np.zeros(16, dtype=np.float64)
     rh[:7] = [m.opt_timestep, m.opt_gravity[0], m.opt_gravity[1], m.opt_gravity[2], m.opt_impratio,
               m.opt_tolerance, m.stat_meaninertia]
-    ints = [ih] + [np.ascontiguousarray(getattr(m, f), dtype=np.int32).ravel() for f in INT_FIELDS]
+    ints = [ih] + [np.ascontiguousarray(pair_geom if f == "pair_geom" else getattr(m, f), dtype=np.int32).ravel()
+                   for f in INT_FIELDS]
     reals = [rh] + [np.ascontiguousarray(getattr(m, f), dtype=np.float64).ravel() for f in REAL_FIELDS]
     return np.concatenate(ints), np.concatenate(reals)
 

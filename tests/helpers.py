@@ -71,20 +71,26 @@ def reference_draws(env, seed=0):
 
 
 def oracle_step_sensitivity(oracle, model_blobs, task_blobs, traj_no, step_no, qpos, qvel, action, ref_obs,
-                            eps=1e-6, n_probe=4, seed=0):
+                            eps=1e-6, n_probe=4, seed=0, relative=False, user=None):
     """How far the ORACLE's own one-step result moves when its start state is perturbed by `eps` (fp32 resolution).
 
     A control step is discontinuous where a contact or a joint limit switches on (trajectory samples clipped onto a
-    joint limit sit exactly on such a switch); there an fp32 engine and an fp64 oracle may legitimately take different
-    branches. Tests use this to tell such a state from a real mismatch: the fp32 error must not exceed what a
-    1e-6 perturbation does to the fp64 result.
+    joint limit sit exactly on such a switch) and where MPR changes the facet whose normal it reports for a bone-bone
+    contact; there an fp32 engine and an fp64 oracle may legitimately take different branches. Tests use this to tell
+    such a state from a real mismatch: the fp32 error must not exceed what an fp32-sized perturbation does to the fp64
+    result. relative=True scales the perturbation with the magnitude of each entry (eps * (1 + |x|): random torques drive
+    joint velocities to O(100) rad/s, where fp32 resolution is 1e-5, not 1e-7).
     """
     rng = np.random.RandomState(seed)
     gap = 0.0
     for _ in range(n_probe):
         oe = oracle.env(model_blobs, task_blobs)
+        if user is not None:
+            oe.set_user(user)
         oe.reset_to(int(traj_no), int(step_no))
-        oe.set_state(qpos + eps * rng.randn(len(qpos)), qvel + eps * rng.randn(len(qvel)))
+        sq = (1.0 + np.abs(qpos)) if relative else 1.0
+        sv = (1.0 + np.abs(qvel)) if relative else 1.0
+        oe.set_state(qpos + eps * sq * rng.randn(len(qpos)), qvel + eps * sv * rng.randn(len(qvel)))
         o, _, _ = oe.step(np.asarray(action, dtype=np.float64))
         gap = max(gap, float(np.abs(o - ref_obs).max()))
         oe.close()

@@ -126,8 +126,9 @@ def _batched_vs_oracle(oracle, task, n_steps=None, **kw):
             if not np.allclose(obs[i], o, rtol=2e-3 * (k + 1), atol=2e-3 * (k + 1)):
                 # A control step is discontinuous where a contact switches on or MPR changes the facet it reports: tell that
                 # from a real mismatch by what a 1e-6 perturbation of the start state does to the ORACLE's own result.
-                gap = oracle_step_sensitivity(oracle, blobs(env, int(rows[i]) if len(env._models) > 1 else 0)[0], tb, tr[i], st[i],
-                                              q_pre, v_pre, act[i], o)
+                mno = int(rows[i]) if len(env._models) > 1 else 0
+                gap = oracle_step_sensitivity(oracle, blobs(env, mno)[0], tb, tr[i], st[i], q_pre, v_pre, act[i], o, eps=1e-5,
+                                              n_probe=8, relative=True, user=env._model_user_features[mno])
                 assert np.abs(obs[i] - o).max() <= 3 * gap + 2e-3 * (k + 1), (task, k, i, np.abs(obs[i] - o).max(), gap)
                 alive[i] = False
                 continue

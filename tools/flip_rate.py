@@ -59,7 +59,7 @@ def main():
             env.step((torch.rand((n, eng.action_dim), generator=gen) * 2 - 1).cuda())
         # ---- (A) per-step comparison from identical states ----
         cmp = dict(compared=0, done_gpu=0, done_oracle=0, mismatch=0, mismatch_near_threshold_1e3=0, mismatch_near_threshold_1e4=0)
-        errs = []
+        errs, rels = [], []
         for k in range(a.steps):
             act = torch.rand((n, eng.action_dim), generator=gen) * 2 - 1
             q, v, w = [x.double().cpu().numpy() for x in eng.get_state()]
@@ -72,6 +72,7 @@ def main():
                 cmp["done_gpu"] += int(done[i])
                 cmp["done_oracle"] += int(d)
                 errs.append(float(np.abs(o - obs[i]).max()))
+                rels.append(float((np.abs(o - obs[i]) / (1.0 + np.abs(o))).max()))
                 if d != done[i]:
                     cmp["mismatch"] += 1
                     cmp["mismatch_near_threshold_1e3"] += int(near_threshold(env, o, 1e-3))
@@ -79,6 +80,9 @@ def main():
         errs = np.array(errs)
         cmp["flip_rate_per_env_step"] = cmp["mismatch"] / cmp["compared"]
         cmp["obs_err_p50_p99_max"] = [float(np.percentile(errs, 50)), float(np.percentile(errs, 99)), float(errs.max())]
+        rels = np.array(rels)
+        cmp["obs_err_relative_p50_p99_max"] = [float(np.percentile(rels, 50)), float(np.percentile(rels, 99)), float(rels.max())]
+        cmp["note"] = "relative = max_k |d_k| / (1 + |obs_k|); random U(-1,1) torques drive joint velocities to O(100) rad/s"
         # ---- (B) free-running from the same reset rows ----
         rng = np.random.RandomState(3)
         tr = rng.randint(0, env.trajectories.number_of_trajectories, n).astype(np.int32)
