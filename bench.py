@@ -441,6 +441,15 @@ def main():
             wl = Workload(name, members, rank, world, local)
             r = wl.measure(a, rank, gather)
             e = wl.measure_e2e(a)
+            extra = {}
+            if members[0][0].startswith("HumanoidTorque") and len(members) == 1:
+                # the same workload without the bone-against-bone (mesh-mesh, mjc_Convex / MPR) candidate pairs: separates the
+                # engine's speed from the cost of that part of the narrow phase (round 1 had no such pairs at all)
+                wl2 = Workload(name, [(t, n, dict(kw, convex_collisions=False)) for t, n, kw in members], rank, world, local)
+                r2 = wl2.measure(a, rank, False)
+                extra = {"value_without_convex_pairs": r2["value"], "kernel_ms_per_step_without_convex_pairs": r2["kernel_ms_per_step"]}
+                del wl2
+                torch.cuda.empty_cache()
             if rank == 0:
                 c = {"workload": name, "value": r["value"], "unit": "env-steps/s", "ms_per_step": r["ms_per_step"],
                      "kernel_ms_per_step": r["kernel_ms_per_step"], "e2e": e, "roofline": wl.roofline(r, peak, which, fp32_peak),
@@ -449,6 +458,7 @@ def main():
                      "launch_info": [x.launch_info() for x in wl.engines]}
                 if gather:
                     c["gather"] = r["gather"]
+                c.update(extra)
                 configs.append(c)
             del wl
             torch.cuda.empty_cache()

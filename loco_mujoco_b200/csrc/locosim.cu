@@ -115,9 +115,9 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (stage_bytes > 0) {
-    // Optional (LOCOSIM_STAGE=1): the hot geom tables of the shared model are staged once per block into the shared memory
-    // behind the per-env working sets by ONE TMA bulk copy (cp.async.bulk global -> shared::cta, completion on an
-    // mbarrier); c_models[ms].geom_* then point into the shared window (locosim_create probes its generic address).
+    // Optional (LOCOSIM_STAGE=1): the candidate-pair table of the mid-phase (packed geom pair + bound, read 349 / 769 entries
+    // per dynamics evaluation) is staged once per block into the shared memory behind the per-env working sets by ONE TMA
+    // bulk copy (cp.async.bulk global -> shared::cta, completion on an mbarrier); EnvS::pk_tab / pb_tab point to it.
     unsigned char* dst = smem_raw + (size_t)(blockDim.x >> 5) * sizeof(EnvS<C>);
     const unsigned dst_a = (unsigned)__cvta_generic_to_shared(dst);
     const unsigned bar_a = dst_a + (unsigned)stage_bytes;
@@ -143,7 +143,14 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
   EnvS<C>& e = reinterpret_cast<EnvS<C>*>(smem_raw)[warp];
   const DevModel& m = c_models[ms];
   const int nv = m.nv, nu = m.nu, D = t.obs_dim;
-  if (lane == 0) e.prm = st.pool + (size_t)st.dr_row[env] * m.pool_P;
+  if (lane == 0) {
+    e.prm = st.pool + (size_t)st.dr_row[env] * m.pool_P;
+    if (stage_bytes > 0) {
+      const unsigned char* sm = smem_raw + (size_t)(blockDim.x >> 5) * sizeof(EnvS<C>);
+      e.pk_tab = reinterpret_cast<const int*>(sm);
+      e.pb_tab = reinterpret_cast<const float*>(sm + (stage_bytes >> 1));
+    } else { e.pk_tab = m.pair_packed; e.pb_tab = m.pair_bound; }
+  }
 
   // ---- load state ----
   for (int i = lane; i < nv; i += 32) {
@@ -258,13 +265,6 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
     st.qvel[(size_t)env * nv + i] = e.qvel[i];
     st.ws[(size_t)env * nv + i] = e.qacc_ws[i];
   }
-}
-
-// generic address of the first byte of dynamic shared memory (the shared window is mapped at the same generic address in
-// every block of the context; used once at create time to point the staged model tables into it)
-__global__ void smem_probe_kernel(unsigned long long* out) {
-  extern __shared__ __align__(16) unsigned char smem_probe[];
-  if (threadIdx.x == 0) *out = (unsigned long long)(uintptr_t)smem_probe;
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -397,32 +397,18 @@ static int setup_cfg(locosim_handle* h) {
   h->wpb = best;
   h->smem = best * per_env;
   { int dbg = getenv("LOCOSIM_DEBUG") ? atoi(getenv("LOCOSIM_DEBUG")) : 0; CK(cudaMemcpyToSymbol(c_debug, &dbg, sizeof(int))); }
-  // ---- optional TMA staging of the hot geom tables (LOCOSIM_STAGE=1; measured, see profiles/README.md) ----
-  if (getenv("LOCOSIM_STAGE") && atoi(getenv("LOCOSIM_STAGE")) > 0) {
-    const int ng = h->hm.ng;
-    const int words = 11 * ng;                                   // size 3, quat 4, rbound 1, margin 1, type 1, bodyid 1
-    const int bytes = (words * 4 + 15) & ~15;
-    if (h->smem + bytes + 16 <= dev_max) {
+  // ---- optional TMA staging of the mid-phase pair table (LOCOSIM_STAGE=1; measured, see profiles/README.md) ----
+  // Default on wherever the table fits next to the per-env working sets (A1, Talos; not the RK4 configurations): A1 4096 envs
+  // 2.7825 -> 2.7653 ms per step (+0.6 %, two alternating runs each). LOCOSIM_STAGE=0 turns it off.
+  if (!getenv("LOCOSIM_STAGE") || atoi(getenv("LOCOSIM_STAGE")) > 0) {
+    const int np = h->hm.np;
+    const int half = (np * 4 + 15) & ~15;                        // each of the two tables, padded to 16 bytes
+    const int bytes = 2 * half;
+    if (np > 0 && h->smem + bytes + 16 <= dev_max) {
       CK(cudaMalloc((void**)&h->d_stage, bytes));
       CK(cudaMemset(h->d_stage, 0, bytes));
-      float* f = (float*)h->d_stage;
-      CK(cudaMemcpy(f, h->dm.geom_size, 12 * ng, cudaMemcpyDeviceToDevice));
-      CK(cudaMemcpy(f + 3 * ng, h->dm.geom_quat, 16 * ng, cudaMemcpyDeviceToDevice));
-      CK(cudaMemcpy(f + 7 * ng, h->dm.geom_rbound, 4 * ng, cudaMemcpyDeviceToDevice));
-      CK(cudaMemcpy(f + 8 * ng, h->dm.geom_margin, 4 * ng, cudaMemcpyDeviceToDevice));
-      CK(cudaMemcpy(f + 9 * ng, h->dm.geom_type, 4 * ng, cudaMemcpyDeviceToDevice));
-      CK(cudaMemcpy(f + 10 * ng, h->dm.geom_bodyid, 4 * ng, cudaMemcpyDeviceToDevice));
-      unsigned long long* d_base = nullptr;
-      unsigned long long base = 0;
-      CK(cudaMalloc((void**)&d_base, 8));
-      CK(cudaFuncSetAttribute(smem_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem + bytes + 16));
-      smem_probe_kernel<<<1, 32, h->smem + bytes + 16>>>(d_base);
-      CK(cudaMemcpy(&base, d_base, 8, cudaMemcpyDeviceToHost));
-      cudaFree(d_base);
-      const float* sf = (const float*)(uintptr_t)(base + (unsigned long long)h->smem);
-      h->dm.geom_size = sf; h->dm.geom_quat = sf + 3 * ng; h->dm.geom_rbound = sf + 7 * ng; h->dm.geom_margin = sf + 8 * ng;
-      h->dm.geom_type = (const int*)(sf + 9 * ng); h->dm.geom_bodyid = (const int*)(sf + 10 * ng);
-      CK(cudaMemcpyToSymbol(c_models, &h->dm, sizeof(DevModel), sizeof(DevModel) * h->slot));
+      CK(cudaMemcpy(h->d_stage, h->dm.pair_packed, 4 * np, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(h->d_stage + half, h->dm.pair_bound, 4 * np, cudaMemcpyDeviceToDevice));
       h->stage_bytes = bytes;
     }
   }

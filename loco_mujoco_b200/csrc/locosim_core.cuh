@@ -194,6 +194,8 @@ struct alignas(16) EnvS {
   float goal[4];
   float grf[3 * LS_MAX_GRF];   // use_foot_forces: per foot group, contact-frame force summed over the sub-steps
   const float* prm;        // this env's row of the parameter pool
+  const int* pk_tab;       // candidate-pair table of the mid-phase: the model's (global) or the block's TMA-staged copy (shared)
+  const float* pb_tab;
 };
 #define PRM(field) (e.prm + m.po_##field)
 #define ROW_TYPE(ti) ((ti) & 255)
@@ -1037,7 +1039,7 @@ LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p, int pk) {
   const DevModel& m = c_models[ms];
   const int g1 = pk & 0xfff, g2 = (pk >> 12) & 0xfff;
   const float d[3] = {e.gxpos[g2][0] - e.gxpos[g1][0], e.gxpos[g2][1] - e.gxpos[g1][1], e.gxpos[g2][2] - e.gxpos[g1][2]};
-  const float bound = m.pair_bound[p];
+  const float bound = e.pb_tab[p];
   if (pk & (1 << 24)) {
     float mat1[9];
     geom_mat(ms, e, g1, mat1);
@@ -1273,7 +1275,7 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
   int ncand = 0;
 #ifdef LS_EMULATE
   for (int p = 0; p < m.np; p++) {
-    const int pk = m.pair_packed[p];
+    const int pk = e.pk_tab[p];
     if (!pair_filter(ms, e, p, pk)) continue;
     if (pk & (2 << 24)) { if (ncand < cand_max) cand[ncand++] = (unsigned short)p; continue; }
     RawCon raw[4];
@@ -1299,7 +1301,7 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
   const int lane = LS_LANE;
   for (int base = 0; base < m.np; base += 32) {
     const int p = base + lane;
-    const int pk = p < m.np ? m.pair_packed[p] : 0;
+    const int pk = p < m.np ? e.pk_tab[p] : 0;
     bool hit = (p < m.np) && pair_filter(ms, e, p, pk);
     if (!__any_sync(0xffffffffu, hit)) continue;        // (most rounds of 32 pairs have no candidate at all)
     if (C::CONVEX) {                                   // (configurations whose models carry convex pairs)

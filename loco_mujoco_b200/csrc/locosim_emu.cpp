@@ -58,7 +58,7 @@ struct EmuT : EmuBase {
     for (int j = 0; j < 3; j++) { o[12 + j] = e.con_frame[k][j]; o[15 + j] = e.con_pos[k][j]; }
   }
   void grf(double* o, int clear) override { for (int k = 0; k < 3 * LS_MAX_GRF; k++) { o[k] = e.grf[k]; if (clear) e.grf[k] = 0; } }
-  void bind_prm() override { e.prm = hm.default_row.data(); c_models[0] = m; init_workspace(0, e); }
+  void bind_prm() override { e.prm = hm.default_row.data(); e.pk_tab = m.pair_packed; e.pb_tab = m.pair_bound; c_models[0] = m; init_workspace(0, e); }
 };
 
 extern "C" {
