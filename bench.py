@@ -24,7 +24,14 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("LOCO_MUJOCO_B200_FORCE_BUNDLED", "1")     # the GPU box has no reference checkout
 
 METRIC = "env-steps/sec (batched random-action rollout)"
-ALGO_BYTES = {"UnitreeA1": 633, "HumanoidTorque": 657, "Atlas": 549, "Talos": 621}
+
+
+def algo_bytes(eng):
+    """Algorithmic HBM bytes of one env-step: read qpos, qvel, warmstart (3 nv floats) and
+    the action (nu floats), write the same state back plus obs (D floats), reward (4 B) and done (1 B).
+    UnitreeA1 633, HumanoidTorque 657, Atlas 549, Talos 621."""
+    return 4 * (6 * eng.nq + eng.action_dim + eng.obs_dim + 1) + 1
+
 # Per-launch figures of step_kernel from the committed ncu captures of the CURRENT build (profiles/README.md, round 2):
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum, `--set full`) and FP32 flops per env-step
 # (2*FFMA + FMUL + FADD thread instructions / envs).  None = not captured for that robot.
@@ -323,7 +330,7 @@ class Workload:
     def roofline(self, res, peak, which, fp32_peak):
         """HBM roofline of step_kernel: algorithmic bytes of one launch / its launch time (CUDA events around the step
         on the launching stream); per member for a mixed batch the figures are summed (the kernels overlap)."""
-        algo = sum(ALGO_BYTES[t.split(".")[0]] * n for t, n, _ in self.members)
+        algo = sum(algo_bytes(e) * e.n_envs for e in self.engines)
         dr_extra = sum(4 * e.lib.locosim_param_pool_row_len(e.h) * e.n_envs for e, (_, _, kw) in zip(self.engines, self.members)
                        if kw.get("domain_randomization_config"))
         sec = res["kernel_ms_per_step"] / 1e3
@@ -335,7 +342,7 @@ class Workload:
         r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
              "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/ncu_constants.json)",
              "peak_source": which, "algorithmic_bytes_per_launch": algo + dr_extra,
-             "algorithmic_bytes_per_env_step": {t: ALGO_BYTES[t.split(".")[0]] for t, _, _ in self.members},
+             "algorithmic_bytes_per_env_step": {t: algo_bytes(e) for (t, _, _), e in zip(self.members, self.engines)},
              "note": "compute/latency-bound by design: the state stays in shared memory across the 10 sub-steps (DESIGN.md); "
                      "the HBM fraction is low on purpose, the FP32 figure below is the relevant utilisation"}
         if flops is not None and fp32_peak:

@@ -110,10 +110,11 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
                                                     const float* __restrict__ action, float* __restrict__ obs,
                                                     float* __restrict__ reward, uint8_t* __restrict__ done,
                                                     float* __restrict__ next_obs, int n_envs, int auto_reset,
-                                                    uint64_t seed, int64_t env_off, int sync_substeps, int key_mode,
+                                                    uint64_t seed, int64_t env_off, int sync_substeps, int key_mode_in,
                                                     const unsigned char* __restrict__ stage_src, int stage_bytes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int key_mode = key_mode_in & 0xffff;
   if (stage_bytes > 0) {
     // Optional (LOCOSIM_STAGE=1): the candidate-pair table of the mid-phase (packed geom pair + bound, read 349 / 769 entries
     // per dynamics evaluation) is staged once per block into the shared memory behind the per-env working sets by ONE TMA
@@ -229,9 +230,11 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
     if (bad) cnt[4] += 1;
     {
       int key = e.iter_sum;
+      const int mpr_w = (key_mode >> 8) & 255;           // weight of one MPR run in Newton-iteration units
+      key_mode &= 255;
       if (key_mode == 1) key = (cnt[5] + e.iter_sum + 1) >> 1;
       else if (key_mode == 2) key = e.solver_iter * 8;
-      else if (key_mode == 3) key = e.iter_sum + (e.nefc >> 1) + 4 * min(e.mpr_calls, 64);   // (an MPR run costs about as much as 4 Newton iterations)
+      else if (key_mode == 3) key = e.iter_sum + (e.nefc >> 1) + mpr_w * min(e.mpr_calls, 64);
       else if (key_mode == 4) key = (3 * cnt[5] + e.iter_sum + 2) >> 2;
       else if (key_mode == 5) key = e.iter_sum + 4 * e.solver_iter;
       else if (key_mode == 6) key = e.iter_sum + e.nefc;
@@ -242,6 +245,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
 
   // ---- auto-reset ----
   if (is_done && (auto_reset || bad)) {
+    const int key_reset = (key_mode_in >> 16) ? (key_mode_in >> 16) - 1 : -1;
     int ep = st.episode[env];
     int tr, sp;
     draw_reset(seed, env_off + env, ep, t.n_traj, t.traj_len, &tr, &sp);
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
     if (lane == 0) {
       const int prow = draw_pool_row(seed, env_off + env, ep, st.pool_K);
       st.episode[env] = ep + 1; st.counters[(size_t)env * 8 + 1] += 1;
+      if (key_reset >= 0) st.counters[(size_t)env * 8 + 5] = key_reset;   // regrouping key of a fresh episode (the finished one's says nothing)
       st.dr_row[env] = prow;
       st.cursor[env] = tr * t.traj_len + sp;
       e.prm = st.pool + (size_t)prow * m.pool_P;      // the next episode's model (LS_OBS_PARAM entries of next_obs)
@@ -334,7 +339,7 @@ static bool has_convex_pairs(const HostModel& hm) {
   bind_model(v, hm, hm.ints.data(), hm.reals.data());
   (void)ip;
   for (int p = 0; p < hm.np; p++)
-    if (v.geom_type[v.pair_geom[2 * p + 1]] == LS_GEOM_MESH && v.geom_type[v.pair_geom[2 * p]] >= LS_GEOM_BOX) return true;
+    if (v.pair_packed[p] & (2 << 24)) return true;
   return false;
 }
 template <class C>
@@ -387,6 +392,13 @@ static int setup_cfg(locosim_handle* h) {
   h->key_shift = C::RK4 ? 2 : 0;   // RK4: four solves per sub-step
   if (getenv("LOCOSIM_KEY_SHIFT")) h->key_shift = atoi(getenv("LOCOSIM_KEY_SHIFT"));
   if (getenv("LOCOSIM_KEY_MODE")) h->key_mode = atoi(getenv("LOCOSIM_KEY_MODE"));
+  {
+    // an MPR run holds its lock-step block about as long as `w` Newton iterations; key of a freshly reset env (+1; 0 = keep)
+    int w = 4, kr = 0;
+    if (getenv("LOCOSIM_MPR_WEIGHT")) w = atoi(getenv("LOCOSIM_MPR_WEIGHT"));
+    if (getenv("LOCOSIM_KEY_RESET")) kr = atoi(getenv("LOCOSIM_KEY_RESET")) + 1;
+    h->key_mode = (h->key_mode & 255) | ((w & 255) << 8) | (kr << 16);
+  }
   h->so.sync_iters = 16;    // lock-step group = the whole block
   if (getenv("LOCOSIM_SYNC_ITERS")) { int v = atoi(getenv("LOCOSIM_SYNC_ITERS")); h->so.sync_iters = v == 1 ? 16 : v; }
   if (getenv("LOCOSIM_GROUP")) h->so.sync_iters = atoi(getenv("LOCOSIM_GROUP"));

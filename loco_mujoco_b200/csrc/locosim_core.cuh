@@ -163,6 +163,8 @@ struct alignas(16) EnvS {
   float M[NV][NVP], H[NV][NVP];                              // H: chol(M) during smooth_forces, then the Newton Hessian factor
   // contacts
   int ncon, nunit, nrow, nefc, solver_iter, iter_sum, sep_next, mpr_calls;   // iter_sum / mpr_calls: Newton iterations / MPR runs of this control step
+  int njobs[2], job_par, job_head;   // convex jobs this env published for the block (collision(); double-buffered by call parity);
+                                     // job_head: head of the block's job queue (env 0 of the block only)
   float con_dist[MAXCON], con_pos[MAXCON][3], con_frame[MAXCON][9], con_fri[MAXCON][5], con_imp[MAXCON], con_K[MAXCON],
       con_B[MAXCON], con_incl[MAXCON], con_mu[MAXCON];
   int con_dim[MAXCON], con_g1[MAXCON], con_g2[MAXCON], con_row[MAXCON];
@@ -302,7 +304,7 @@ LS_FN void init_workspace(const int ms, EnvS<C>& e) {
     (&e.M[0][0])[idx] = (i == j && i >= m.nv) ? 1.0f : 0.0f;
   }
   PAR_FOR(k, EnvS<C>::NSEP) e.sep_pair[k] = -1;
-  LANE0 { e.sep_next = 0; e.mpr_calls = 0; }
+  LANE0 { e.sep_next = 0; e.mpr_calls = 0; e.job_par = 0; e.job_head = 0; e.njobs[0] = e.njobs[1] = 0; }
   // entries [nv, NV) of the solver vectors are never written by the phases (they loop to nv): keep them 0
   PAR_FOR(i, EnvS<C>::NV) {
     if (i >= m.nv) {
@@ -746,6 +748,37 @@ LS_FN int sphere_capsule(RawCon* c, float margin, const float* pos1, float r1, c
   float p[3] = {pos2[0] + axis[0] * x, pos2[1] + axis[1] * x, pos2[2] + axis[2] * x};
   return sphere_sphere_raw(c, margin, pos1, r1, p, size2[0]);
 }
+// mjc_SphereBox: sphere g1 against box g2 (restated in oracle/locosim_ref.c sphere_box)
+LS_FN int sphere_box(RawCon* c, float margin, const float* pos1, float r, const float* pos2, const float* mat2,
+                     const float* size2) {
+  const float tmp[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]};
+  float cen[3], cl[3], d[3], nb[3] = {0, 0, 0}, pl[3];
+  mulmatTvec3(cen, mat2, tmp);
+  for (int k = 0; k < 3; k++) { cl[k] = fmaxf(-size2[k], fminf(size2[k], cen[k])); d[k] = cen[k] - cl[k]; }
+  const float dist = sqrtf(dot3(d, d));
+  if (dist - r > margin) return 0;
+  if (dist <= LS_MINVAL) {
+    float closest = 2 * (size2[0] + size2[1] + size2[2]);
+    int kk = 0;
+    for (int i = 0; i < 6; i++) {
+      const float f = fabsf(((i & 1) ? 1.0f : -1.0f) * size2[i >> 1] - cen[i >> 1]);
+      if (closest > f) { closest = f; kk = i; }
+    }
+    for (int k = 0; k < 3; k++) nb[k] = (k == (kk >> 1)) ? ((kk & 1) ? 1.0f : -1.0f) : 0.0f;
+    for (int k = 0; k < 3; k++) pl[k] = cen[k] + nb[k] * 0.5f * (closest - r);
+    c->dist = -closest - r;
+  } else {
+    const float inv = 1.0f / dist;
+    for (int k = 0; k < 3; k++) { nb[k] = d[k] * inv; pl[k] = cl[k] + nb[k] * 0.5f * (dist - r); }
+    c->dist = dist - r;
+  }
+  float nw[3], pw[3];
+  mulmatvec3(nw, mat2, nb);
+  mulmatvec3(pw, mat2, pl);
+  for (int k = 0; k < 3; k++) { c->frame[k] = -nw[k]; c->frame[3 + k] = 0; c->pos[k] = pos2[k] + pw[k]; }
+  return 1;
+}
+
 LS_FN int capsule_capsule(RawCon* c, float margin, const float* pos1, const float* mat1, const float* size1,
                            const float* pos2, const float* mat2, const float* size2) {
   float a1[3] = {mat1[2], mat1[5], mat1[8]}, a2[3] = {mat2[2], mat2[5], mat2[8]};
@@ -785,7 +818,7 @@ LS_FN int capsule_capsule(RawCon* c, float margin, const float* pos1, const floa
 
 
 // ----------------------------------------------------------------------------------------------------------
-// General convex pairs (mesh-mesh, box-mesh): mjc_Convex = libccd's Minkowski Portal Refinement, restated in
+// General convex pairs (sphere | capsule | cylinder | box | mesh against cylinder | box | mesh): mjc_Convex = libccd's Minkowski Portal Refinement, restated in
 // oracle/locosim_ref.c (ccd_mpr_penetration) where it is pinned by the reference goldens. Here: fp32, ONE pair at a
 // time by the whole warp -- the control flow is warp-uniform, the mesh support function (argmax of dir . vertex over
 // the hull vertices) is the parallel part: lanes stride over the vertices, then a warp argmax.
@@ -799,7 +832,10 @@ LS_FN int capsule_capsule(RawCon* c, float margin, const float* pos1, const floa
 static long g_mpr_supports = 0, g_mpr_calls = 0, g_mpr_candidates = 0, g_forward_evals = 0, g_sep_found = 0, g_sep_ok = 0, g_mpr_nohit = 0, g_obb_pass = 0;
 #endif
 struct MprSup { float v[3], v1[3], v2[3]; };
-struct MprGeom { int type, vnum; const float* verts; float pos[3], mat[9], size[3], margin; };
+// world = 1: `verts` are WORLD-space points (pos + mat * vertex; the 8 corners of a box count as a mesh) staged in shared
+// memory by convex_job, so a support call is a plain argmax of dir . vertex without any frame change; world = 0: analytic
+// smooth geoms (sphere / capsule / cylinder) and meshes too large to stage (scanned in their own frame from global memory).
+struct MprGeom { int type, vnum, world; const float* verts; float pos[3], mat[9], size[3], margin; };
 LS_DEV bool mpr_is_zero(float x) { return fabsf(x) < MPR_EPS; }
 LS_DEV bool mpr_eq(float a, float b) {
   float ab = fabsf(a - b);
@@ -810,70 +846,85 @@ LS_DEV bool mpr_eq(float a, float b) {
 LS_DEV void mpr_normalize(float* d) { const float inv = rsqrtf(dot3(d, d)); d[0] *= inv; d[1] *= inv; d[2] *= inv; }
 
 // Per-warp MPR scratch in shared memory (it lives in the contact-Jacobian storage, free until make_constraint): the two
-// geoms and the result of the last support call. Keeping them in shared memory (not in structs handed by reference to
-// __noinline__ functions, which the ABI places in local memory) and the portal in registers is what makes a lone warp's
-// MPR call fast: its lock-step block waits for it.
-struct MprScratch { MprGeom g[2]; float out[12]; };
+// geoms. The portal and every support point stay in registers; mpr_support is inlined into its callers (a lone warp's MPR
+// call is pure latency: its lock-step block waits for it).
+struct MprScratch { MprGeom g[2]; };
 
-// mjccd_support of geom g (inflated by margin) in the unit world direction (dx, dy, dz); all lanes compute the same point
-LS_DEV void mpr_support_geom(const MprGeom& g, float dx, float dy, float dz, float* res) {
-  const float dir[3] = {dx, dy, dz};
-  float ld[3], r[3] = {0, 0, 0};
-  mulmatTvec3(ld, g.mat, dir);
-  if (g.type == LS_GEOM_MESH) {
+// mjccd_support of geom g (inflated by margin) in the unit world direction d, computed by the lanes [l0, l0 + nl) of the
+// warp (GPU: one half-warp per geom, both geoms at once; emulation: one serial lane). All participating lanes return the
+// same point. The first maximum of the vertex scan wins ties, like a serial scan.
+LS_DEV void mpr_support_geom(const MprGeom& g, const float* d, float* res, int l0, int nl, unsigned mask) {
+  float r[3] = {0, 0, 0};
+  if (g.type == LS_GEOM_MESH || g.world) {
+    float q[3] = {d[0], d[1], d[2]};
+    if (!g.world) mulmatTvec3(q, g.mat, d);
     const float* v = g.verts;
     float mx = -3.0e38f;
     int best = 0x7fffffff;
 #ifdef LS_EMULATE
     for (int i = 0; i < g.vnum; i++) {
-      const float d = ld[0] * v[3 * i] + ld[1] * v[3 * i + 1] + ld[2] * v[3 * i + 2];
-      if (d > mx) { mx = d; best = i; }
+      const float t = q[0] * v[3 * i] + q[1] * v[3 * i + 1] + q[2] * v[3 * i + 2];
+      if (t > mx) { mx = t; best = i; }
     }
 #else
     const int n = g.vnum;
-#pragma unroll 4
-    for (int i = LS_LANE; i < n; i += 32) {
-      const float d = ld[0] * v[3 * i] + ld[1] * v[3 * i + 1] + ld[2] * v[3 * i + 2];
-      if (d > mx) { mx = d; best = i; }
+#pragma unroll 2
+    for (int i = LS_LANE - l0; i < n; i += nl) {
+      const float t = q[0] * v[3 * i] + q[1] * v[3 * i + 1] + q[2] * v[3 * i + 2];
+      if (t > mx) { mx = t; best = i; }
     }
-    // warp argmax in two redux instructions instead of a 5-round shuffle butterfly (this sits on the critical path of a
-    // lone warp): max of the order-preserving integer image of the dot product, then the smallest index among the
-    // lanes that hold it (= the first maximum of a serial scan)
+    // argmax in two redux instructions: max of the order-preserving integer image of the dot product, then the smallest
+    // index among the lanes that hold it
     unsigned key = __float_as_uint(mx);
     key = (key & 0x80000000u) ? ~key : (key | 0x80000000u);
-    const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
-    best = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (unsigned)best : 0x7fffffffu);
+    const unsigned kmax = __reduce_max_sync(mask, key);
+    best = (int)__reduce_min_sync(mask, key == kmax ? (unsigned)best : 0x7fffffffu);
 #endif
     r[0] = v[3 * best]; r[1] = v[3 * best + 1]; r[2] = v[3 * best + 2];
-  } else if (g.type == LS_GEOM_BOX) {
-    for (int k = 0; k < 3; k++) r[k] = ld[k] >= 0 ? g.size[k] : -g.size[k];
+    if (g.world) { for (int k = 0; k < 3; k++) res[k] = r[k] + d[k] * g.margin; return; }
+  } else {
+    float ld[3];
+    mulmatTvec3(ld, g.mat, d);
+    if (g.type == LS_GEOM_BOX) {
+      for (int k = 0; k < 3; k++) r[k] = ld[k] >= 0 ? g.size[k] : -g.size[k];
+    } else if (g.type == LS_GEOM_SPHERE) {
+      for (int k = 0; k < 3; k++) r[k] = ld[k] * g.size[0];
+    } else if (g.type == LS_GEOM_CAPSULE) {
+      for (int k = 0; k < 3; k++) r[k] = ld[k] * g.size[0];
+      r[2] += ld[2] >= 0 ? g.size[1] : -g.size[1];
+    } else if (g.type == LS_GEOM_CYLINDER) {
+      const float t = sqrtf(ld[0] * ld[0] + ld[1] * ld[1]);
+      if (t > LS_MINVAL) { const float inv = g.size[0] / t; r[0] = ld[0] * inv; r[1] = ld[1] * inv; }
+      r[2] = ld[2] >= 0 ? g.size[1] : -g.size[1];
+    }
   }
   mulmatvec3(res, g.mat, r);
-  for (int k = 0; k < 3; k++) res[k] += g.pos[k] + dir[k] * g.margin;
+  for (int k = 0; k < 3; k++) res[k] += g.pos[k] + d[k] * g.margin;
 }
-// support point of the Minkowski difference: sc->out = {v = v1 - v2, v1, v2}. ONE out-of-line copy (the vertex scan is
-// the bulk of the MPR code and has 6 call sites).
-LS_FN void mpr_support_call(MprScratch* sc, float dx, float dy, float dz) {
-  float v1[3], v2[3];
-  mpr_support_geom(sc->g[0], dx, dy, dz, v1);
-  mpr_support_geom(sc->g[1], -dx, -dy, -dz, v2);
-  LANE0 {
-    for (int k = 0; k < 3; k++) { sc->out[k] = v1[k] - v2[k]; sc->out[3 + k] = v1[k]; sc->out[6 + k] = v2[k]; }
-  }
-  SYNC();
-#if !defined(LS_EMULATE)
-  if ((c_debug & 8) && LS_LANE == 0) atomicAdd(&g_dbg[1], 1ULL);
-#else
+// support point of the Minkowski difference in direction dir: v = v1 - v2
+LS_DEV void mpr_support(const MprScratch* sc, const float* dir, MprSup& sp) {
+#ifdef LS_EMULATE
+  const float nd[3] = {-dir[0], -dir[1], -dir[2]};
+  mpr_support_geom(sc->g[0], dir, sp.v1, 0, 1, 0u);
+  mpr_support_geom(sc->g[1], nd, sp.v2, 0, 1, 0u);
   g_mpr_supports++;
 #if defined(LS_TRACE)
-  printf("    [f32] dir %.6f %.6f %.6f -> v %.7f %.7f %.7f\n", dx, dy, dz, sc->out[0], sc->out[1], sc->out[2]);
+  printf("    [f32] dir %.6f %.6f %.6f -> v %.7f %.7f %.7f\n", dir[0], dir[1], dir[2], sp.v1[0] - sp.v2[0], sp.v1[1] - sp.v2[1], sp.v1[2] - sp.v2[2]);
 #endif
+#else
+  // lanes 0-15: geom 1 along +dir, lanes 16-31: geom 2 along -dir, at the same time; one shuffle round exchanges the points
+  const int half = LS_LANE >> 4;
+  const float sg = half ? -1.0f : 1.0f;
+  const float d[3] = {sg * dir[0], sg * dir[1], sg * dir[2]};
+  float r[3];
+  mpr_support_geom(sc->g[half], d, r, half << 4, 16, half ? 0xffff0000u : 0x0000ffffu);
+  for (int k = 0; k < 3; k++) {
+    sp.v1[k] = __shfl_sync(0xffffffffu, r[k], 0);
+    sp.v2[k] = __shfl_sync(0xffffffffu, r[k], 16);
+  }
+  if ((c_debug & 8) && LS_LANE == 0) atomicAdd(&g_dbg[1], 1ULL);
 #endif
-}
-LS_DEV void mpr_support(MprScratch* sc, const float* dir, MprSup& sp) {
-  mpr_support_call(sc, dir[0], dir[1], dir[2]);
-  for (int k = 0; k < 3; k++) { sp.v[k] = sc->out[k]; sp.v1[k] = sc->out[3 + k]; sp.v2[k] = sc->out[6 + k]; }
-  SYNC();                                    // (everybody has read `out` before the next call rewrites it)
+  for (int k = 0; k < 3; k++) sp.v[k] = sp.v1[k] - sp.v2[k];
 }
 LS_DEV void mpr_portal_dir(const MprSup* p, float* dir) {
   float a[3], b[3];
@@ -895,37 +946,55 @@ LS_DEV void mpr_expand_portal(MprSup* p, const MprSup& v4) {
     if (dot3(p[3].v, v4v0) > 0) p[2] = v4; else p[1] = v4;
   }
 }
-LS_DEV float mpr_point_seg_dist2(const float* x0, const float* b, float* wit) {      // distance of the origin
-  float d[3] = {b[0] - x0[0], b[1] - x0[1], b[2] - x0[2]};
-  const float t = -dot3(x0, d) / dot3(d, d);
-  if (t < 0 || mpr_is_zero(t)) { wit[0] = x0[0]; wit[1] = x0[1]; wit[2] = x0[2]; }
-  else if (t > 1 || mpr_eq(t, 1.0f)) { wit[0] = b[0]; wit[1] = b[1]; wit[2] = b[2]; }
-  else for (int k = 0; k < 3; k++) wit[k] = d[k] * t + x0[k];
-  return dot3(wit, wit);
+// Distance of the origin from the final portal triangle (ccdVec3PointTriDist2), once per MPR call, in DOUBLE precision on
+// the fp32 portal points: the refined portal of a curved geom (cylinder rim) or of a finely tessellated hull is often a
+// sliver (corner angle < 0.1 deg); wv - r^2 then cancels below fp32 resolution, the triangle would be classified as
+// degenerate and the closest point taken on an edge instead of the face: penetration normals up to tens of degrees off
+// (measured against the fp64 oracle on UnitreeH1's hip cylinder / mesh pairs). With the fp64 evaluation the classification
+// is libccd's own (same epsilons as oracle/locosim_ref.c).
+#define MPR_DEPS 2.220446049250313e-16
+LS_DEV bool mprd_is_zero(double x) { return fabs(x) < MPR_DEPS; }
+LS_DEV bool mprd_eq(double a, double b) {
+  double ab = fabs(a - b);
+  if (ab < MPR_DEPS) return true;
+  a = fabs(a); b = fabs(b);
+  return b > a ? ab < MPR_DEPS * b : ab < MPR_DEPS * a;
 }
-LS_DEV float mpr_point_tri_dist2(const float* x0, const float* B, const float* C, float* wit) {
-  float d1[3], d2[3];
-  for (int k = 0; k < 3; k++) { d1[k] = B[k] - x0[k]; d2[k] = C[k] - x0[k]; }
-  const float v = dot3(d1, d1), w = dot3(d2, d2), pp = dot3(x0, d1), q = dot3(x0, d2), r = dot3(d1, d2);
-  const float d = w * v - r * r;
-  float s, t, dist;
-  // (libccd tests |d| < DBL_EPSILON; the portal triangle near the origin has edges of ~1e-3 m, so in fp32 the absolute
-  //  test would call every such triangle degenerate: relative test, sin^2 of the corner angle below fp32 resolution)
-  if (!(d > 1e-6f * w * v)) s = t = -1.0f;
+LS_DEV double mprd_point_seg_dist2(const double* x0, const double* b, double* wit) {      // distance of the origin
+  const double d[3] = {b[0] - x0[0], b[1] - x0[1], b[2] - x0[2]};
+  const double t = -(x0[0] * d[0] + x0[1] * d[1] + x0[2] * d[2]) / (d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (t < 0 || mprd_is_zero(t)) { wit[0] = x0[0]; wit[1] = x0[1]; wit[2] = x0[2]; }
+  else if (t > 1 || mprd_eq(t, 1.0)) { wit[0] = b[0]; wit[1] = b[1]; wit[2] = b[2]; }
+  else for (int k = 0; k < 3; k++) wit[k] = d[k] * t + x0[k];
+  return wit[0] * wit[0] + wit[1] * wit[1] + wit[2] * wit[2];
+}
+LS_DEV float mpr_point_tri_dist2(const float* x0f, const float* Bf, const float* Cf, float* witf) {
+  double x0[3], B[3], C[3], d1[3], d2[3], wit[3];
+  for (int k = 0; k < 3; k++) { x0[k] = x0f[k]; B[k] = Bf[k]; C[k] = Cf[k]; d1[k] = B[k] - x0[k]; d2[k] = C[k] - x0[k]; }
+  const double v = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], w = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2];
+  const double pp = x0[0] * d1[0] + x0[1] * d1[1] + x0[2] * d1[2], q = x0[0] * d2[0] + x0[1] * d2[1] + x0[2] * d2[2];
+  const double r = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
+  const double d = w * v - r * r;
+  double s, t, dist;
+  if (mprd_is_zero(d)) s = t = -1.0;
   else { s = (q * r - w * pp) / d; t = (-s * r - q) / w; }
-  if ((mpr_is_zero(s) || s > 0) && (mpr_eq(s, 1.0f) || s < 1) && (mpr_is_zero(t) || t > 0) && (mpr_eq(t, 1.0f) || t < 1) &&
-      (mpr_eq(t + s, 1.0f) || t + s < 1)) {
+  if ((mprd_is_zero(s) || s > 0) && (mprd_eq(s, 1.0) || s < 1) && (mprd_is_zero(t) || t > 0) && (mprd_eq(t, 1.0) || t < 1) &&
+      (mprd_eq(t + s, 1.0) || t + s < 1)) {
     for (int k = 0; k < 3; k++) wit[k] = x0[k] + d1[k] * s + d2[k] * t;
-    dist = dot3(wit, wit);
+    dist = wit[0] * wit[0] + wit[1] * wit[1] + wit[2] * wit[2];
   } else {
-    float w2[3], dist2;
-    dist = mpr_point_seg_dist2(x0, B, wit);
-    dist2 = mpr_point_seg_dist2(x0, C, w2);
+    double w2[3], dist2;
+    dist = mprd_point_seg_dist2(x0, B, wit);
+    dist2 = mprd_point_seg_dist2(x0, C, w2);
     if (dist2 < dist) { dist = dist2; wit[0] = w2[0]; wit[1] = w2[1]; wit[2] = w2[2]; }
-    dist2 = mpr_point_seg_dist2(B, C, w2);
+    dist2 = mprd_point_seg_dist2(B, C, w2);
     if (dist2 < dist) { dist = dist2; wit[0] = w2[0]; wit[1] = w2[1]; wit[2] = w2[2]; }
   }
-  return dist;
+  // the direction is normalised in double as well (|wit| can be 1e-5: keep its relative precision), the depth returned as is
+  const double n = sqrt(dist);
+  if (n > 0) { witf[0] = (float)(wit[0] / n); witf[1] = (float)(wit[1] / n); witf[2] = (float)(wit[2] / n); }
+  else { witf[0] = witf[1] = witf[2] = 0.0f; }
+  return (float)dist;
 }
 LS_DEV void mpr_find_pos(const MprSup* p, float* pos) {
   float dir[3], vec[3], b[4], sum;
@@ -950,7 +1019,7 @@ LS_DEV void mpr_find_pos(const MprSup* p, float* pos) {
 // ccdMPRPenetration: true and (depth, dir, pos) if the inflated geoms intersect
 // returns false if the geoms do not intersect; `sep` then holds the last direction tested (a separating direction whenever
 // the search stopped because a support point did not reach past the origin)
-LS_FN bool mpr_penetration(MprScratch* sc, float* depth, float* pdir, float* pos, float* sep) {
+LS_FN bool mpr_penetration(const MprScratch* sc, float* depth, float* pdir, float* pos, float* sep) {
   const MprGeom& o1 = sc->g[0];
   const MprGeom& o2 = sc->g[1];
   MprSup p[4], v4;
@@ -1023,9 +1092,8 @@ LS_FN bool mpr_penetration(MprScratch* sc, float* depth, float* pdir, float* pos
     if ((c_debug & 8) && LS_LANE == 0 && !(dir[0] == dir[0])) atomicAdd(&g_dbg[4], 1ULL);
 #endif
     if (mpr_reach_tolerance(p, v4, dir) || it > MPR_MAXIT) {
-      *depth = sqrtf(mpr_point_tri_dist2(p[1].v, p[2].v, p[3].v, pdir));
+      *depth = sqrtf(mpr_point_tri_dist2(p[1].v, p[2].v, p[3].v, pdir));      // (pdir comes back normalised)
       if (mpr_is_zero(*depth)) pdir[0] = pdir[1] = pdir[2] = 0;
-      else mpr_normalize(pdir);
       mpr_find_pos(p, pos);
       return true;
     }
@@ -1049,7 +1117,16 @@ LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p, int pk) {
   return dot3(d, d) <= bound * bound;
 }
 
-// second filter of a convex pair (box | mesh vs mesh) that passed the bounding spheres
+// half extents of the geom's oriented bounding box in its own frame, inflated by mg (box / mesh: geom_size; sphere:
+// r; capsule: (r, r, r + half length); cylinder: (r, r, half length))
+LS_DEV void geom_halfext(int type, const float* size, float mg, float* h) {
+  if (type == LS_GEOM_SPHERE) { h[0] = h[1] = h[2] = size[0] + mg; }
+  else if (type == LS_GEOM_CAPSULE) { h[0] = h[1] = size[0] + mg; h[2] = size[0] + size[1] + mg; }
+  else if (type == LS_GEOM_CYLINDER) { h[0] = h[1] = size[0] + mg; h[2] = size[1] + mg; }
+  else { h[0] = size[0] + mg; h[1] = size[1] + mg; h[2] = size[2] + mg; }
+}
+
+// second filter of a general convex pair that passed the bounding spheres
 template <class C>
 LS_FN bool convex_obb_filter(const int ms, const EnvS<C>& e, int p) {
   const DevModel& m = c_models[ms];
@@ -1066,8 +1143,9 @@ LS_FN bool convex_obb_filter(const int ms, const EnvS<C>& e, int p) {
   geom_mat(ms, e, g1, RA);
   geom_mat(ms, e, g2, RB);
   const float mg = 0.5f * fmaxf(m.geom_margin[g1], m.geom_margin[g2]) + 1e-6f;
-  const float a[3] = {m.geom_size[3 * g1] + mg, m.geom_size[3 * g1 + 1] + mg, m.geom_size[3 * g1 + 2] + mg};
-  const float b[3] = {m.geom_size[3 * g2] + mg, m.geom_size[3 * g2 + 1] + mg, m.geom_size[3 * g2 + 2] + mg};
+  float a[3], b[3];
+  geom_halfext(m.geom_type[g1], m.geom_size + 3 * g1, mg, a);
+  geom_halfext(m.geom_type[g2], m.geom_size + 3 * g2, mg, b);
   float R[3][3], AR[3][3], t[3];
   for (int i = 0; i < 3; i++) {
     t[i] = RA[i] * d[0] + RA[3 + i] * d[1] + RA[6 + i] * d[2];                     // d in A's frame
@@ -1090,85 +1168,6 @@ LS_FN bool convex_obb_filter(const int ms, const EnvS<C>& e, int p) {
     }
   }
   return true;
-}
-
-// warp-cooperative narrow phase of one convex pair (mjc_Convex): at most one contact
-template <class C>
-LS_FN int convex_narrow(const int ms, EnvS<C>& e, int p, RawCon* raw) {
-  const DevModel& m = c_models[ms];
-  const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
-  const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
-  // scratch + staged vertices live in the contact-Jacobian storage (nobody uses it before make_constraint)
-  constexpr int SCR = (int)((sizeof(MprScratch) + 15) / 16 * 4);                  // floats taken by the scratch block
-  MprScratch* sc = reinterpret_cast<MprScratch*>(&e.J[0][0]);
-  float* buf = &e.J[0][0] + SCR;
-  const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
-  const int n1 = t1 == LS_GEOM_MESH ? 3 * m.geom_meshnum[g1] : 0, n2 = t2 == LS_GEOM_MESH ? 3 * m.geom_meshnum[g2] : 0;
-  const float* s1 = m.mesh_vert + 3 * m.geom_meshadr[g1];
-  const float* s2 = m.mesh_vert + 3 * m.geom_meshadr[g2];
-  // An MPR call scans the two vertex sets ~10 times each, one after the other: the vertices of both meshes are copied once
-  // (coalesced, all loads in flight) into shared memory whenever they fit (~400 vertices; larger pairs scan global memory)
-  const bool staged = n1 + n2 <= EnvS<C>::MAXROW * EnvS<C>::JS - SCR;
-  if (staged) {
-#ifdef LS_EMULATE
-    for (int i = 0; i < n1; i++) buf[i] = s1[i];
-    for (int i = 0; i < n2; i++) buf[n1 + i] = s2[i];
-#else
-#pragma unroll 4
-    for (int i = LS_LANE; i < n1; i += 32) buf[i] = s1[i];
-#pragma unroll 4
-    for (int i = LS_LANE; i < n2; i += 32) buf[n1 + i] = s2[i];
-#endif
-  }
-  {
-    float m1[9], m2[9];
-    geom_mat(ms, e, g1, m1);
-    geom_mat(ms, e, g2, m2);
-    LANE0 {
-      MprGeom& a = sc->g[0];
-      MprGeom& b = sc->g[1];
-      a.type = t1; a.vnum = m.geom_meshnum[g1]; a.margin = 0.5f * margin; a.verts = staged ? buf : s1;
-      b.type = t2; b.vnum = m.geom_meshnum[g2]; b.margin = 0.5f * margin; b.verts = staged ? buf + n1 : s2;
-      for (int k = 0; k < 3; k++) {
-        a.pos[k] = e.gxpos[g1][k]; b.pos[k] = e.gxpos[g2][k];
-        a.size[k] = m.geom_size[3 * g1 + k]; b.size[k] = m.geom_size[3 * g2 + k];
-      }
-      for (int k = 0; k < 9; k++) { a.mat[k] = m1[k]; b.mat[k] = m2[k]; }
-    }
-  }
-  SYNC();
-  float depth, dir[3], pos[3], sep[3] = {0, 0, 0};
-  // A direction that separated this pair in an earlier evaluation of the control step is tried first (ONE support pair;
-  // strict separation of the inflated geoms along it means MPR would not report a contact either); if it fails the full
-  // MPR runs and its last test direction refreshes the cache.
-  int slot = -1;
-  for (int k = 0; k < EnvS<C>::NSEP; k++) if (e.sep_pair[k] == p) slot = k;
-  if (slot >= 0 && !(c_debug & 16)) {
-    MprSup sp;
-    const float cd[3] = {e.sep_dir[slot][0], e.sep_dir[slot][1], e.sep_dir[slot][2]};
-    mpr_support(sc, cd, sp);
-    if (dot3(sp.v, cd) < -1e-7f) return 0;
-  }
-#if defined(LS_EMULATE)
-  g_mpr_calls++;
-#else
-  if ((c_debug & 8) && LS_LANE == 0) atomicAdd(&g_dbg[0], 1ULL);
-#endif
-  LANE0 { e.mpr_calls += 1; }
-  if (!mpr_penetration(sc, &depth, dir, pos, sep)) {
-    if (slot < 0) { slot = e.sep_next & (EnvS<C>::NSEP - 1); }
-    SYNC();
-    LANE0 {
-      if (e.sep_pair[slot] != p) e.sep_next = e.sep_next + 1;
-      e.sep_pair[slot] = p; e.sep_dir[slot][0] = sep[0]; e.sep_dir[slot][1] = sep[1]; e.sep_dir[slot][2] = sep[2];
-    }
-    SYNC();
-    return 0;
-  }
-  if (dir[0] == 0.0f && dir[1] == 0.0f && dir[2] == 0.0f) return 0;      // contact found but normal undefined
-  raw->dist = margin - depth;
-  for (int k = 0; k < 3; k++) { raw->pos[k] = pos[k]; raw->frame[k] = dir[k]; raw->frame[3 + k] = 0; }
-  return 1;
 }
 
 // contact parameters (mj_contactParam), frame completion (mju_makeFrame) and storage of one raw contact
@@ -1227,6 +1226,140 @@ LS_FN void fill_contact(const int ms, EnvS<C>& e, const int ci, int g1, int g2, 
   }
 }
 
+// warp-cooperative narrow phase of one convex pair (mjc_Convex): at most one contact.
+// The pair belongs to env `o` (geom frames, separating-direction cache: read only); the executing warp's own env `e` only
+// lends its contact-Jacobian storage as scratch. On the GPU the warps of a block SHARE these jobs (collision()): a lone
+// warp running several MPR calls while its lock-step block waits was the largest cost of the bone-bone pairs.
+// Result record res[8]: res[7] = 0 nothing to do (the cached direction still separates the pair, no MPR run),
+//                                1 contact: res[0] dist, res[1..3] position, res[4..6] normal,
+//                                2 MPR ran, no contact; res[1..3] = the last direction tested (refreshes o's cache),
+//                                3 MPR ran, touching contact without a normal (ignored).
+#define LS_MAXJOB 32
+template <class C>
+LS_FN void convex_job(const int ms, const EnvS<C>& o, EnvS<C>& e, int p, float* res) {
+  const DevModel& m = c_models[ms];
+  const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+  const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
+  // scratch + staged vertices live in the contact-Jacobian storage (nobody uses it before make_constraint)
+  constexpr int SCR = (int)((sizeof(MprScratch) + 15) / 16 * 4);                  // floats taken by the scratch block
+  MprScratch* sc = reinterpret_cast<MprScratch*>(&e.J[0][0]);
+  float* buf = &e.J[0][0] + SCR;
+  const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+  // vertex sets: a mesh's hull vertices, a box's 8 corners (corner 0 = (+,+,+): ties resolve like sign(0) = +)
+  const int n1 = t1 == LS_GEOM_MESH ? m.geom_meshnum[g1] : (t1 == LS_GEOM_BOX ? 8 : 0);
+  const int n2 = t2 == LS_GEOM_MESH ? m.geom_meshnum[g2] : (t2 == LS_GEOM_BOX ? 8 : 0);
+  const float* s1 = m.mesh_vert + 3 * m.geom_meshadr[g1];
+  const float* s2 = m.mesh_vert + 3 * m.geom_meshadr[g2];
+  // An MPR call scans the two vertex sets ~10 times each: whenever they fit (~400 vertices) the vertices of both geoms are
+  // written ONCE, already in world coordinates, into shared memory (all loads in flight, parallel over the vertices), so
+  // the support calls on the serial critical path are a bare argmax; larger pairs scan global memory in the mesh frame.
+  const bool staged = 3 * (n1 + n2) <= EnvS<C>::MAXROW * EnvS<C>::JS - SCR;
+  {
+    float m1[9], m2[9];
+    geom_mat(ms, o, g1, m1);
+    geom_mat(ms, o, g2, m2);
+    if (staged) {
+      PAR_FOR(i, n1 + n2) {
+        const bool second = i >= n1;
+        const int j = second ? i - n1 : i;
+        const int ty = second ? t2 : t1;
+        const float* mm = second ? m2 : m1;
+        const float* gp = second ? o.gxpos[g2] : o.gxpos[g1];
+        float v[3];
+        if (ty == LS_GEOM_MESH) { const float* sv = (second ? s2 : s1) + 3 * j; v[0] = sv[0]; v[1] = sv[1]; v[2] = sv[2]; }
+        else {
+          const float* sz = m.geom_size + 3 * (second ? g2 : g1);
+          v[0] = (j & 1) ? -sz[0] : sz[0]; v[1] = (j & 2) ? -sz[1] : sz[1]; v[2] = (j & 4) ? -sz[2] : sz[2];
+        }
+        float w[3];
+        mulmatvec3(w, mm, v);
+        buf[3 * i] = w[0] + gp[0]; buf[3 * i + 1] = w[1] + gp[1]; buf[3 * i + 2] = w[2] + gp[2];
+      }
+    }
+    LANE0 {
+      MprGeom& a = sc->g[0];
+      MprGeom& b = sc->g[1];
+      a.type = t1; a.vnum = n1; a.margin = 0.5f * margin; a.world = (staged && n1 > 0) ? 1 : 0; a.verts = a.world ? buf : s1;
+      b.type = t2; b.vnum = n2; b.margin = 0.5f * margin; b.world = (staged && n2 > 0) ? 1 : 0; b.verts = b.world ? buf + 3 * n1 : s2;
+      for (int k = 0; k < 3; k++) {
+        a.pos[k] = o.gxpos[g1][k]; b.pos[k] = o.gxpos[g2][k];
+        a.size[k] = m.geom_size[3 * g1 + k]; b.size[k] = m.geom_size[3 * g2 + k];
+      }
+      for (int k = 0; k < 9; k++) { a.mat[k] = m1[k]; b.mat[k] = m2[k]; }
+    }
+  }
+  SYNC();
+  float depth, dir[3], pos[3], sep[3] = {0, 0, 0};
+  // A direction that separated this pair in an earlier evaluation of the control step is tried first (ONE support pair;
+  // strict separation of the inflated geoms along it means MPR would not report a contact either); if it fails the full
+  // MPR runs and its last test direction refreshes the cache (applied by the owner, in job order).
+  int slot = -1;
+  for (int k = 0; k < EnvS<C>::NSEP; k++) if (o.sep_pair[k] == p) slot = k;
+  float code = 0.0f, r[7] = {0, 0, 0, 0, 0, 0, 0};
+  bool run = true;
+  if (slot >= 0 && !(c_debug & 16)) {
+    MprSup sp;
+    const float cd[3] = {o.sep_dir[slot][0], o.sep_dir[slot][1], o.sep_dir[slot][2]};
+    mpr_support(sc, cd, sp);
+    if (dot3(sp.v, cd) < -1e-7f) run = false;
+  }
+  if (run) {
+#if defined(LS_EMULATE)
+    g_mpr_calls++;
+    const long sup0_ = g_mpr_supports;
+#else
+    if ((c_debug & 8) && LS_LANE == 0) atomicAdd(&g_dbg[0], 1ULL);
+#endif
+    const bool hit_ = mpr_penetration(sc, &depth, dir, pos, sep);
+#if defined(LS_EMULATE) && defined(LS_MPRLOG)
+    printf("MPR %d %d %d %d %ld %d\n", g1, g2, n1 / 3, n2 / 3, g_mpr_supports - sup0_, (int)hit_);
+#endif
+    if (!hit_) { code = 2.0f; r[1] = sep[0]; r[2] = sep[1]; r[3] = sep[2]; }
+    else if (dir[0] == 0.0f && dir[1] == 0.0f && dir[2] == 0.0f) code = 3.0f;      // contact found but normal undefined
+    else {
+      code = 1.0f; r[0] = margin - depth;
+      for (int k = 0; k < 3; k++) { r[1 + k] = pos[k]; r[4 + k] = dir[k]; }
+    }
+  }
+  SYNC();                                      // (the scratch is free for the next job of this warp)
+  LANE0 { for (int k = 0; k < 7; k++) res[k] = r[k]; res[7] = code; }
+}
+
+// owner side of a finished convex job: contact into the list, or the separating direction into the cache
+template <class C>
+LS_FN void convex_consume(const int ms, EnvS<C>& e, int p, const float* res) {
+  const DevModel& m = c_models[ms];
+  const int code = (int)res[7];
+  if (code == 0) return;
+  LANE0 { e.mpr_calls += 1; }
+  if (code == 2) {
+    int slot = -1;
+    for (int k = 0; k < EnvS<C>::NSEP; k++) if (e.sep_pair[k] == p) slot = k;
+    if (slot < 0) slot = e.sep_next & (EnvS<C>::NSEP - 1);
+    SYNC();
+    LANE0 {
+      if (e.sep_pair[slot] != p) e.sep_next = e.sep_next + 1;
+      e.sep_pair[slot] = p; e.sep_dir[slot][0] = res[1]; e.sep_dir[slot][1] = res[2]; e.sep_dir[slot][2] = res[3];
+    }
+    SYNC();
+    return;
+  }
+  if (code != 1) return;
+  const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
+  const float incl = pair_incl(m, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]));
+  const int ci = e.ncon;
+  if (res[0] < incl && ci < EnvS<C>::MAXCON) {
+    LANE0 {
+      RawCon rc;
+      rc.dist = res[0];
+      for (int k = 0; k < 3; k++) { rc.pos[k] = res[1 + k]; rc.frame[k] = res[4 + k]; rc.frame[3 + k] = 0; }
+      fill_contact(ms, e, ci, g1, g2, incl, &rc);
+      e.ncon = ci + 1;
+    }
+    SYNC();
+  }
+}
+
 // narrow phase of pair p: up to 4 raw contacts (one lane per pair)
 template <class C>
 LS_FN int pair_narrow(const int ms, EnvS<C>& e, int p, RawCon* raw, int* g1_out, int* g2_out, float* margin_out) {
@@ -1255,6 +1388,8 @@ LS_FN int pair_narrow(const int ms, EnvS<C>& e, int p, RawCon* raw, int* g1_out,
     n = sphere_capsule(raw, margin, pos1, size1[0], pos2, mat2, size2);
   } else if (t1 == LS_GEOM_CAPSULE && t2 == LS_GEOM_CAPSULE) {
     n = capsule_capsule(raw, margin, pos1, mat1, size1, pos2, mat2, size2);
+  } else if (t1 == LS_GEOM_SPHERE && t2 == LS_GEOM_BOX) {
+    n = sphere_box(raw, margin, pos1, size1[0], pos2, mat2, size2);
   }
   *g1_out = g1; *g2_out = g2; *margin_out = margin;
   return n;
@@ -1267,11 +1402,15 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
   SYNC();
   // Convex pairs (box | mesh vs mesh, mjc_Convex) that pass the bounding spheres are only COLLECTED in the pair loop
   // (compacted list in the constraint-row storage, which is free until make_constraint) and handled afterwards: the
-  // oriented-box test runs on the compacted list (full lanes instead of a few lanes in every round of 32 pairs) and the
-  // survivors go through the warp-cooperative MPR one by one. Their contacts therefore FOLLOW the primitive contacts in
-  // the list (ordered by pair among themselves); the order of constraint rows has no influence on the solution.
-  unsigned short* cand = reinterpret_cast<unsigned short*>(e.r_D);
-  const int cand_max = (int)(5 * EnvS<C>::MAXEFC * sizeof(float) / sizeof(unsigned short));
+  // oriented-box test runs on the compacted list (full lanes instead of a few lanes in every round of 32 pairs), the
+  // survivors become JOBS (one warp-cooperative MPR each) that the warps of the block share, and every env then consumes
+  // the results of its own jobs in pair order. Their contacts therefore FOLLOW the primitive contacts in the list (ordered
+  // by pair among themselves); the order of constraint rows has no influence on the solution.
+  // Layout of the 5 * MAXEFC floats: [results: LS_MAXJOB x 8 floats][candidate / job list: unsigned short ...].
+  float* jobres = e.r_D;
+  unsigned short* cand = reinterpret_cast<unsigned short*>(e.r_D + 8 * LS_MAXJOB);
+  const int cand_max = (int)((5 * EnvS<C>::MAXEFC - 8 * LS_MAXJOB) * sizeof(float) / sizeof(unsigned short));
+  static_assert(5 * EnvS<C>::MAXEFC - 8 * LS_MAXJOB >= 128, "room for the candidate list");
   int ncand = 0;
 #ifdef LS_EMULATE
   for (int p = 0; p < m.np; p++) {
@@ -1285,14 +1424,15 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
     for (int k = 0; k < n; k++)
       if (raw[k].dist < incl && e.ncon < EnvS<C>::MAXCON) fill_contact(ms, e, e.ncon++, g1, g2, incl, raw + k);
   }
-  for (int k = 0; k < ncand; k++) {
-    const int p = cand[k];
-    if (!convex_obb_filter(ms, e, p)) continue;
-    RawCon rc;
-    if (!convex_narrow(ms, e, p, &rc)) continue;
-    const int g1 = m.pair_geom[2 * p], g2 = m.pair_geom[2 * p + 1];
-    const float incl = pair_incl(m, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]));
-    if (rc.dist < incl && e.ncon < EnvS<C>::MAXCON) fill_contact(ms, e, e.ncon++, g1, g2, incl, &rc);
+  {
+    int nsurv = 0;
+    for (int k = 0; k < ncand; k++) if (convex_obb_filter(ms, e, cand[k])) cand[nsurv++] = cand[k];
+    float tmp[8];
+    for (int base = 0; base < nsurv; base += LS_MAXJOB) {
+      const int nj = nsurv - base < LS_MAXJOB ? nsurv - base : LS_MAXJOB;
+      for (int j = 0; j < nj; j++) convex_job(ms, e, e, cand[base + j], jobres + 8 * j);
+      for (int j = 0; j < nj; j++) { for (int k = 0; k < 8; k++) tmp[k] = jobres[8 * j + k]; convex_consume(ms, e, cand[base + j], tmp); }
+    }
   }
 #else
   // 32 candidate pairs at a time: every lane filters its pair, the lanes that hit run the narrow phase in parallel,
@@ -1345,26 +1485,70 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
     LANE0 { const int nc = e.ncon + total; e.ncon = nc < EnvS<C>::MAXCON ? nc : EnvS<C>::MAXCON; }
     __syncwarp();
   }
-  if (C::CONVEX && ncand > 0) {
+  if (C::CONVEX) {
     if (ncand > cand_max) ncand = cand_max;
     __syncwarp();
+    // (1) oriented-box test on the compacted candidates; the survivors are compacted in place (pair order is kept)
+    int nsurv = 0;
     NOUNROLL for (int base = 0; base < ncand; base += 32) {
       const int p = base + lane < ncand ? (int)cand[base + lane] : -1;
-      unsigned pm = __ballot_sync(0xffffffffu, p >= 0 && ((c_debug & 2) || convex_obb_filter(ms, e, p)));
-      while (pm) {
-        const int src = __ffs(pm) - 1;
-        pm &= pm - 1;
-        const int pp = __shfl_sync(0xffffffffu, p, src);
-        RawCon rc;
-        const int nn = (c_debug & 1) ? 0 : convex_narrow(ms, e, pp, &rc);   // warp-cooperative; every lane holds the result
-        const int g1 = m.pair_geom[2 * pp], g2 = m.pair_geom[2 * pp + 1];
-        const float incl = pair_incl(m, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]));
-        const int ci = e.ncon;
-        if (nn > 0 && rc.dist < incl && ci < EnvS<C>::MAXCON) {
-          LANE0 { fill_contact(ms, e, ci, g1, g2, incl, &rc); e.ncon = ci + 1; }
-          __syncwarp();
-        }
+      const bool pass = p >= 0 && ((c_debug & 2) || convex_obb_filter(ms, e, p));
+      const unsigned pm = __ballot_sync(0xffffffffu, pass);
+      if (pass) cand[nsurv + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)p;      // (slot <= base + lane: in place is safe)
+      nsurv += __popc(pm);
+      __syncwarp();
+    }
+    if (c_debug & 1) nsurv = 0;
+    // (2) the block's warps share the jobs: every env publishes its first LS_MAXJOB survivors, all warps drain the queue
+    //     (dynamic: one shared-memory atomic per job), results land in the OWNER's record list. Block barriers: every
+    //     warp of the block runs collision() the same number of times (ghost warps included).
+    EnvS<C>* blk = &e - (threadIdx.x >> 5);
+    const int nw = (int)(blockDim.x >> 5);
+    const int nj = nsurv < LS_MAXJOB ? nsurv : LS_MAXJOB;
+    // (njobs is double-buffered by call parity: when no env of the block has a job there is no second barrier, and a warp
+    //  that runs ahead into its next evaluation must not overwrite the count a slower warp is still about to read)
+    const int par = e.job_par & 1;
+    __syncwarp();
+    LANE0 { e.njobs[par] = nj; e.job_par = par ^ 1; }
+    __syncthreads();
+    int incl = lane < nw ? blk[lane].njobs[par] : 0;
+    const int mine = incl;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total > 0) {
+      for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(&blk[0].job_head, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= total) break;
+        const int owner = __popc(__ballot_sync(0xffffffffu, incl <= g));         // first lane whose inclusive prefix exceeds g
+        const int first = __shfl_sync(0xffffffffu, incl - mine, owner);
+        EnvS<C>& o = blk[owner];
+        const unsigned short* ocand = reinterpret_cast<const unsigned short*>(o.r_D + 8 * LS_MAXJOB);
+        convex_job(ms, o, e, (int)ocand[g - first], o.r_D + 8 * (g - first));
       }
+      __syncthreads();
+      if (threadIdx.x == 0) blk[0].job_head = 0;       // (next use is behind the next evaluation's first barrier)
+      // (3) owners consume their records in pair order
+      NOUNROLL for (int j = 0; j < nj; j++) {
+        float rec[8];
+        for (int k = 0; k < 8; k++) rec[k] = jobres[8 * j + k];
+        __syncwarp();
+        convex_consume(ms, e, (int)cand[j], rec);
+      }
+    }
+    // (4) overflow (more than LS_MAXJOB survivors in one evaluation: not seen in the in-scope models): the owner alone
+    NOUNROLL for (int j = LS_MAXJOB; j < nsurv; j++) {
+      float rec[8];
+      convex_job(ms, e, e, (int)cand[j], jobres);
+      __syncwarp();
+      for (int k = 0; k < 8; k++) rec[k] = jobres[k];
+      __syncwarp();
+      convex_consume(ms, e, (int)cand[j], rec);
     }
   }
 #endif

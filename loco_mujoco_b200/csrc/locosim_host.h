@@ -83,14 +83,21 @@ static inline std::string parse_model(HostModel& h, const int* ints, int n_ints,
   h.ints.insert(h.ints.end(), mask.begin(), mask.end());
   h.ints.insert(h.ints.end(), frow.begin(), frow.end());
   for (int i = 0; i < 32; i++) for (int j = 0; j <= i; j++) h.ints.push_back((i << 8) | j);   // row-major lower triangle, n <= 32
-  // packed candidate-pair table of the mid-phase: g1 | g2 << 12 | flags << 24 (1: g1 is a plane, 2: convex pair = box | mesh
-  // vs mesh) and, as float bits, the bound of the bounding-sphere test (rbound[g2] for planes, else rbound[g1] + rbound[g2])
+  // packed candidate-pair table of the mid-phase: g1 | g2 << 12 | flags << 24 (1: g1 is a plane, 2: general convex
+  // pair) and, as float bits, the bound of the bounding-sphere test (rbound[g2] for planes, else rbound[g1] + rbound[g2])
   if (ng >= 4096) return "more than 4095 geoms";
   for (int p = 0; p < np; p++) {
     const int g1 = pair_geom[2 * p], g2 = pair_geom[2 * p + 1];
     int flags = 0;
     if (geom_type[g1] == LS_GEOM_PLANE) flags |= 1;
-    if (geom_type[g2] == LS_GEOM_MESH && geom_type[g1] >= LS_GEOM_BOX) flags |= 2;
+    else {
+      // dedicated primitive routines: sphere-sphere, sphere-capsule, capsule-capsule, sphere-box; everything else is a
+      // general convex pair (mjc_Convex / MPR)  [same rule as modelpack.py convex_pair_mask]
+      const int t1 = geom_type[g1], t2 = geom_type[g2];
+      const bool prim = (t1 == LS_GEOM_SPHERE && (t2 == LS_GEOM_SPHERE || t2 == LS_GEOM_CAPSULE || t2 == LS_GEOM_BOX)) ||
+                        (t1 == LS_GEOM_CAPSULE && t2 == LS_GEOM_CAPSULE);
+      if (!prim) flags |= 2;
+    }
     h.ints.push_back(g1 | (g2 << 12) | (flags << 24));
   }
   for (int p = 0; p < np; p++) {

@@ -759,7 +759,7 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64, fuse_stati
     m.geom_rbound = rb
 
     # ---- collision pair filter (static part of mj_collision's broadphase) --------------------------------
-    pairs, dropped = [], []
+    pairs, dropped, approx = [], [], []
     for g1 in range(m.ngeom):
         for g2 in range(g1 + 1, m.ngeom):
             b1, b2 = m.geom_bodyid[g1], m.geom_bodyid[g2]
@@ -776,17 +776,24 @@ def compile_model(handle, timestep=None, collision_mesh_max_verts=64, fuse_stati
             if m.geom_type[a] == GEOM_PLANE and m.geom_type[b] == GEOM_PLANE:
                 continue
             ta, tb = m.geom_type[a], m.geom_type[b]
-            supported = (ta == GEOM_PLANE and tb in (GEOM_SPHERE, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH)) or \
-                        (ta, tb) in ((GEOM_SPHERE, GEOM_SPHERE), (GEOM_SPHERE, GEOM_CAPSULE), (GEOM_CAPSULE, GEOM_CAPSULE),
-                                     (GEOM_MESH, GEOM_MESH), (GEOM_BOX, GEOM_MESH))      # the last two: mjc_Convex (MPR)
+            # MuJoCo 2.3.7 collision table (type(a) <= type(b)): dedicated routines for plane-X, sphere-sphere, sphere-capsule,
+            # capsule-capsule, sphere-box (all restated); capsule-box / box-box have dedicated MULTI-contact routines that are
+            # not restated: they run through the general convex routine (one contact, counted in n_approx_pairs);
+            # every other pair of sphere | capsule | cylinder | box | mesh is mjc_Convex (MPR) in MuJoCo too.
+            convexable = (GEOM_SPHERE, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH)
+            if ta == GEOM_PLANE:
+                supported = tb in convexable
+            else:
+                supported = ta in convexable and tb in convexable
             if not supported:
-                # mjc_BoxBox / mjc_CapsuleBox / mjc_SphereBox (dedicated routines) and convex pairs with a smooth geom
-                # (sphere / capsule / cylinder vs cylinder / mesh): not built
-                dropped.append((a, b))
+                dropped.append((a, b))          # ellipsoids, height fields: no in-scope model has them
                 continue
+            if (ta, tb) in ((GEOM_CAPSULE, GEOM_BOX), (GEOM_BOX, GEOM_BOX)):
+                approx.append((a, b))
             pairs.append((a, b))
     m.npair = len(pairs)
     m.n_dropped_pairs = len(dropped)
+    m.n_approx_pairs = len(approx)
     m.pair_geom = np.array(pairs, dtype=np.int32).reshape(-1, 2)
 
     # ---- actuators ------------------------------------------------------------------------------------------

@@ -28,18 +28,20 @@ EXTRA_ARRAYS = ["opt_gravity", "body_weldid", "body_dofadr", "body_dofnum", "dof
                 "geom_conaffinity", "site_bodyid", "site_pos", "site_quat"]
 
 
-GEOM_BOX, GEOM_MESH = 6, 7
+GEOM_PLANE, GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX, GEOM_MESH = 0, 2, 3, 6, 7
+PRIMITIVE_PAIRS = {(GEOM_SPHERE, GEOM_SPHERE), (GEOM_SPHERE, GEOM_CAPSULE), (GEOM_CAPSULE, GEOM_CAPSULE), (GEOM_SPHERE, GEOM_BOX)}
 
 
 def convex_pair_mask(m):
-    """True for the candidate pairs that go through the general convex routine (mjc_Convex / MPR): box | mesh vs mesh."""
+    """True for the candidate pairs that go through the general convex routine (mjc_Convex / MPR): everything that is
+    neither a plane pair nor one of the dedicated primitive routines (same rule as csrc/locosim_host.h parse_model)."""
     pg = np.asarray(m.pair_geom).reshape(-1, 2)
     t = np.asarray(m.geom_type)
-    return (t[pg[:, 1]] == GEOM_MESH) & (t[pg[:, 0]] >= GEOM_BOX) if len(pg) else np.zeros(0, dtype=bool)
+    return np.array([t[a] != GEOM_PLANE and (int(t[a]), int(t[b])) not in PRIMITIVE_PAIRS for a, b in pg], dtype=bool)
 
 
 def pack(m, convex_pairs=True):
-    """Model -> (ints int32[], reals float64[]). convex_pairs=False leaves the mesh-mesh / box-mesh candidate pairs out of
+    """Model -> (ints int32[], reals float64[]). convex_pairs=False leaves the general convex (MPR) candidate pairs out of
     the pair table (LocoEnv kwarg `convex_collisions=False`: the round-1 feature set, without bone-bone contacts)."""
     pair_geom = np.asarray(m.pair_geom).reshape(-1, 2)
     if not convex_pairs:

@@ -551,6 +551,38 @@ static int sphere_capsule(RawCon* c, double margin, const double* pos1, double r
   double p[3] = {pos2[0] + axis[0] * x, pos2[1] + axis[1] * x, pos2[2] + axis[2] * x};
   return sphere_sphere_raw(c, margin, pos1, r1, p, size2[0]);
 }
+/* mjc_SphereBox (engine_collision_box.c, not under /root/reference): sphere g1 against box g2 -- the sphere centre is
+ * clamped to the box in the box frame; outside: normal along (clamped - centre), dist = |centre - clamped| - r; centre
+ * inside the box: exit through the nearest face. Geometrically unique results; no reference golden exercises it
+ * (parity unpinned). The contact normal points from geom 1 (sphere) to geom 2 (box). */
+static int sphere_box(RawCon* c, double margin, const double* pos1, double r, const double* pos2, const double* mat2,
+                      const double* size2) {
+  double tmp[3] = {pos1[0] - pos2[0], pos1[1] - pos2[1], pos1[2] - pos2[2]}, cen[3], cl[3], d[3], nb[3] = {0, 0, 0}, pl[3];
+  mulmatTvec3(cen, mat2, tmp);
+  for (int k = 0; k < 3; k++) { cl[k] = fmax(-size2[k], fmin(size2[k], cen[k])); d[k] = cen[k] - cl[k]; }
+  double dist = norm3(d);
+  if (dist - r > margin) return 0;
+  if (dist <= mjMINVAL) {
+    double closest = 2 * (size2[0] + size2[1] + size2[2]);
+    int kk = 0;
+    for (int i = 0; i < 6; i++) {
+      double f = fabs((i % 2 ? 1.0 : -1.0) * size2[i / 2] - cen[i / 2]);
+      if (closest > f) { closest = f; kk = i; }
+    }
+    nb[kk / 2] = kk % 2 ? 1.0 : -1.0;                                  /* outward normal of the nearest face */
+    for (int k = 0; k < 3; k++) pl[k] = cen[k] + nb[k] * 0.5 * (closest - r);
+    c->dist = -closest - r;
+  } else {
+    for (int k = 0; k < 3; k++) { nb[k] = d[k] / dist; pl[k] = cl[k] + nb[k] * 0.5 * (dist - r); }
+    c->dist = dist - r;
+  }
+  double nw[3], pw[3];
+  mulmatvec3(nw, mat2, nb);
+  mulmatvec3(pw, mat2, pl);
+  memset(c->frame, 0, sizeof(c->frame));
+  for (int k = 0; k < 3; k++) { c->frame[k] = -nw[k]; c->pos[k] = pos2[k] + pw[k]; }
+  return 1;
+}
 static int capsule_capsule(RawCon* c, double margin, const double* pos1, const double* mat1, const double* size1,
                            const double* pos2, const double* mat2, const double* size2) {
   double a1[3] = {mat1[2], mat1[5], mat1[8]}, a2[3] = {mat2[2], mat2[5], mat2[8]};
@@ -913,9 +945,14 @@ static void collision(RefSim* s) {
       n = sphere_capsule(raw, margin, pos1, size1[0], pos2, mat2, size2);
     } else if (t1 == LS_GEOM_CAPSULE && t2 == LS_GEOM_CAPSULE) {
       n = capsule_capsule(raw, margin, pos1, mat1, size1, pos2, mat2, size2);
+    } else if (t1 == LS_GEOM_SPHERE && t2 == LS_GEOM_BOX) {
+      n = sphere_box(raw, margin, pos1, size1[0], pos2, mat2, size2);
     } else {
-      /* every other pair the compiler lets through (mesh-mesh, box-mesh, ...): mjc_Convex, one contact. (mjc_BoxBox,
-         mjc_CapsuleBox, mjc_SphereBox have their own routines in MuJoCo: those pairs are dropped at compile time.) */
+      /* every other pair: mjc_Convex (MPR), one contact -- MuJoCo 2.3.7's collision table routes sphere | capsule |
+         cylinder | box | mesh against cylinder | mesh there (and ellipsoids, which no in-scope model has).
+         DEVIATION: capsule-box and box-box have dedicated multi-contact routines in MuJoCo (mjc_CapsuleBox, mjc_BoxBox,
+         not restated); they also go through MPR here: ONE contact at the deepest point instead of up to 2 / 8
+         (mjcf.py counts them in Model.n_approx_pairs; A1 trunk vs legs, the humanoid's two foot boxes). */
       n = convex_pair(raw, s, g1, g2, margin);
     }
     for (int k = 0; k < n && s->ncon < MAXCON; k++) {

@@ -34,6 +34,12 @@ class Oracle:
         lib.ref_rollout.argtypes = [vp, ip, vp, ip, vp, ip, vp, ip, ip, ip, ip, ctypes.c_ulonglong, vp, vp]
         lib.ref_nv.restype = ip
         lib.ref_nv.argtypes = [vp]
+        lib.ref_debug_convex.restype = ctypes.c_long
+        lib.ref_debug_convex.argtypes = [ip]
+
+    def convex_hits(self):
+        """Contacts reported so far by the oracle's general convex routine (mjc_Convex / MPR), process-wide counter."""
+        return int(self.lib.ref_debug_convex(1))
 
     def env(self, model_blobs, task_blobs):
         return OracleEnv(self, model_blobs, task_blobs)
