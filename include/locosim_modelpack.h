@@ -29,7 +29,10 @@ enum {
   MPR_HEADER_LEN = 16
 };
 
-/* X(name, count-expression) ; nb=nbody nv=nv ng=ngeom nu=nu np=npair nm=nmeshvert */
+/* X(name, count-expression) ; nb=nbody nv=nv ng=ngeom nu=nu np=npair nm=nmeshvert
+ * pair_geom: candidate geom pairs (g1, g2) with type(g1) <= type(g2); the pairs handled by a dedicated primitive routine
+ * (plane-X, sphere-sphere, sphere-capsule, capsule-capsule, sphere-box) MUST come first, the general convex pairs
+ * (mjc_Convex / MPR) last; model order inside each part (loco_mujoco_b200/modelpack.py pack()). */
 #define LOCOSIM_MP_INT_FIELDS(X) \
   X(body_parentid, nb) X(body_jntadr, nb) X(body_jntnum, nb) X(body_lastdof, nb) X(body_rootid, nb) \
   X(jnt_type, nv) X(jnt_bodyid, nv) X(jnt_limited, nv) X(dof_parentid, nv) \

@@ -394,7 +394,7 @@ static int setup_cfg(locosim_handle* h) {
   if (getenv("LOCOSIM_KEY_MODE")) h->key_mode = atoi(getenv("LOCOSIM_KEY_MODE"));
   {
     // an MPR run holds its lock-step block about as long as `w` Newton iterations; key of a freshly reset env (+1; 0 = keep)
-    int w = 4, kr = 0;
+    int w = C::CONE == 1 ? 4 : 32, kr = C::CONE == 1 ? 1 : 0;       // (measured: profiles/README.md, round-2 knob sweeps)
     if (getenv("LOCOSIM_MPR_WEIGHT")) w = atoi(getenv("LOCOSIM_MPR_WEIGHT"));
     if (getenv("LOCOSIM_KEY_RESET")) kr = atoi(getenv("LOCOSIM_KEY_RESET")) + 1;
     h->key_mode = (h->key_mode & 255) | ((w & 255) << 8) | (kr << 16);

@@ -93,6 +93,7 @@ struct DevModel {
   int nb, nv, ng, nu, np, nm, integrator, cone, iterations, nlevel, nfric;
   float timestep, gravity[3], impratio, tolerance, meaninertia;
   int has_damping;
+  int np_prim;               // the first np_prim candidate pairs are primitive (plane / sphere / capsule routines), the rest general convex
 #define X(name, cnt) const int* name;
   LOCOSIM_MP_INT_FIELDS(X)
 #undef X
@@ -868,10 +869,18 @@ LS_DEV void mpr_support_geom(const MprGeom& g, const float* d, float* res, int l
     }
 #else
     const int n = g.vnum;
+    if (g.world) {                             // shared memory
 #pragma unroll 2
-    for (int i = LS_LANE - l0; i < n; i += nl) {
-      const float t = q[0] * v[3 * i] + q[1] * v[3 * i + 1] + q[2] * v[3 * i + 2];
-      if (t > mx) { mx = t; best = i; }
+      for (int i = LS_LANE - l0; i < n; i += nl) {
+        const float t = q[0] * v[3 * i] + q[1] * v[3 * i + 1] + q[2] * v[3 * i + 2];
+        if (t > mx) { mx = t; best = i; }
+      }
+    } else {                                   // global memory (L2): many loads in flight, the scan is pure latency
+#pragma unroll 8
+      for (int i = LS_LANE - l0; i < n; i += nl) {
+        const float t = q[0] * __ldg(v + 3 * i) + q[1] * __ldg(v + 3 * i + 1) + q[2] * __ldg(v + 3 * i + 2);
+        if (t > mx) { mx = t; best = i; }
+      }
     }
     // argmax in two redux instructions: max of the order-preserving integer image of the dot product, then the smallest
     // index among the lanes that hold it
@@ -1254,45 +1263,26 @@ LS_FN void convex_job(const int ms, const EnvS<C>& o, EnvS<C>& e, int p, float* 
   // written ONCE, already in world coordinates, into shared memory (all loads in flight, parallel over the vertices), so
   // the support calls on the serial critical path are a bare argmax; larger pairs scan global memory in the mesh frame.
   const bool staged = 3 * (n1 + n2) <= EnvS<C>::MAXROW * EnvS<C>::JS - SCR;
-  {
-    float m1[9], m2[9];
-    geom_mat(ms, o, g1, m1);
-    geom_mat(ms, o, g2, m2);
-    if (staged) {
-      PAR_FOR(i, n1 + n2) {
-        const bool second = i >= n1;
-        const int j = second ? i - n1 : i;
-        const int ty = second ? t2 : t1;
-        const float* mm = second ? m2 : m1;
-        const float* gp = second ? o.gxpos[g2] : o.gxpos[g1];
-        float v[3];
-        if (ty == LS_GEOM_MESH) { const float* sv = (second ? s2 : s1) + 3 * j; v[0] = sv[0]; v[1] = sv[1]; v[2] = sv[2]; }
-        else {
-          const float* sz = m.geom_size + 3 * (second ? g2 : g1);
-          v[0] = (j & 1) ? -sz[0] : sz[0]; v[1] = (j & 2) ? -sz[1] : sz[1]; v[2] = (j & 4) ? -sz[2] : sz[2];
-        }
-        float w[3];
-        mulmatvec3(w, mm, v);
-        buf[3 * i] = w[0] + gp[0]; buf[3 * i + 1] = w[1] + gp[1]; buf[3 * i + 2] = w[2] + gp[2];
-      }
+  float m1[9], m2[9];
+  geom_mat(ms, o, g1, m1);
+  geom_mat(ms, o, g2, m2);
+  LANE0 {                                      // descriptors first WITHOUT staged vertices (frame-local supports)
+    MprGeom& a = sc->g[0];
+    MprGeom& b = sc->g[1];
+    a.type = t1; a.vnum = n1; a.margin = 0.5f * margin; a.world = 0; a.verts = s1;
+    b.type = t2; b.vnum = n2; b.margin = 0.5f * margin; b.world = 0; b.verts = s2;
+    for (int k = 0; k < 3; k++) {
+      a.pos[k] = o.gxpos[g1][k]; b.pos[k] = o.gxpos[g2][k];
+      a.size[k] = m.geom_size[3 * g1 + k]; b.size[k] = m.geom_size[3 * g2 + k];
     }
-    LANE0 {
-      MprGeom& a = sc->g[0];
-      MprGeom& b = sc->g[1];
-      a.type = t1; a.vnum = n1; a.margin = 0.5f * margin; a.world = (staged && n1 > 0) ? 1 : 0; a.verts = a.world ? buf : s1;
-      b.type = t2; b.vnum = n2; b.margin = 0.5f * margin; b.world = (staged && n2 > 0) ? 1 : 0; b.verts = b.world ? buf + 3 * n1 : s2;
-      for (int k = 0; k < 3; k++) {
-        a.pos[k] = o.gxpos[g1][k]; b.pos[k] = o.gxpos[g2][k];
-        a.size[k] = m.geom_size[3 * g1 + k]; b.size[k] = m.geom_size[3 * g2 + k];
-      }
-      for (int k = 0; k < 9; k++) { a.mat[k] = m1[k]; b.mat[k] = m2[k]; }
-    }
+    for (int k = 0; k < 9; k++) { a.mat[k] = m1[k]; b.mat[k] = m2[k]; }
   }
   SYNC();
   float depth, dir[3], pos[3], sep[3] = {0, 0, 0};
-  // A direction that separated this pair in an earlier evaluation of the control step is tried first (ONE support pair;
-  // strict separation of the inflated geoms along it means MPR would not report a contact either); if it fails the full
-  // MPR runs and its last test direction refreshes the cache (applied by the owner, in job order).
+  // A direction that separated this pair in an earlier evaluation of the control step is tried first (ONE support pair,
+  // straight from the model's vertex arrays: nothing is staged for it; strict separation of the inflated geoms along it
+  // means MPR would not report a contact either); if it fails the full MPR runs and its last test direction refreshes the
+  // cache (applied by the owner, in job order).
   int slot = -1;
   for (int k = 0; k < EnvS<C>::NSEP; k++) if (o.sep_pair[k] == p) slot = k;
   float code = 0.0f, r[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -1302,6 +1292,30 @@ LS_FN void convex_job(const int ms, const EnvS<C>& o, EnvS<C>& e, int p, float* 
     const float cd[3] = {o.sep_dir[slot][0], o.sep_dir[slot][1], o.sep_dir[slot][2]};
     mpr_support(sc, cd, sp);
     if (dot3(sp.v, cd) < -1e-7f) run = false;
+  }
+  SYNC();                                      // (every lane is done reading the descriptors before lane 0 rewrites them)
+  if (run && staged) {
+    PAR_FOR(i, n1 + n2) {
+      const bool second = i >= n1;
+      const int j = second ? i - n1 : i;
+      const int ty = second ? t2 : t1;
+      const float* mm = second ? m2 : m1;
+      const float* gp = second ? o.gxpos[g2] : o.gxpos[g1];
+      float v[3];
+      if (ty == LS_GEOM_MESH) { const float* sv = (second ? s2 : s1) + 3 * j; v[0] = sv[0]; v[1] = sv[1]; v[2] = sv[2]; }
+      else {
+        const float* sz = m.geom_size + 3 * (second ? g2 : g1);
+        v[0] = (j & 1) ? -sz[0] : sz[0]; v[1] = (j & 2) ? -sz[1] : sz[1]; v[2] = (j & 4) ? -sz[2] : sz[2];
+      }
+      float w[3];
+      mulmatvec3(w, mm, v);
+      buf[3 * i] = w[0] + gp[0]; buf[3 * i + 1] = w[1] + gp[1]; buf[3 * i + 2] = w[2] + gp[2];
+    }
+    LANE0 {
+      if (n1 > 0) { sc->g[0].world = 1; sc->g[0].verts = buf; }
+      if (n2 > 0) { sc->g[1].world = 1; sc->g[1].verts = buf + 3 * n1; }
+    }
+    SYNC();
   }
   if (run) {
 #if defined(LS_EMULATE)
@@ -1439,22 +1453,14 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
   // an exclusive scan over the lanes' contact counts assigns the slots, i.e. the list order is pair order, contact
   // order within the pair: the same order as the serial loop (and as the oracle).
   const int lane = LS_LANE;
-  for (int base = 0; base < m.np; base += 32) {
+  // The pair table holds the primitive pairs first (ModelPack order: modelpack.pack partitions it), then the general convex
+  // pairs: the latter only need the bounding-sphere test and a compaction, a lean loop (2 rounds of 32 per iteration).
+  const int np_prim = m.np_prim;
+  for (int base = 0; base < np_prim; base += 32) {
     const int p = base + lane;
-    const int pk = p < m.np ? e.pk_tab[p] : 0;
-    bool hit = (p < m.np) && pair_filter(ms, e, p, pk);
+    const int pk = p < np_prim ? e.pk_tab[p] : 0;
+    bool hit = (p < np_prim) && pair_filter(ms, e, p, pk);
     if (!__any_sync(0xffffffffu, hit)) continue;        // (most rounds of 32 pairs have no candidate at all)
-    if (C::CONVEX) {                                   // (configurations whose models carry convex pairs)
-      const bool conv = hit && (pk & (2 << 24));
-      const unsigned cmask = (c_debug & 4) ? 0u : __ballot_sync(0xffffffffu, conv);
-      if (cmask) {
-        const int slot = ncand + __popc(cmask & ((1u << lane) - 1u));
-        if (conv && slot < cand_max) cand[slot] = (unsigned short)p;
-        ncand += __popc(cmask);
-        if (conv) hit = false;
-        if (!__any_sync(0xffffffffu, hit)) continue;
-      }
-    }
     RawCon raw[4];
     int g1 = 0, g2 = 0, n = 0, nact = 0;
     float margin = 0, incl = 0;
@@ -1485,6 +1491,30 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
     LANE0 { const int nc = e.ncon + total; e.ncon = nc < EnvS<C>::MAXCON ? nc : EnvS<C>::MAXCON; }
     __syncwarp();
   }
+  if (C::CONVEX && !(c_debug & 4)) {
+    const int npt = m.np;
+    NOUNROLL for (int base = np_prim; base < npt; base += 64) {
+      const int pa = base + lane, pb = pa + 32;
+      const int ka = pa < npt ? e.pk_tab[pa] : 0, kb = pb < npt ? e.pk_tab[pb] : 0;
+      const float ba = pa < npt ? e.pb_tab[pa] : -1.0f, bb = pb < npt ? e.pb_tab[pb] : -1.0f;
+      const float* xa1 = e.gxpos[ka & 0xfff];
+      const float* xa2 = e.gxpos[(ka >> 12) & 0xfff];
+      const float* xb1 = e.gxpos[kb & 0xfff];
+      const float* xb2 = e.gxpos[(kb >> 12) & 0xfff];
+      const float ax = xa2[0] - xa1[0], ay = xa2[1] - xa1[1], az = xa2[2] - xa1[2];
+      const float bx = xb2[0] - xb1[0], by = xb2[1] - xb1[1], bz = xb2[2] - xb1[2];
+      const bool ha = pa < npt && ax * ax + ay * ay + az * az <= ba * ba;
+      const bool hb = pb < npt && bx * bx + by * by + bz * bz <= bb * bb;
+      const unsigned ma = __ballot_sync(0xffffffffu, ha), mb = __ballot_sync(0xffffffffu, hb);
+      if (ma | mb) {
+        const unsigned lt = (1u << lane) - 1u;
+        const int sa = ncand + __popc(ma & lt), sb = ncand + __popc(ma) + __popc(mb & lt);
+        if (ha && sa < cand_max) cand[sa] = (unsigned short)pa;
+        if (hb && sb < cand_max) cand[sb] = (unsigned short)pb;
+        ncand += __popc(ma) + __popc(mb);
+      }
+    }
+  }
   if (C::CONVEX) {
     if (ncand > cand_max) ncand = cand_max;
     __syncwarp();
@@ -1494,6 +1524,7 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
       const int p = base + lane < ncand ? (int)cand[base + lane] : -1;
       const bool pass = p >= 0 && ((c_debug & 2) || convex_obb_filter(ms, e, p));
       const unsigned pm = __ballot_sync(0xffffffffu, pass);
+      __syncwarp();                              // (all 32 entries are read before the in-place compaction overwrites any)
       if (pass) cand[nsurv + __popc(pm & ((1u << lane) - 1u))] = (unsigned short)p;      // (slot <= base + lane: in place is safe)
       nsurv += __popc(pm);
       __syncwarp();

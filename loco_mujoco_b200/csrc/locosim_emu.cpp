@@ -23,6 +23,7 @@ struct EmuBase {
   virtual void bind_prm() = 0;
   virtual void contact(int k, double* o) = 0;
   virtual void grf(double* o, int clear) = 0;
+  virtual void frames(double* gx, double* bx) = 0;
 };
 template <class C>
 struct EmuT : EmuBase {
@@ -58,6 +59,10 @@ struct EmuT : EmuBase {
     for (int j = 0; j < 3; j++) { o[12 + j] = e.con_frame[k][j]; o[15 + j] = e.con_pos[k][j]; }
   }
   void grf(double* o, int clear) override { for (int k = 0; k < 3 * LS_MAX_GRF; k++) { o[k] = e.grf[k]; if (clear) e.grf[k] = 0; } }
+  void frames(double* gx, double* bx) override {
+    for (int g = 0; g < m.ng; g++) for (int k = 0; k < 3; k++) gx[3 * g + k] = e.gxpos[g][k];
+    for (int b = 0; b < m.nb; b++) { for (int k = 0; k < 3; k++) bx[7 * b + k] = e.xpos[b][k]; for (int k = 0; k < 4; k++) bx[7 * b + 3 + k] = e.xquat[b][k]; }
+  }
   void bind_prm() override { e.prm = hm.default_row.data(); e.pk_tab = m.pair_packed; e.pb_tab = m.pair_bound; c_models[0] = m; init_workspace(0, e); }
 };
 
@@ -96,6 +101,7 @@ int emu_ncon(EmuBase* s) { return s->info(0); }
 void emu_contact(EmuBase* s, int k, double* o) { s->contact(k, o); }
 void emu_set_grf(EmuBase* s, const int* group, int ng, int n_grf) { s->grf_group.assign(group, group + ng); s->n_grf = n_grf; }
 void emu_get_grf(EmuBase* s, double* o, int clear) { s->grf(o, clear); }
+void emu_frames(EmuBase* s, double* gx, double* bx) { s->frames(gx, bx); }
 int emu_nefc(EmuBase* s) { return s->info(1); }
 int emu_iter(EmuBase* s) { return s->info(2); }
 int emu_sizeof_env(int which) {

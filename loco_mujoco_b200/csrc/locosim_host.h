@@ -14,6 +14,7 @@ struct HostModel {
   int nb, nv, ng, nu, np, nm, integrator, cone, iterations, nlevel, nfric, has_damping;
   float timestep, gravity[3], impratio, tolerance, meaninertia;
   int max_condim;
+  int np_prim;                 // leading primitive pairs of the candidate-pair table (the general convex pairs follow)
   int po[13], pool_P;          // parameter pool row layout (float offsets), see domain_randomization.py POOL_FIELDS
   std::vector<float> default_row;   // the model's own parameters as one pool row
 };
@@ -86,6 +87,8 @@ static inline std::string parse_model(HostModel& h, const int* ints, int n_ints,
   // packed candidate-pair table of the mid-phase: g1 | g2 << 12 | flags << 24 (1: g1 is a plane, 2: general convex
   // pair) and, as float bits, the bound of the bounding-sphere test (rbound[g2] for planes, else rbound[g1] + rbound[g2])
   if (ng >= 4096) return "more than 4095 geoms";
+  h.np_prim = np;
+  bool seen_convex = false;
   for (int p = 0; p < np; p++) {
     const int g1 = pair_geom[2 * p], g2 = pair_geom[2 * p + 1];
     int flags = 0;
@@ -98,6 +101,8 @@ static inline std::string parse_model(HostModel& h, const int* ints, int n_ints,
                         (t1 == LS_GEOM_CAPSULE && t2 == LS_GEOM_CAPSULE);
       if (!prim) flags |= 2;
     }
+    if (flags & 2) { if (!seen_convex) h.np_prim = p; seen_convex = true; }
+    else if (seen_convex) return "candidate pairs not partitioned (primitive pairs first, general convex pairs last: modelpack.pack)";
     h.ints.push_back(g1 | (g2 << 12) | (flags << 24));
   }
   for (int p = 0; p < np; p++) {
@@ -141,6 +146,7 @@ static inline void bind_model(DevModel& m, const HostModel& h, const int* ibase,
   m.integrator = h.integrator; m.cone = h.cone; m.iterations = h.iterations; m.nlevel = h.nlevel; m.nfric = h.nfric;
   m.timestep = h.timestep; m.gravity[0] = h.gravity[0]; m.gravity[1] = h.gravity[1]; m.gravity[2] = h.gravity[2];
   m.impratio = h.impratio; m.tolerance = h.tolerance; m.meaninertia = h.meaninertia; m.has_damping = h.has_damping;
+  m.np_prim = h.np_prim;
   const int nb = h.nb, nv = h.nv, ng = h.ng, nu = h.nu, np = h.np, nm = h.nm;
   const int* ip = ibase;
   const float* rp = rbase;

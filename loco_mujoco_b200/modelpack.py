@@ -44,8 +44,10 @@ def pack(m, convex_pairs=True):
     """Model -> (ints int32[], reals float64[]). convex_pairs=False leaves the general convex (MPR) candidate pairs out of
     the pair table (LocoEnv kwarg `convex_collisions=False`: the round-1 feature set, without bone-bone contacts)."""
     pair_geom = np.asarray(m.pair_geom).reshape(-1, 2)
-    if not convex_pairs:
-        pair_geom = pair_geom[~convex_pair_mask(m)]
+    # wire order of the candidate pairs: primitive pairs first, general convex pairs last, model order within each part
+    # (the engine runs a lean bounding-sphere loop over the convex part; contact lists are ordered accordingly)
+    cm = convex_pair_mask(m)
+    pair_geom = pair_geom[~cm] if not convex_pairs else np.concatenate([pair_geom[~cm], pair_geom[cm]])
     ih = np.zeros(16, dtype=np.int32)
     ih[:11] = [MAGIC, VERSION, m.nbody, m.nv, m.ngeom, m.nu, len(pair_geom), len(m.mesh_vert), m.opt_integrator,
                m.opt_cone, m.opt_iterations]
