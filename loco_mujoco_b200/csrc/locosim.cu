@@ -149,8 +149,7 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
     if (stage_bytes > 0) {
       const unsigned char* sm = smem_raw + (size_t)(blockDim.x >> 5) * sizeof(EnvS<C>);
       e.pk_tab = reinterpret_cast<const int*>(sm);
-      e.pb_tab = reinterpret_cast<const float*>(sm + (stage_bytes >> 1));
-    } else { e.pk_tab = m.pair_packed; e.pb_tab = m.pair_bound; }
+    } else { e.pk_tab = m.pair_packed; }
   }
 
   // ---- load state ----
@@ -350,6 +349,12 @@ static bool cfg_fits(const HostModel& hm, const HostTask& ht) {
 }
 template <class C>
 static int cfg_smem() { return (int)sizeof(EnvS<C>); }
+// sizeof(EnvS) decides the envs resident per SM (227 KB of dynamic shared memory per block on sm_100): a field added without
+// looking costs a whole env per SM (and, for the RK4 robots, a third wave of blocks at 4096 envs). Guard the measured layout.
+static_assert(sizeof(EnvS<CfgEllEuler>) * 15 <= 232448, "UnitreeA1: 15 envs per SM");
+static_assert(sizeof(EnvS<CfgPyrEuler>) * 15 <= 232448, "Talos / UnitreeH1: 15 envs per SM");
+static_assert(sizeof(EnvS<CfgPyrRK4>) * 14 <= 232448, "HumanoidTorque / Atlas: 14 envs per SM (293 blocks = 1.98 waves at 4096 envs)");
+static_assert(sizeof(EnvS<CfgPyrEuler29>) * 9 <= 232448, "UnitreeG1: 9 envs per SM");
 
 template <class C>
 static int launch_step(locosim_handle* h, const float* a, float* o, float* r, uint8_t* d, float* no, int auto_reset,
@@ -414,13 +419,12 @@ static int setup_cfg(locosim_handle* h) {
   // 2.7825 -> 2.7653 ms per step (+0.6 %, two alternating runs each). LOCOSIM_STAGE=0 turns it off.
   if (!getenv("LOCOSIM_STAGE") || atoi(getenv("LOCOSIM_STAGE")) > 0) {
     const int np = h->hm.np;
-    const int half = (np * 4 + 15) & ~15;                        // each of the two tables, padded to 16 bytes
-    const int bytes = 2 * half;
+    const int bytes = (2 * np * 4 + 15) & ~15;                   // np packed pairs directly followed by np bounds (as in the model)
     if (np > 0 && h->smem + bytes + 16 <= dev_max) {
       CK(cudaMalloc((void**)&h->d_stage, bytes));
       CK(cudaMemset(h->d_stage, 0, bytes));
       CK(cudaMemcpy(h->d_stage, h->dm.pair_packed, 4 * np, cudaMemcpyDeviceToDevice));
-      CK(cudaMemcpy(h->d_stage + half, h->dm.pair_bound, 4 * np, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(h->d_stage + 4 * np, h->dm.pair_bound, 4 * np, cudaMemcpyDeviceToDevice));
       h->stage_bytes = bytes;
     }
   }

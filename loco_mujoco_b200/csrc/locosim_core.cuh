@@ -164,8 +164,8 @@ struct alignas(16) EnvS {
   float M[NV][NVP], H[NV][NVP];                              // H: chol(M) during smooth_forces, then the Newton Hessian factor
   // contacts
   int ncon, nunit, nrow, nefc, solver_iter, iter_sum, sep_next, mpr_calls;   // iter_sum / mpr_calls: Newton iterations / MPR runs of this control step
-  int njobs[2], job_par, job_head;   // convex jobs this env published for the block (collision(); double-buffered by call parity);
-                                     // job_head: head of the block's job queue (env 0 of the block only)
+  int njobs, job_head;     // convex jobs this env published for the block (collision()); job_head: head of the block's job queue
+                           // (env 0 of the block only). NOTE: sizeof(EnvS) decides the envs per SM (CfgPyrRK4: 16592 B = 14)
   float con_dist[MAXCON], con_pos[MAXCON][3], con_frame[MAXCON][9], con_fri[MAXCON][5], con_imp[MAXCON], con_K[MAXCON],
       con_B[MAXCON], con_incl[MAXCON], con_mu[MAXCON];
   int con_dim[MAXCON], con_g1[MAXCON], con_g2[MAXCON], con_row[MAXCON];
@@ -197,8 +197,8 @@ struct alignas(16) EnvS {
   float goal[4];
   float grf[3 * LS_MAX_GRF];   // use_foot_forces: per foot group, contact-frame force summed over the sub-steps
   const float* prm;        // this env's row of the parameter pool
-  const int* pk_tab;       // candidate-pair table of the mid-phase: the model's (global) or the block's TMA-staged copy (shared)
-  const float* pb_tab;
+  const int* pk_tab;       // candidate-pair table of the mid-phase: the model's (global) or the block's TMA-staged copy (shared):
+                           // np packed pairs, directly followed by np bounds (float)
 };
 #define PRM(field) (e.prm + m.po_##field)
 #define ROW_TYPE(ti) ((ti) & 255)
@@ -305,7 +305,7 @@ LS_FN void init_workspace(const int ms, EnvS<C>& e) {
     (&e.M[0][0])[idx] = (i == j && i >= m.nv) ? 1.0f : 0.0f;
   }
   PAR_FOR(k, EnvS<C>::NSEP) e.sep_pair[k] = -1;
-  LANE0 { e.sep_next = 0; e.mpr_calls = 0; e.job_par = 0; e.job_head = 0; e.njobs[0] = e.njobs[1] = 0; }
+  LANE0 { e.sep_next = 0; e.mpr_calls = 0; e.job_head = 0; e.njobs = 0; }
   // entries [nv, NV) of the solver vectors are never written by the phases (they loop to nv): keep them 0
   PAR_FOR(i, EnvS<C>::NV) {
     if (i >= m.nv) {
@@ -1116,7 +1116,7 @@ LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p, int pk) {
   const DevModel& m = c_models[ms];
   const int g1 = pk & 0xfff, g2 = (pk >> 12) & 0xfff;
   const float d[3] = {e.gxpos[g2][0] - e.gxpos[g1][0], e.gxpos[g2][1] - e.gxpos[g1][1], e.gxpos[g2][2] - e.gxpos[g1][2]};
-  const float bound = e.pb_tab[p];
+  const float bound = reinterpret_cast<const float*>(e.pk_tab + m.np)[p];
   if (pk & (1 << 24)) {
     float mat1[9];
     geom_mat(ms, e, g1, mat1);
@@ -1496,7 +1496,8 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
     NOUNROLL for (int base = np_prim; base < npt; base += 64) {
       const int pa = base + lane, pb = pa + 32;
       const int ka = pa < npt ? e.pk_tab[pa] : 0, kb = pb < npt ? e.pk_tab[pb] : 0;
-      const float ba = pa < npt ? e.pb_tab[pa] : -1.0f, bb = pb < npt ? e.pb_tab[pb] : -1.0f;
+      const float* pbt = reinterpret_cast<const float*>(e.pk_tab + npt);
+      const float ba = pa < npt ? pbt[pa] : -1.0f, bb = pb < npt ? pbt[pb] : -1.0f;
       const float* xa1 = e.gxpos[ka & 0xfff];
       const float* xa2 = e.gxpos[(ka >> 12) & 0xfff];
       const float* xb1 = e.gxpos[kb & 0xfff];
@@ -1536,13 +1537,10 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
     EnvS<C>* blk = &e - (threadIdx.x >> 5);
     const int nw = (int)(blockDim.x >> 5);
     const int nj = nsurv < LS_MAXJOB ? nsurv : LS_MAXJOB;
-    // (njobs is double-buffered by call parity: when no env of the block has a job there is no second barrier, and a warp
-    //  that runs ahead into its next evaluation must not overwrite the count a slower warp is still about to read)
-    const int par = e.job_par & 1;
-    __syncwarp();
-    LANE0 { e.njobs[par] = nj; e.job_par = par ^ 1; }
+    LANE0 { e.njobs = nj; }
     __syncthreads();
-    int incl = lane < nw ? blk[lane].njobs[par] : 0;
+    int incl = lane < nw ? blk[lane].njobs : 0;
+    __syncthreads();        // (everybody has read the counts: a warp that runs ahead may publish its next evaluation's count)
     const int mine = incl;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {

@@ -63,7 +63,7 @@ struct EmuT : EmuBase {
     for (int g = 0; g < m.ng; g++) for (int k = 0; k < 3; k++) gx[3 * g + k] = e.gxpos[g][k];
     for (int b = 0; b < m.nb; b++) { for (int k = 0; k < 3; k++) bx[7 * b + k] = e.xpos[b][k]; for (int k = 0; k < 4; k++) bx[7 * b + 3 + k] = e.xquat[b][k]; }
   }
-  void bind_prm() override { e.prm = hm.default_row.data(); e.pk_tab = m.pair_packed; e.pb_tab = m.pair_bound; c_models[0] = m; init_workspace(0, e); }
+  void bind_prm() override { e.prm = hm.default_row.data(); e.pk_tab = m.pair_packed; c_models[0] = m; init_workspace(0, e); }
 };
 
 extern "C" {
