@@ -100,7 +100,7 @@ def _ptr(t):
 class CudaEngine:
     """n_envs independent worlds of one compiled model on one GPU; all I/O are torch.cuda tensors."""
 
-    def __init__(self, model_blobs, task_blobs, n_envs, device=0, seed=0, env_id_offset=0):
+    def __init__(self, model_blobs, task_blobs, n_envs, device=0, seed=0, env_id_offset=0, warps_per_block=None):
         import torch
         if not torch.cuda.is_available():
             raise EngineUnavailable("no CUDA device visible: the locosim engine has no CPU path")
@@ -113,11 +113,30 @@ class CudaEngine:
         ti = np.ascontiguousarray(ti, dtype=np.int32)
         tr = np.ascontiguousarray(tr, dtype=np.float64)
         h = ctypes.c_void_p()
-        rc = self.lib.locosim_create(mi.ctypes.data, len(mi), mr.ctypes.data, len(mr), ti.ctypes.data, len(ti),
-                                     tr.ctypes.data, len(tr), int(n_envs), int(device), int(seed), int(env_id_offset),
-                                     ctypes.byref(h))
+        # launch geometry: envs (= warps) per block; None = the engine's own choice (the largest block that keeps the most
+        # envs resident per SM). Smaller blocks let several engines share an SM (MixedBatch). Scheduling only.
+        prev = os.environ.get("LOCOSIM_WPB")
+        if warps_per_block is not None:
+            os.environ["LOCOSIM_WPB"] = str(int(warps_per_block))
+        try:
+            rc = self._create(mi, mr, ti, tr, n_envs, device, seed, env_id_offset, h)
+        finally:
+            if warps_per_block is not None:
+                if prev is None:
+                    os.environ.pop("LOCOSIM_WPB", None)
+                else:
+                    os.environ["LOCOSIM_WPB"] = prev
         if rc != 0:
             raise RuntimeError("locosim_create failed: %s" % self.lib.locosim_last_error(None).decode())
+        self._finish_init(h, n_envs, device)
+
+    def _create(self, mi, mr, ti, tr, n_envs, device, seed, env_id_offset, h):
+        return self.lib.locosim_create(mi.ctypes.data, len(mi), mr.ctypes.data, len(mr), ti.ctypes.data, len(ti),
+                                       tr.ctypes.data, len(tr), int(n_envs), int(device), int(seed), int(env_id_offset),
+                                       ctypes.byref(h))
+
+    def _finish_init(self, h, n_envs, device):
+        torch = self.torch
         self.h = h
         self.device = torch.device("cuda", device)
         self.n_envs = int(n_envs)

@@ -137,7 +137,7 @@ class LocoEnv:
                  init_step_no=None, timestep=0.001, use_foot_forces=False, default_camera_mode="follow",
                  use_absorbing_states=True, domain_randomization_config=None, parallel_dom_rand=True,
                  N_worker_per_xml_dom_rand=4, num_envs=None, device="cuda:0", seed=0, env_id_offset=0,
-                 compiled_model=None, copy_outputs=True, convex_collisions=True, **viewer_params):
+                 compiled_model=None, copy_outputs=True, convex_collisions=True, warps_per_block=None, **viewer_params):
         if type(xml_handles) != list:
             xml_handles = [xml_handles]
         self._xml_handles = xml_handles
@@ -201,6 +201,8 @@ class LocoEnv:
         # convex_collisions=False drops the mesh-mesh / box-mesh candidate pairs (bone against bone: mjc_Convex / MPR) from the
         # engine's pair table: faster (HumanoidTorque: ~3x), but not what the reference simulates. Default: on.
         self._convex_collisions = bool(convex_collisions)
+        # launch geometry of the step kernel (envs per block); None = the engine's choice. Scheduling only (MixedBatch uses it)
+        self._warps_per_block = warps_per_block
         self._engine = None
         self._obs = None
 
@@ -379,7 +381,8 @@ class LocoEnv:
             dev = torch.device(self._device)
             self._engine = CudaEngine(modelpack.pack(self._model, convex_pairs=self._convex_collisions),
                                       self.task_spec().pack(), self.num_envs,
-                                      device=dev.index or 0, seed=self._seed, env_id_offset=self._env_id_offset)
+                                      device=dev.index or 0, seed=self._seed, env_id_offset=self._env_id_offset,
+                                      warps_per_block=self._warps_per_block)
             if self._domain_rand_config is not None:
                 self._engine.set_param_pool(self.domain_randomization_pool())
             elif len(self._models) > 1 or len(self._model_user_features[0]):
