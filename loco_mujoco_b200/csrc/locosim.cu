@@ -390,6 +390,14 @@ static int setup_cfg(locosim_handle* h) {
   for (int w = 16; w >= 1; w--) {
     if (envs_per_sm(w) == best_env) { best = w; break; }
   }
+  {
+    // A batch that does not even give every SM one full block is spread over all SMs with smaller blocks: one block per SM
+    // beats half of the SMs running 14-15 warps (measured, BASELINE config 4: Atlas.walk 1024 envs as 147 blocks of 7
+    // instead of 74 of 14, next to Talos.walk 1024: 634 k -> 834 k env-steps/s; 5 or 10 warps per block are both worse).
+    int n_sm = 0;
+    CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+    if (n_sm > 0 && (h->n_envs + best - 1) / best < n_sm) { int w = (h->n_envs + n_sm - 1) / n_sm; best = w < 1 ? 1 : (w < best ? w : best); }
+  }
   if (getenv("LOCOSIM_WPB")) { int w = atoi(getenv("LOCOSIM_WPB")); if (w >= 1 && w <= 16 && w * per_env <= dev_max) best = w; }
   if (getenv("LOCOSIM_SYNC")) h->sync_substeps = atoi(getenv("LOCOSIM_SYNC"));
   h->regroup = 1;

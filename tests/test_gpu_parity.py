@@ -100,8 +100,11 @@ def test_foot_forces_match_oracle(oracle, bundled_only, task):
 def _batched_vs_oracle(oracle, task, n_steps=None, **kw):
     n, default_steps = (96, 3) if task.startswith("UnitreeA1") else (48, 2)
     n_steps = default_steps if n_steps is None else n_steps
-    env = make_env(task, num_envs=n, seed=5, **kw)
+    # (12 envs per block: small batches would otherwise get one env per block - the engine spreads them over the SMs - and
+    #  the lock-step barriers / the block-shared MPR job queue would not be exercised against the oracle)
+    env = make_env(task, num_envs=n, seed=5, warps_per_block=8 if task.startswith("UnitreeG1") else 12, **kw)
     eng = env._get_engine()
+    assert eng.launch_info()["warps_per_block"] in (8, 12)
     mb, tb = blobs(env)
     rng = np.random.RandomState(0)
     tr = rng.randint(0, env.trajectories.number_of_trajectories, n).astype(np.int32)
