@@ -396,7 +396,10 @@ static int setup_cfg(locosim_handle* h) {
     // instead of 74 of 14, next to Talos.walk 1024: 634 k -> 834 k env-steps/s; 5 or 10 warps per block are both worse).
     int n_sm = 0;
     CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
-    if (n_sm > 0 && (h->n_envs + best - 1) / best < n_sm) { int w = (h->n_envs + n_sm - 1) / n_sm; best = w < 1 ? 1 : (w < best ? w : best); }
+    // LOCOSIM_WPB=-1 keeps the largest block (MixedBatch: the lighter members of a mixed batch; 7-warp blocks of two different
+    // kernels on every SM lost 0.7 ms per step to the cold start after an L2 flush, Atlas spread + Talos in full blocks did not).
+    const bool keep = getenv("LOCOSIM_WPB") && atoi(getenv("LOCOSIM_WPB")) == -1;
+    if (!keep && n_sm > 0 && (h->n_envs + best - 1) / best < n_sm) { int w = (h->n_envs + n_sm - 1) / n_sm; best = w < 1 ? 1 : (w < best ? w : best); }
   }
   if (getenv("LOCOSIM_WPB")) { int w = atoi(getenv("LOCOSIM_WPB")); if (w >= 1 && w <= 16 && w * per_env <= dev_max) best = w; }
   if (getenv("LOCOSIM_SYNC")) h->sync_substeps = atoi(getenv("LOCOSIM_SYNC"));

@@ -476,6 +476,14 @@ class LocoEnv:
         self._obs = out.clone() if self._copy_outputs else out
         return self._obs
 
+    def set_launch_geometry(self, warps_per_block):
+        """Envs (= warps) per block of the step kernel: None = the engine's choice, -1 = always the largest block, k = k.
+        Scheduling only. The engine is rebuilt (state lost): call before reset()."""
+        self._warps_per_block = warps_per_block
+        if getattr(self, "_engine", None) is not None:
+            self._engine.close() if hasattr(self._engine, "close") else None
+            self._engine = None
+
     def _reset_rotation_angle(self):
         """Drop-in single-env reset: host-drawn rotation angle of setup_random_rot envs (None: env has no such option)."""
         return None

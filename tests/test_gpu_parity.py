@@ -158,6 +158,30 @@ def _batched_vs_oracle(oracle, task, n_steps=None, **kw):
     return env
 
 
+def test_mixed_batch_equals_separate_engines(bundled_only):
+    """MixedBatch (BASELINE config 4: several robots on one GPU, own streams, balanced launch geometry) is scheduling only:
+    every member behaves bit for bit like the same env stepped on its own."""
+    from loco_mujoco_b200.parallel import MixedBatch
+    n, steps = 48, 12
+    mb = MixedBatch([("Atlas.walk.real", n, {}), ("Talos.walk.real", n, {})], device="cuda:0", seed=3, debug=True)
+    assert hasattr(mb, "calibration_ms") and len(mb.calibration_ms) == 2
+    geo = [e.launch_info()["warps_per_block"] for e in mb.engines]
+    assert min(geo) == 1 and max(geo) > 1, geo            # the slower member is spread over the SMs, the other keeps full blocks
+    solo = [make_env("Atlas.walk", num_envs=n, seed=3, env_id_offset=0, warps_per_block=6),
+            make_env("Talos.walk", num_envs=n, seed=3, env_id_offset=n, warps_per_block=6)]
+    o_mb, o_solo = mb.reset(), [e.reset() for e in solo]
+    for a, b in zip(o_mb, o_solo):
+        assert torch.equal(a, b)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for _ in range(steps):
+        acts = [(torch.rand((n, e.action_dim), generator=g) * 2 - 1).cuda() for e in mb.engines]
+        out = mb.step(acts)
+        torch.cuda.synchronize()
+        for i, env in enumerate(solo):
+            o, r, d, info = env.step(acts[i])
+            assert torch.equal(out[i][0], o) and torch.equal(out[i][1], r) and torch.equal(out[i][2], d)
+
+
 def test_sharded_envs_equal_single_batch(bundled_only):
     """Multi-GPU sharding contract: env i of a shard with env_id_offset=o behaves exactly like env o+i of one batch."""
     n, steps = 64, 25

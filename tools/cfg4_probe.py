@@ -1,7 +1,5 @@
 """Probe of BASELINE config 4 (Atlas.walk + Talos.walk with domain randomisation, 1024 + 1024 envs on one GPU): launch
-geometry variants (warps per block per engine) -> env-steps/s.   (under gpurun)   python tools/cfg4_probe.py"""
-import argparse
-import json
+geometry variants (warps per block per engine) -> per-step time over a long rollout.   (under gpurun)"""
 import os
 import sys
 
@@ -13,17 +11,32 @@ import bench  # noqa: E402
 
 def main():
     import torch
-    a = argparse.Namespace(steps=40, warmup=5, no_flush=False, gather_chunk=0)
     dr = lambda robot: "domain_randomization_%s.yaml" % robot
     members = [("Atlas.walk", 1024, {"domain_randomization_config": dr("atlas")}),
                ("Talos.walk", 1024, {"domain_randomization_config": dr("talos")})]
-    for label, wpbs in [("default", (None, None)), ("7/7", (7, 7)), ("7/15", (7, None)), ("5/5", (5, 5)), ("7/8", (7, 8)), ("4/5", (4, 5)),
-                        ("10/5", (10, 5)), ("14/7", (None, 7))]:
+    T = 260
+    for label, wpbs, flush_on in [("auto(7/7) flush", (None, None), True), ("14/15 flush", (14, 15), True), ("auto(7/7) noflush", (None, None), False),
+                                  ("14/15 noflush", (14, 15), False), ("7/15 flush", (7, 15), True)]:
         mem = [(t, n, dict(kw, warps_per_block=w)) for (t, n, kw), w in zip(members, wpbs)]
         wl = bench.Workload("cfg4", mem, 0, 1, 0)
-        r = wl.measure(a, 0, False)
-        print(label, [e.launch_info() for e in wl.engines], "%.0f env-steps/s, %.3f ms" % (r["value"], r["ms_per_step"]), flush=True)
-        del wl
+        dev = wl.dev
+        wl.batch.reset()
+        gen = torch.Generator(device=dev).manual_seed(1234)
+        actions = [torch.rand((T, e.n_envs, e.action_dim), device=dev, generator=gen) * 2 - 1 for e in wl.engines]
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(T)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(T)]
+        for k in range(T):
+            if flush_on:
+                flush.fill_(k & 0xff)
+            ev0[k].record()
+            wl.step([x[k] for x in actions])
+            ev1[k].record()
+        torch.cuda.synchronize()
+        ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+        win = ["%.2f" % (sum(ms[i:i + 20]) / 20) for i in range(0, T, 20)]
+        print(label, [e.launch_info()["warps_per_block"] for e in wl.engines], "ms/step per 20-step window:", " ".join(win), flush=True)
+        del wl, flush
         torch.cuda.empty_cache()
 
 
