@@ -8,7 +8,7 @@ Headline workload (BASELINE.json configs[1]): UnitreeA1.simple, 4096 envs per GP
 from the mini-dataset table; a "step" is one LocoEnv.step() of the whole batch (= 10 MuJoCo sub-steps per env).
 The same JSON line carries, under "configs", the other single-box BASELINE configs measured the same way in the same
 run: HumanoidTorque.run @ 4096 envs/GPU (config 3) and the mixed Atlas.walk + Talos.walk batch with domain randomisation
-@ 1024 + 1024 envs/GPU (config 4).  One JSON line on stdout (rank 0).  DESIGN.md "Measurement" explains every field.
+@ 1024 + 1024 envs/GPU (config 4: two engines, each spread over all SMs, back to back).  One JSON line on stdout (rank 0).  DESIGN.md "Measurement" explains every field.
 """
 import argparse
 import json
@@ -440,8 +440,8 @@ def main():
         dr = lambda robot: "domain_randomization_%s.yaml" % robot
         plan = [("config 3: HumanoidTorque.run, 4096 envs/GPU (reference default TargetVelocityReward(2.5); the reference has "
                  "no mocap-tracking reward, SURVEY F7)", [("HumanoidTorque.run", 4096, {})]),
-                ("config 4: Atlas.walk + Talos.walk mixed batch with domain randomisation, 1024 + 1024 envs/GPU, two engines "
-                 "on two streams (shipped YAMLs, pre-built seeded pools: tools/build_dr_pools.py)",
+                ("config 4: Atlas.walk + Talos.walk mixed batch with domain randomisation, 1024 + 1024 envs/GPU, two engines, "
+                 "each spread over all SMs, launched back to back (shipped YAMLs, pre-built seeded pools: tools/build_dr_pools.py)",
                  [("Atlas.walk", 1024, {"domain_randomization_config": dr("atlas")}),
                   ("Talos.walk", 1024, {"domain_randomization_config": dr("talos")})])]
         for name, members in plan:

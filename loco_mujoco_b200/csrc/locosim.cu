@@ -116,9 +116,10 @@ __global__ void __launch_bounds__(512, 1) step_kernel(int ms, DevTask t, SolverO
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int key_mode = key_mode_in & 0xffff;
   if (stage_bytes > 0) {
-    // Optional (LOCOSIM_STAGE=1): the candidate-pair table of the mid-phase (packed geom pair + bound, read 349 / 769 entries
-    // per dynamics evaluation) is staged once per block into the shared memory behind the per-env working sets by ONE TMA
-    // bulk copy (cp.async.bulk global -> shared::cta, completion on an mbarrier); EnvS::pk_tab / pb_tab point to it.
+    // LOCOSIM_STAGE (default on where it fits): the table of the PRIMITIVE candidate pairs of the mid-phase (packed geom pair +
+    // bound; UnitreeA1: 357 entries read in every dynamics evaluation by every warp) is staged once per block into the shared
+    // memory behind the per-env working sets by ONE TMA bulk copy (cp.async.bulk global -> shared::cta, completion on an
+    // mbarrier); EnvS::pk_tab points to it, DevModel::pk_n is its entry count.
     unsigned char* dst = smem_raw + (size_t)(blockDim.x >> 5) * sizeof(EnvS<C>);
     const unsigned dst_a = (unsigned)__cvta_generic_to_shared(dst);
     const unsigned bar_a = dst_a + (unsigned)stage_bytes;
@@ -429,18 +430,21 @@ static int setup_cfg(locosim_handle* h) {
   // Default on wherever the table fits next to the per-env working sets (A1, Talos; not the RK4 configurations): A1 4096 envs
   // 2.7825 -> 2.7653 ms per step (+0.6 %, two alternating runs each). LOCOSIM_STAGE=0 turns it off.
   if (!getenv("LOCOSIM_STAGE") || atoi(getenv("LOCOSIM_STAGE")) > 0) {
-    const int np = h->hm.np;
-    const int bytes = (2 * np * 4 + 15) & ~15;                   // np packed pairs directly followed by np bounds (as in the model)
+    // the PRIMITIVE part of the table (the lean loop over the convex part streams the model's table from L2)
+    const int np = h->hm.np_prim;
+    const int bytes = (2 * np * 4 + 15) & ~15;                   // np packed pairs directly followed by np bounds
     if (np > 0 && h->smem + bytes + 16 <= dev_max) {
       CK(cudaMalloc((void**)&h->d_stage, bytes));
       CK(cudaMemset(h->d_stage, 0, bytes));
       CK(cudaMemcpy(h->d_stage, h->dm.pair_packed, 4 * np, cudaMemcpyDeviceToDevice));
       CK(cudaMemcpy(h->d_stage + 4 * np, h->dm.pair_bound, 4 * np, cudaMemcpyDeviceToDevice));
+      h->dm.pk_n = np;
+      CK(cudaMemcpyToSymbol(c_models, &h->dm, sizeof(DevModel), sizeof(DevModel) * h->slot));
       h->stage_bytes = bytes;
     }
   }
-  CK(cudaFuncSetAttribute(step_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          h->smem + (h->stage_bytes ? h->stage_bytes + 16 : 0)));
+  // (a property of the FUNCTION, shared by every handle of this instantiation whatever its block size: always the device maximum)
+  CK(cudaFuncSetAttribute(step_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev_max));
   return 0;
 }
 

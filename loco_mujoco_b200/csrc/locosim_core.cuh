@@ -94,6 +94,7 @@ struct DevModel {
   float timestep, gravity[3], impratio, tolerance, meaninertia;
   int has_damping;
   int np_prim;               // the first np_prim candidate pairs are primitive (plane / sphere / capsule routines), the rest general convex
+  int pk_n;                  // entries of the table EnvS::pk_tab points to (np: the model's; np_prim: the block's TMA-staged copy)
 #define X(name, cnt) const int* name;
   LOCOSIM_MP_INT_FIELDS(X)
 #undef X
@@ -197,8 +198,8 @@ struct alignas(16) EnvS {
   float goal[4];
   float grf[3 * LS_MAX_GRF];   // use_foot_forces: per foot group, contact-frame force summed over the sub-steps
   const float* prm;        // this env's row of the parameter pool
-  const int* pk_tab;       // candidate-pair table of the mid-phase: the model's (global) or the block's TMA-staged copy (shared):
-                           // np packed pairs, directly followed by np bounds (float)
+  const int* pk_tab;       // table of the PRIMITIVE candidate pairs of the mid-phase: the model's (global) or the block's TMA-staged
+                           // copy (shared): DevModel::pk_n packed pairs, directly followed by pk_n bounds (float)
 };
 #define PRM(field) (e.prm + m.po_##field)
 #define ROW_TYPE(ti) ((ti) & 255)
@@ -1116,7 +1117,7 @@ LS_DEV bool pair_filter(const int ms, const EnvS<C>& e, int p, int pk) {
   const DevModel& m = c_models[ms];
   const int g1 = pk & 0xfff, g2 = (pk >> 12) & 0xfff;
   const float d[3] = {e.gxpos[g2][0] - e.gxpos[g1][0], e.gxpos[g2][1] - e.gxpos[g1][1], e.gxpos[g2][2] - e.gxpos[g1][2]};
-  const float bound = reinterpret_cast<const float*>(e.pk_tab + m.np)[p];
+  const float bound = reinterpret_cast<const float*>(e.pk_tab + m.pk_n)[p];
   if (pk & (1 << 24)) {
     float mat1[9];
     geom_mat(ms, e, g1, mat1);
@@ -1495,9 +1496,8 @@ LS_FN void collision(const int ms, EnvS<C>& e) {
     const int npt = m.np;
     NOUNROLL for (int base = np_prim; base < npt; base += 64) {
       const int pa = base + lane, pb = pa + 32;
-      const int ka = pa < npt ? e.pk_tab[pa] : 0, kb = pb < npt ? e.pk_tab[pb] : 0;
-      const float* pbt = reinterpret_cast<const float*>(e.pk_tab + npt);
-      const float ba = pa < npt ? pbt[pa] : -1.0f, bb = pb < npt ? pbt[pb] : -1.0f;
+      const int ka = pa < npt ? m.pair_packed[pa] : 0, kb = pb < npt ? m.pair_packed[pb] : 0;      // (model table: global / L2)
+      const float ba = pa < npt ? m.pair_bound[pa] : -1.0f, bb = pb < npt ? m.pair_bound[pb] : -1.0f;
       const float* xa1 = e.gxpos[ka & 0xfff];
       const float* xa2 = e.gxpos[(ka >> 12) & 0xfff];
       const float* xb1 = e.gxpos[kb & 0xfff];

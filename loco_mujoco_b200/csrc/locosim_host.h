@@ -146,7 +146,7 @@ static inline void bind_model(DevModel& m, const HostModel& h, const int* ibase,
   m.integrator = h.integrator; m.cone = h.cone; m.iterations = h.iterations; m.nlevel = h.nlevel; m.nfric = h.nfric;
   m.timestep = h.timestep; m.gravity[0] = h.gravity[0]; m.gravity[1] = h.gravity[1]; m.gravity[2] = h.gravity[2];
   m.impratio = h.impratio; m.tolerance = h.tolerance; m.meaninertia = h.meaninertia; m.has_damping = h.has_damping;
-  m.np_prim = h.np_prim;
+  m.np_prim = h.np_prim; m.pk_n = h.np;
   const int nb = h.nb, nv = h.nv, ng = h.ng, nu = h.nu, np = h.np, nm = h.nm;
   const int* ip = ibase;
   const float* rp = rbase;

@@ -118,14 +118,22 @@ class RolloutGather:
 
 class MixedBatch:
     """Heterogeneous batch on ONE GPU (BASELINE config 4: Atlas.walk + Talos.walk): the robots differ in nv, observation
-    size and integrator, i.e. in the step-kernel instantiation, so every member is its own homogeneous engine; the
-    members' kernels are launched on separate CUDA streams and share the SMs (each sub-batch alone does not fill them).
+    size and integrator, i.e. in the step-kernel instantiation, so every member is its own homogeneous engine.
 
         mb = MixedBatch([("Atlas.walk.real", 1024, {...}), ("Talos.walk.real", 1024, {...})], device="cuda:0", seed=0)
         obs = mb.reset();  results = mb.step([a_atlas, a_talos])      # lists, one entry per member
+
+    Scheduling (results do not depend on it). A sub-batch that cannot give every SM a full block is spread by its engine
+    over all SMs in smaller blocks (1024 envs -> 147 blocks of 7), so each member alone already occupies the whole GPU and
+    the members' kernels are simply enqueued one after the other on the caller's stream (`concurrent=False`, default).
+    Measured for config 4 on B200 (ms per step, L2 flushed between steps; profiles/README.md): full blocks on two streams
+    3.27 (Atlas' 74 blocks of 14 warps leave half of the SMs to Talos, which is done after 0.8 ms); spread blocks on two
+    streams 2.47 OR 3.0-3.2, depending on which kernel the hardware happens to place first (if Talos' blocks grab their
+    SMs first, Atlas' blocks pair up on the remaining ones); spread blocks back to back on one stream: the fast mode,
+    deterministically.  `concurrent=True` keeps one stream per member (useful when the members are tiny).
     """
 
-    def __init__(self, members, device="cuda:0", seed=0, env_id_offset=0, balance=True, **common):
+    def __init__(self, members, device="cuda:0", seed=0, env_id_offset=0, concurrent=False, **common):
         from . import LocoEnv
         self.device = torch.device(device)
         self.envs, off = [], int(env_id_offset)
@@ -133,46 +141,18 @@ class MixedBatch:
             kw = dict(common, **(kw or {}))
             self.envs.append(LocoEnv.make(task_id, num_envs=int(n), device=str(self.device), seed=seed, env_id_offset=off, **kw))
             off += int(n)
-        if balance and len(self.envs) > 1:
-            self._balance()
         self.engines = [e._get_engine() for e in self.envs]
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.envs]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.envs] if concurrent else None
         self.num_envs = sum(e.num_envs for e in self.envs)
-
-    def _balance(self, steps=6):
-        """Launch geometry of a mixed batch (scheduling only, results do not depend on it): every member is timed alone for a
-        few random-action steps; the SLOWEST one keeps the engine's own choice (a sub-batch that does not give every SM a
-        full block is spread over all SMs in smaller blocks), the lighter ones run in full blocks on few SMs and finish
-        early.  Measured on BASELINE config 4 (Atlas.walk 1024 + Talos.walk 1024, ms per step with the L2 flushed between
-        steps): both in full blocks 3.27, both spread 3.18, Atlas spread + Talos full 2.46."""
-        cost = []
-        for env in self.envs:
-            if getattr(env, "_warps_per_block", None) is not None:
-                return                                   # the caller chose a geometry: leave everything alone
-            eng = env._get_engine()
-            eng.reset()
-            a = torch.rand((eng.n_envs, eng.action_dim), device=self.device) * 2 - 1
-            for _ in range(3):
-                eng.step(a, auto_reset=True)
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-            for _ in range(steps):
-                eng.step(a, auto_reset=True)
-            t1.record()
-            torch.cuda.synchronize(self.device)
-            cost.append(t0.elapsed_time(t1))
-        slowest = max(range(len(cost)), key=lambda i: cost[i])
-        for i, env in enumerate(self.envs):
-            # every engine is rebuilt (fresh episode counters: the calibration must not shift the envs' random streams);
-            # -1 = always the largest block, None = the engine's own choice
-            env.set_launch_geometry(None if i == slowest else -1)
-        self.calibration_ms = [c / steps for c in cost]
 
     def reset(self):
         return [e.reset() for e in self.envs]
 
     def step(self, actions, packed=None):
         """actions: one [n_i, nu_i] tensor per member. All members are enqueued before anything is awaited."""
+        if self.streams is None:
+            return [eng.step(actions[i], auto_reset=True, packed=None if packed is None else packed[i])
+                    for i, eng in enumerate(self.engines)]
         cur = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(cur)

@@ -158,15 +158,15 @@ def _batched_vs_oracle(oracle, task, n_steps=None, **kw):
     return env
 
 
-def test_mixed_batch_equals_separate_engines(bundled_only):
-    """MixedBatch (BASELINE config 4: several robots on one GPU, own streams, balanced launch geometry) is scheduling only:
-    every member behaves bit for bit like the same env stepped on its own."""
+@pytest.mark.parametrize("concurrent", [False, True])
+def test_mixed_batch_equals_separate_engines(bundled_only, concurrent):
+    """MixedBatch (BASELINE config 4: several robots on one GPU) is scheduling only: every member behaves bit for bit like
+    the same env stepped on its own, whatever the launch geometry (spread one-env blocks vs 6 envs per block) and whether
+    the members share a stream or not."""
     from loco_mujoco_b200.parallel import MixedBatch
     n, steps = 48, 12
-    mb = MixedBatch([("Atlas.walk.real", n, {}), ("Talos.walk.real", n, {})], device="cuda:0", seed=3, debug=True)
-    assert hasattr(mb, "calibration_ms") and len(mb.calibration_ms) == 2
-    geo = [e.launch_info()["warps_per_block"] for e in mb.engines]
-    assert min(geo) == 1 and max(geo) > 1, geo            # the slower member is spread over the SMs, the other keeps full blocks
+    mb = MixedBatch([("Atlas.walk.real", n, {}), ("Talos.walk.real", n, {})], device="cuda:0", seed=3, debug=True, concurrent=concurrent)
+    assert [e.launch_info()["warps_per_block"] for e in mb.engines] == [1, 1]      # 48 envs: spread over the SMs
     solo = [make_env("Atlas.walk", num_envs=n, seed=3, env_id_offset=0, warps_per_block=6),
             make_env("Talos.walk", num_envs=n, seed=3, env_id_offset=n, warps_per_block=6)]
     o_mb, o_solo = mb.reset(), [e.reset() for e in solo]
