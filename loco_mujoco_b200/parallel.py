@@ -124,16 +124,16 @@ class MixedBatch:
         obs = mb.reset();  results = mb.step([a_atlas, a_talos])      # lists, one entry per member
 
     Scheduling (results do not depend on it). A sub-batch that cannot give every SM a full block is spread by its engine
-    over all SMs in smaller blocks (1024 envs -> 147 blocks of 7), so each member alone already occupies the whole GPU and
-    the members' kernels are simply enqueued one after the other on the caller's stream (`concurrent=False`, default).
-    Measured for config 4 on B200 (ms per step, L2 flushed between steps; profiles/README.md): full blocks on two streams
-    3.27 (Atlas' 74 blocks of 14 warps leave half of the SMs to Talos, which is done after 0.8 ms); spread blocks on two
-    streams 2.47 OR 3.0-3.2, depending on which kernel the hardware happens to place first (if Talos' blocks grab their
-    SMs first, Atlas' blocks pair up on the remaining ones); spread blocks back to back on one stream: the fast mode,
-    deterministically.  `concurrent=True` keeps one stream per member (useful when the members are tiny).
+    over all SMs in smaller blocks (1024 envs -> 147 blocks of 7). The members' kernels run on one stream each so that the
+    light member's blocks fill the SMs the heavy member's early-finishing blocks free; which kernel the block scheduler
+    places FIRST decides between two modes (measured for config 4, ms per step: 2.47 if Atlas' blocks go first, 3.0-3.2 if
+    Talos' do; back to back on one stream 3.3; full 14/15-warp blocks 3.27), so the members are timed alone once
+    (`balance=True`) and the slowest one gets the high-priority stream: its blocks are dispatched first whenever both
+    kernels have blocks pending; the lighter members run in full blocks (two spread kernels sharing every SM still hit the slow
+    mode in 1 of 4 runs, spread + full blocks in 0 of 8).
     """
 
-    def __init__(self, members, device="cuda:0", seed=0, env_id_offset=0, concurrent=False, **common):
+    def __init__(self, members, device="cuda:0", seed=0, env_id_offset=0, concurrent=True, balance=True, **common):
         from . import LocoEnv
         self.device = torch.device(device)
         self.envs, off = [], int(env_id_offset)
@@ -141,9 +141,45 @@ class MixedBatch:
             kw = dict(common, **(kw or {}))
             self.envs.append(LocoEnv.make(task_id, num_envs=int(n), device=str(self.device), seed=seed, env_id_offset=off, **kw))
             off += int(n)
+        order = list(range(len(self.envs)))
+        if concurrent and balance and len(self.envs) > 1:
+            cost = self._calibrate()
+            order = sorted(order, key=lambda i: -cost[i])
         self.engines = [e._get_engine() for e in self.envs]
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.envs] if concurrent else None
+        self.launch_order = order                      # heaviest first
+        self.streams = None
+        if concurrent:
+            lo, hi = 0, -1                               # torch: a lower number is a higher priority
+            self.streams = [torch.cuda.Stream(device=self.device, priority=hi if (i == order[0] and len(order) > 1) else lo)
+                            for i in range(len(self.envs))]
         self.num_envs = sum(e.num_envs for e in self.envs)
+
+    def _calibrate(self, steps=6):
+        """ms per step of every member alone (random actions); the engines are rebuilt afterwards so that the calibration does
+        not shift the envs' counter-based random streams."""
+        cost = []
+        for env in self.envs:
+            eng = env._get_engine()
+            eng.reset()
+            a = torch.rand((eng.n_envs, eng.action_dim), device=self.device) * 2 - 1
+            for _ in range(3):
+                eng.step(a, auto_reset=True)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(steps):
+                eng.step(a, auto_reset=True)
+            t1.record()
+            torch.cuda.synchronize(self.device)
+            cost.append(t0.elapsed_time(t1) / steps)
+        slowest = max(range(len(cost)), key=lambda i: cost[i])
+        for i, env in enumerate(self.envs):
+            # every engine is dropped and rebuilt fresh on next use. Geometry: the slowest member keeps the engine's choice (spread),
+            # the lighter ones run in FULL blocks (-1) unless the caller fixed a geometry: two spread kernels sharing every SM
+            # still fell into the slow mode now and then (1 of 4 runs), spread + full blocks never did (0 of 8).
+            wpb = getattr(env, "_warps_per_block", None)
+            env.set_launch_geometry(wpb if (wpb is not None or i == slowest) else -1)
+        self.calibration_ms = cost
+        return cost
 
     def reset(self):
         return [e.reset() for e in self.envs]
@@ -157,10 +193,12 @@ class MixedBatch:
         ready = torch.cuda.Event()
         ready.record(cur)
         out = []
-        for i, (eng, st) in enumerate(zip(self.engines, self.streams)):
+        out = [None] * len(self.engines)
+        for i in self.launch_order:
+            eng, st = self.engines[i], self.streams[i]
             st.wait_event(ready)
             with torch.cuda.stream(st):
-                out.append(eng.step(actions[i], auto_reset=True, packed=None if packed is None else packed[i]))
+                out[i] = eng.step(actions[i], auto_reset=True, packed=None if packed is None else packed[i])
         for st in self.streams:
             cur.wait_stream(st)
         return out
