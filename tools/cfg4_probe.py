@@ -15,8 +15,8 @@ def main():
     members = [("Atlas.walk", 1024, {"domain_randomization_config": dr("atlas")}),
                ("Talos.walk", 1024, {"domain_randomization_config": dr("talos")})]
     T = 260
-    for label, wpbs, flush_on in [("default (spread, priority stream) flush", None, True), ("7/15 flush", (7, 15), True), ("default noflush", None, False),
-                                  ("7/15 flush", (7, 15), True), ("default flush", None, True), ("7/15 noflush", (7, 15), False), ("default flush", None, True)]:
+    print("CUDA_DEVICE_MAX_CONNECTIONS =", os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"))
+    for label, wpbs, flush_on in [("default flush", None, True), ("default flush", None, True), ("7/7 flush", (7, 7), True), ("default flush", None, True)]:
         mem = members if wpbs is None else [(t, n, dict(kw, warps_per_block=w)) for (t, n, kw), w in zip(members, wpbs)]
         wl = bench.Workload("cfg4", mem, 0, 1, 0)
         dev = wl.dev
