@@ -1028,96 +1028,91 @@ LS_DEV void mpr_find_pos(const MprSup* p, float* pos) {
   for (int i = 0; i < 4; i++) for (int k = 0; k < 3; k++) { p1[k] += p[i].v1[k] * b[i]; p2[k] += p[i].v2[k] * b[i]; }
   for (int k = 0; k < 3; k++) pos[k] = (p1[k] * inv + p2[k] * inv) * 0.5f;
 }
-// ccdMPRPenetration: true and (depth, dir, pos) if the inflated geoms intersect
+// ccdMPRPenetration: true and (depth, dir, pos) if the inflated geoms intersect.
+// (Tried and rejected: the same algorithm as ONE loop around ONE inlined support call, to shrink the code a lone warp has to
+//  fetch - the library got 4 % smaller and every robot slower, Atlas.walk, which never calls this function, by 16 %: with
+//  ~220 KB of SASS against 32 KB of instruction cache the LAYOUT of the hot functions matters more than their size.)
 // returns false if the geoms do not intersect; `sep` then holds the last direction tested (a separating direction whenever
-// the search stopped because a support point did not reach past the origin).
-// Written as ONE loop around ONE support call (the phases of libccd's discoverPortal / refinePortal / findPenetration are the
-// states 1-5): a lone warp executes this while its block waits, and with the vertex scan inlined at six call sites the code
-// did not stay in the instruction caches (no_instruction was the top stall of this function); the arithmetic and the
-// order of the support directions are exactly those of the straight-line version (oracle/locosim_ref.c ccd_mpr_penetration).
+// the search stopped because a support point did not reach past the origin)
 LS_FN bool mpr_penetration(const MprScratch* sc, float* depth, float* pdir, float* pos, float* sep) {
   const MprGeom& o1 = sc->g[0];
   const MprGeom& o2 = sc->g[1];
-  MprSup p[4], s;
+  MprSup p[4], v4;
   float dir[3], va[3], vb[3], dot;
+  // ---- discoverPortal ----
   for (int k = 0; k < 3; k++) { p[0].v1[k] = o1.pos[k]; p[0].v2[k] = o2.pos[k]; p[0].v[k] = o1.pos[k] - o2.pos[k]; }
   if (mpr_eq(p[0].v[0], 0.0f) && mpr_eq(p[0].v[1], 0.0f) && mpr_eq(p[0].v[2], 0.0f)) p[0].v[0] += MPR_EPS * 10.0f;
   for (int k = 0; k < 3; k++) dir[k] = -p[0].v[k];
   mpr_normalize(dir);
-  int state = 1, guard = 0, it = 0;
-  NOUNROLL for (;;) {
-    mpr_support(sc, dir, s);
-    if (state <= 4) { sep[0] = dir[0]; sep[1] = dir[1]; sep[2] = dir[2]; }
-    if (state == 1) {                                   // ---- discoverPortal: first point ----
-      p[1] = s;
-      dot = dot3(p[1].v, dir);
-      if (mpr_is_zero(dot) || dot < 0) return false;
-      cross3(dir, p[0].v, p[1].v);
-      if (!(dot3(dir, dir) > 1e-10f * dot3(p[0].v, p[0].v) * dot3(p[1].v, p[1].v))) {      // origin on the segment v0-v1 (relative test)
-        for (int k = 0; k < 3; k++) { pos[k] = 0.5f * (p[1].v1[k] + p[1].v2[k]); pdir[k] = p[1].v[k]; }
-        *depth = sqrtf(dot3(pdir, pdir));
-        if (mpr_is_zero(*depth)) { pdir[0] = pdir[1] = pdir[2] = 0; *depth = 0; }      // touching contact: no normal
-        else mpr_normalize(pdir);
-        return true;
-      }
-      mpr_normalize(dir);
-      state = 2;
-    } else if (state == 2) {                            // ---- second point ----
-      p[2] = s;
-      dot = dot3(p[2].v, dir);
-      if (mpr_is_zero(dot) || dot < 0) return false;
-      for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
-      cross3(dir, va, vb);
-      mpr_normalize(dir);
-      if (dot3(dir, p[0].v) > 0) {
-        const MprSup t = p[1]; p[1] = p[2]; p[2] = t;
-        for (int k = 0; k < 3; k++) dir[k] = -dir[k];
-      }
-      state = 3;
-    } else if (state == 3) {                            // ---- third point: until the portal faces the origin ----
-      p[3] = s;
-      dot = dot3(p[3].v, dir);
-      if (mpr_is_zero(dot) || dot < 0) return false;
-      bool cont = false;
-      cross3(va, p[1].v, p[3].v);
+  mpr_support(sc, dir, p[1]);
+  dot = dot3(p[1].v, dir);
+  sep[0] = dir[0]; sep[1] = dir[1]; sep[2] = dir[2];
+  if (mpr_is_zero(dot) || dot < 0) return false;
+  cross3(dir, p[0].v, p[1].v);
+  if (!(dot3(dir, dir) > 1e-10f * dot3(p[0].v, p[0].v) * dot3(p[1].v, p[1].v))) {      // origin on the segment v0-v1 (relative test)
+    for (int k = 0; k < 3; k++) { pos[k] = 0.5f * (p[1].v1[k] + p[1].v2[k]); pdir[k] = p[1].v[k]; }
+    *depth = sqrtf(dot3(pdir, pdir));
+    if (mpr_is_zero(*depth)) { pdir[0] = pdir[1] = pdir[2] = 0; *depth = 0; }      // touching contact: no normal
+    else mpr_normalize(pdir);
+    return true;
+  }
+  mpr_normalize(dir);
+  mpr_support(sc, dir, p[2]);
+  dot = dot3(p[2].v, dir);
+  sep[0] = dir[0]; sep[1] = dir[1]; sep[2] = dir[2];
+  if (mpr_is_zero(dot) || dot < 0) return false;
+  for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+  cross3(dir, va, vb);
+  mpr_normalize(dir);
+  if (dot3(dir, p[0].v) > 0) {
+    const MprSup t = p[1]; p[1] = p[2]; p[2] = t;
+    for (int k = 0; k < 3; k++) dir[k] = -dir[k];
+  }
+  NOUNROLL for (int guard = 0; guard < 4 * MPR_MAXIT; guard++) {
+    mpr_support(sc, dir, p[3]);
+    dot = dot3(p[3].v, dir);
+    sep[0] = dir[0]; sep[1] = dir[1]; sep[2] = dir[2];
+    if (mpr_is_zero(dot) || dot < 0) return false;
+    bool cont = false;
+    cross3(va, p[1].v, p[3].v);
+    dot = dot3(va, p[0].v);
+    if (dot < 0 && !mpr_is_zero(dot)) { p[2] = p[3]; cont = true; }
+    if (!cont) {
+      cross3(va, p[3].v, p[2].v);
       dot = dot3(va, p[0].v);
-      if (dot < 0 && !mpr_is_zero(dot)) { p[2] = p[3]; cont = true; }
-      if (!cont) {
-        cross3(va, p[3].v, p[2].v);
-        dot = dot3(va, p[0].v);
-        if (dot < 0 && !mpr_is_zero(dot)) { p[1] = p[3]; cont = true; }
-      }
-      if (cont && ++guard < 4 * MPR_MAXIT) {
-        for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
-        cross3(dir, va, vb);
-        mpr_normalize(dir);
-      } else {
-        guard = 0;
-        mpr_portal_dir(p, dir);                         // ---- refinePortal entry: does the portal already enclose the origin? ----
-        dot = dot3(dir, p[1].v);
-        state = (mpr_is_zero(dot) || dot > 0) ? 5 : 4;
-      }
-    } else if (state == 4) {                            // ---- refinePortal ----
-      dot = dot3(s.v, dir);
-      if (!(mpr_is_zero(dot) || dot > 0) || mpr_reach_tolerance(p, s, dir) || guard++ > 4 * MPR_MAXIT) return false;
-      mpr_expand_portal(p, s);
-      mpr_portal_dir(p, dir);
-      dot = dot3(dir, p[1].v);
-      if (mpr_is_zero(dot) || dot > 0) state = 5;
-    } else {                                            // ---- findPenetration ----
-#if !defined(LS_EMULATE)
-      if ((c_debug & 8) && LS_LANE == 0 && it > MPR_MAXIT) atomicAdd(&g_dbg[3], 1ULL);
-#endif
-      if (mpr_reach_tolerance(p, s, dir) || it > MPR_MAXIT) {
-        *depth = sqrtf(mpr_point_tri_dist2(p[1].v, p[2].v, p[3].v, pdir));      // (pdir comes back normalised)
-        if (mpr_is_zero(*depth)) pdir[0] = pdir[1] = pdir[2] = 0;
-        mpr_find_pos(p, pos);
-        return true;
-      }
-      it++;
-      mpr_expand_portal(p, s);
-      mpr_portal_dir(p, dir);
+      if (dot < 0 && !mpr_is_zero(dot)) { p[1] = p[3]; cont = true; }
     }
+    if (!cont) break;
+    for (int k = 0; k < 3; k++) { va[k] = p[1].v[k] - p[0].v[k]; vb[k] = p[2].v[k] - p[0].v[k]; }
+    cross3(dir, va, vb);
+    mpr_normalize(dir);
+  }
+  // ---- refinePortal ----
+  NOUNROLL for (int guard = 0;; guard++) {
+    mpr_portal_dir(p, dir);
+    dot = dot3(dir, p[1].v);
+    if (mpr_is_zero(dot) || dot > 0) break;
+    mpr_support(sc, dir, v4);
+    dot = dot3(v4.v, dir);
+    sep[0] = dir[0]; sep[1] = dir[1]; sep[2] = dir[2];
+    if (!(mpr_is_zero(dot) || dot > 0) || mpr_reach_tolerance(p, v4, dir) || guard > 4 * MPR_MAXIT) return false;
+    mpr_expand_portal(p, v4);
+  }
+  // ---- findPenetr ----
+  NOUNROLL for (int it = 0;; it++) {
+    mpr_portal_dir(p, dir);
+    mpr_support(sc, dir, v4);
+#if !defined(LS_EMULATE)
+    if ((c_debug & 8) && LS_LANE == 0 && it > MPR_MAXIT) atomicAdd(&g_dbg[3], 1ULL);
+    if ((c_debug & 8) && LS_LANE == 0 && !(dir[0] == dir[0])) atomicAdd(&g_dbg[4], 1ULL);
+#endif
+    if (mpr_reach_tolerance(p, v4, dir) || it > MPR_MAXIT) {
+      *depth = sqrtf(mpr_point_tri_dist2(p[1].v, p[2].v, p[3].v, pdir));      // (pdir comes back normalised)
+      if (mpr_is_zero(*depth)) pdir[0] = pdir[1] = pdir[2] = 0;
+      mpr_find_pos(p, pos);
+      return true;
+    }
+    mpr_expand_portal(p, v4);
   }
 }
 
