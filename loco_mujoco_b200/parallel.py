@@ -133,9 +133,10 @@ class MixedBatch:
     mode in 1 of 4 runs, spread + full blocks in 0 of 8).
     """
 
-    def __init__(self, members, device="cuda:0", seed=0, env_id_offset=0, concurrent=True, balance=True, **common):
+    def __init__(self, members, device="cuda:0", seed=0, env_id_offset=0, concurrent=True, balance=True, stagger_us=40.0, **common):
         from . import LocoEnv
         self.device = torch.device(device)
+        self.stagger_cycles = int(stagger_us * 2000) if (concurrent and balance) else 0      # (~2 GHz SM clock)
         self.envs, off = [], int(env_id_offset)
         for task_id, n, kw in members:
             kw = dict(common, **(kw or {}))
@@ -194,10 +195,14 @@ class MixedBatch:
         ready.record(cur)
         out = []
         out = [None] * len(self.engines)
-        for i in self.launch_order:
+        for k, i in enumerate(self.launch_order):
             eng, st = self.engines[i], self.streams[i]
             st.wait_event(ready)
             with torch.cuda.stream(st):
+                if k > 0 and self.stagger_cycles > 0:
+                    # the lighter members start a few tens of microseconds after the heaviest one, so that ITS blocks are on the
+                    # SMs first (its one-block regrouping kernel has to finish before its step kernel can start)
+                    torch.cuda._sleep(self.stagger_cycles)
                 out[i] = eng.step(actions[i], auto_reset=True, packed=None if packed is None else packed[i])
         for st in self.streams:
             cur.wait_stream(st)

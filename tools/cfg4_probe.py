@@ -15,8 +15,7 @@ def main():
     members = [("Atlas.walk", 1024, {"domain_randomization_config": dr("atlas")}),
                ("Talos.walk", 1024, {"domain_randomization_config": dr("talos")})]
     T = 260
-    print("CUDA_DEVICE_MAX_CONNECTIONS =", os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"))
-    for label, wpbs, flush_on in [("default flush", None, True), ("default flush", None, True), ("7/7 flush", (7, 7), True), ("default flush", None, True)]:
+    for label, wpbs, flush_on in [("default flush", None, True), ("default flush", None, True), ("default noflush", None, False)]:
         mem = members if wpbs is None else [(t, n, dict(kw, warps_per_block=w)) for (t, n, kw), w in zip(members, wpbs)]
         wl = bench.Workload("cfg4", mem, 0, 1, 0)
         dev = wl.dev
