@@ -162,9 +162,9 @@ class HumanoidTorque4Ages(BaseHumanoid):
     """HumanoidTorque scaled to one of four body sizes (base_humanoid_4_ages.py:28-105,243-277,305-358): 0.4 (infant),
     0.6, 0.8, 1.0 (adult); the 2-bit env id is appended to the observation and scales the default reward's target.
 
-    Modes "1".."4" (one scaling) are built. Mode "all" mixes four models of DIFFERENT kinematics (body offsets, mesh and
-    foot sizes, gears) in one env; the engine's multi-model mechanism only swaps inertial / joint parameters, so a mixed
-    batch needs one engine per scaling (use four envs) and is not offered as a single env."""
+    Modes "1".."4" (one scaling) are this class. Mode "all" mixes four models of DIFFERENT kinematics (body offsets, mesh and
+    foot sizes, gears) in one env; the engine's multi-model mechanism only swaps inertial / joint parameters, so mode "all"
+    is a composite of four single-scaling envs, one engine each: `HumanoidTorque4AgesAll` below."""
     valid_task_confs = ValidTaskConf(tasks=["walk", "run"], modes=["all", "1", "2", "3", "4"], data_types=["real", "perfect"])
     _default_scalings = [0.4, 0.6, 0.8, 1.0]
     _hidable_obs = ("positions", "velocities", "foot_forces", "env_type")
@@ -223,7 +223,7 @@ class HumanoidTorque4Ages(BaseHumanoid):
         if dataset_type != "real":
             raise NotImplementedError("perfect datasets are not shipped (network download in the reference)")
         if mode == "all":
-            raise NotImplementedError("mode 'all' (four kinematically different models in one env): create one env per mode")
+            return HumanoidTorque4AgesAll(task, dataset_type=dataset_type, debug=debug, **kwargs)
         scaling = cls._default_scalings[int(mode) - 1]
         reward_type = kwargs.pop("reward_type", "multi_target_velocity")
         reward_params = kwargs.pop("reward_params", dict(target_velocity=1.25 if task == "walk" else 2.5))
@@ -246,3 +246,90 @@ class HumanoidTorque4Ages(BaseHumanoid):
     @staticmethod
     def generate(task="walk", mode="all", dataset_type="real", **kwargs):
         return HumanoidTorque4Ages._generate4(task, mode, dataset_type, **kwargs)
+
+
+class HumanoidTorque4AgesAll:
+    """HumanoidTorque4Ages, mode "all" (base_humanoid_4_ages.py:28-105,107-150; humanoids.py:855-892): at the beginning of each
+    episode one of the four humanoids (scalings 0.4 / 0.6 / 0.8 / 1.0) is drawn, then a start state from THAT humanoid's
+    trajectories. The four models differ in kinematics, so this is a composite of the four single-scaling envs (one engine
+    each); the trajectories of `..._POMDP_all.npz` are the four single-scaling datasets in scaling order (default
+    `scaling_trajectory_map`), which is what the sub-envs load.
+
+    Drop-in single env (num_envs omitted): the reference's semantics and legacy numpy RNG draw order - model
+    (base.py:187-191), trajectory within the model's range (base_humanoid_4_ages.py:132-136), sample (trajectory.py:253-259);
+    reproduces the reference goldens HumanoidTorque4Ages.{walk,run}.all.
+    Batched (num_envs=N): env i permanently belongs to humanoid i % 4 (the reference redraws the humanoid per episode; a fixed
+    assignment keeps the same marginal mix and lets every engine stay homogeneous); everything else as in LocoEnv."""
+
+    def __init__(self, task="walk", dataset_type="real", debug=False, num_envs=None, env_id_offset=0, **kwargs):
+        n = None if num_envs is None else int(num_envs)
+        self.num_envs = 1 if n is None else n
+        self.batched = n is not None
+        self._index = None
+        self.subs = []
+        off = int(env_id_offset)
+        for k in range(4):
+            kw = dict(kwargs)
+            if self.batched:
+                nk = len(range(k, n, 4))
+                if nk == 0:
+                    raise ValueError("mode 'all' needs num_envs >= 4 (one env per humanoid)")
+                kw.update(num_envs=nk, env_id_offset=off)
+                off += nk
+            self.subs.append(HumanoidTorque4Ages._generate4(task, str(k + 1), dataset_type, debug=debug, **kw))
+        self._current_model_idx = 0
+        self.info = self.subs[0].info
+        self.trajectories = None            # per humanoid: self.subs[k].trajectories
+
+    # ---- everything that does not depend on the humanoid comes from the first sub-env ----
+    def __getattr__(self, name):
+        if name in ("subs", "__setstate__"):
+            raise AttributeError(name)
+        return getattr(self.subs[0], name)
+
+    @property
+    def dt(self):
+        return self.subs[0].dt
+
+    def _scatter(self, parts):
+        """Per-humanoid tensors [n_k, ...] -> one tensor in env order (env i = humanoid i % 4, its (i // 4)-th env)."""
+        import torch
+        if self._index is None:
+            order = [i for k in range(4) for i in range(k, self.num_envs, 4)]          # env ids in concatenation order
+            inv = torch.empty(self.num_envs, dtype=torch.long)
+            inv[torch.tensor(order)] = torch.arange(self.num_envs)
+            self._index = inv.to(parts[0].device)
+        return torch.cat(parts, dim=0)[self._index]
+
+    def reset(self, obs=None):
+        if obs is not None:
+            raise TypeError("Initializing the environment from an observation is not allowed in this environment.")
+        if not self.batched:
+            import torch
+            model_no = np.random.randint(0, 4)                                      # base.py:187-191
+            self._current_model_idx = model_no
+            sub = self.subs[model_no]
+            sub._reward_function.reset_state()
+            np.random.randint(model_no, model_no + 1)                               # traj_no within the model's range (one trajectory each)
+            sub.trajectories.reset_trajectory(traj_no=0)                           # draws the sample
+            eng = sub._get_engine()
+            out = eng.reset(traj_no=torch.zeros(1, dtype=torch.int32, device=eng.device),
+                            step_no=torch.tensor([sub.trajectories.subtraj_step_no], dtype=torch.int32, device=eng.device))
+            sub._obs = out[0].double().cpu().numpy()
+            return sub._obs.copy()
+        return self._scatter([s.reset() for s in self.subs])
+
+    def step(self, action):
+        if not self.batched:
+            return self.subs[self._current_model_idx].step(action)
+        outs = [s.step(action[k::4].contiguous()) for k, s in enumerate(self.subs)]
+        obs, rew, done = (self._scatter([o[j] for o in outs]) for j in range(3))
+        return obs, rew, done, {"next_obs": self._scatter([o[3]["next_obs"] for o in outs])}
+
+    def create_dataset(self, ignore_keys=None):
+        """The four humanoids' datasets, concatenated in scaling order (the layout of the reference's `_all` dataset)."""
+        parts = [s.create_dataset(ignore_keys=ignore_keys) for s in self.subs]
+        return {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+
+    def stop(self):
+        pass

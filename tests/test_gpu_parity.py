@@ -40,6 +40,45 @@ def test_dropin_single_env_reproduces_reference_golden(bundled_only, task):
     assert np.allclose(rows, g, rtol=5e-3, atol=5e-3), "max abs err %.3e" % np.abs(rows - g).max()
 
 
+@pytest.mark.parametrize("task", ["walk", "run"])
+def test_dropin_4ages_all_reproduces_reference_golden(bundled_only, task):
+    """HumanoidTorque4Ages mode "all" through the drop-in API (composite of four engines; see test_oracle_golden.py for run.all)."""
+    g = golden("HumanoidTorque4Ages.%s.all" % task)
+    np.random.seed(0)
+    env = make_env("HumanoidTorque4Ages.%s.all" % task)
+    rows = [env.reset()]
+    absorbing = False
+    while not absorbing and len(rows) < 1001:
+        obs, reward, absorbing, info = env.step(np.random.randn(env.info.action_space.shape[0]) * 0.1)
+        rows.append(obs)
+    rows = np.array(rows)
+    assert np.abs(rows[0] - g[0]).max() < 1e-6
+    assert rows.shape == g.shape, "done-flag timing differs from the golden (len %d vs %d)" % (len(rows), len(g))
+    tol = 5e-3 if task == "walk" else 2e-2
+    assert np.allclose(rows, g, rtol=tol, atol=tol), "max abs err %.3e" % np.abs(rows - g).max()
+
+
+def test_4ages_all_batched(bundled_only):
+    """Batched mode "all": env i is humanoid i % 4 (its 2-bit id is observed) and behaves like the same env of the single-
+    scaling batch it belongs to."""
+    n = 20
+    env = make_env("HumanoidTorque4Ages.walk.all", num_envs=n, seed=2)
+    obs = env.reset()
+    assert tuple(obs.shape) == (n, 38)
+    ids = (obs[:, -2] * 2 + obs[:, -1]).long().cpu().numpy()
+    assert list(ids) == [i % 4 for i in range(n)]
+    solo = make_env("HumanoidTorque4Ages.walk.3", num_envs=5, seed=2, env_id_offset=10)     # humanoid 2 owns envs 2, 6, 10, 14, 18
+    o_solo = solo.reset()
+    assert torch.equal(obs[2::4], o_solo)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    for _ in range(6):
+        a = (torch.rand((n, 13), generator=g) * 2 - 1).cuda()
+        obs, rew, done, info = env.step(a)
+        o2, r2, d2, i2 = solo.step(a[2::4].contiguous())
+        assert torch.equal(obs[2::4], o2) and torch.equal(rew[2::4], r2) and torch.equal(done[2::4], d2)
+        assert torch.equal(info["next_obs"][2::4], i2["next_obs"])
+
+
 def test_gymnasium_wrapper_contract(bundled_only):
     from loco_mujoco_b200 import make_gym
     np.random.seed(0)
