@@ -502,7 +502,7 @@ int locosim_create(const int32_t* mi, int nmi, const double* mr, int nmr, const 
   h->st.pool = h->d_pool; h->st.pool_K = 1;
   bind_model(h->dm, h->hm, h->d_mints, h->d_mreals);
   for (int k = 0; k < LS_MAX_SLOTS && h->slot < 0; k++) if (!g_slot_used[k]) { h->slot = k; g_slot_used[k] = true; }
-  if (h->slot < 0) { locosim_destroy(h); g_create_error = "too many live locosim handles (max 8 per process)"; return 1; }
+  if (h->slot < 0) { locosim_destroy(h); g_create_error = "too many live locosim handles (max 16 per process)"; return 1; }
   if (cudaMemcpyToSymbol(c_models, &h->dm, sizeof(DevModel), sizeof(DevModel) * h->slot) != cudaSuccess) {
     g_create_error = std::string("cudaMemcpyToSymbol: ") + cudaGetErrorString(cudaGetLastError()); locosim_destroy(h); return 1;
   }

@@ -127,8 +127,8 @@ struct DevTask {
 };
 
 
-// Model descriptors live in __constant__ memory (8 slots, one per live handle): every warp reads them uniformly.
-#define LS_MAX_SLOTS 8
+// Model descriptors live in __constant__ memory (16 slots, one per live handle): every warp reads them uniformly.
+#define LS_MAX_SLOTS 16
 #ifdef LS_EMULATE
 static DevModel c_models[LS_MAX_SLOTS];
 static int c_debug = 0;

@@ -142,8 +142,14 @@ def test_humanoid_4ages_modes(bundled_only):
     env = make_env("HumanoidTorque4Ages.run.2")
     assert env._model_user_features == [(0.0, 1.0)] and env.info.observation_space.shape == (38,)
     assert abs(env._reward_params["target_velocity"] - 2.5 * 0.6) < 1e-12      # MultiTargetVelocityReward: target x scaling
-    with pytest.raises(NotImplementedError):
-        make_env("HumanoidTorque4Ages.run.all")
+    # mode "all": a composite of the four single-scaling envs (one engine each, created lazily)
+    env = make_env("HumanoidTorque4Ages.run.all")
+    assert type(env).__name__ == "HumanoidTorque4AgesAll" and len(env.subs) == 4 and not env.batched
+    assert env.info.observation_space.shape == (38,) and env.info.action_space.shape == (13,)
+    assert [s._model_user_features[0] for s in env.subs] == [(0.0, 0.0), (0.0, 1.0), (1.0, 0.0), (1.0, 1.0)]
+    assert sum(len(s.create_dataset()["states"]) for s in env.subs) == len(env.create_dataset()["states"])
+    with pytest.raises(ValueError):
+        make_env("HumanoidTorque4Ages.run.all", num_envs=3)
 
 
 def test_vector_wrapper_spaces(bundled_only):
