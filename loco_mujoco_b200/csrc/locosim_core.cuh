@@ -1241,6 +1241,51 @@ LS_FN void fill_contact(const int ms, EnvS<C>& e, const int ci, int g1, int g2, 
   }
 }
 
+// mjc_BoxBox, edge-edge branch (restated and pinned in oracle/locosim_ref.c box_box_edge: the reference golden
+// HumanoidTorque4Ages.run.all): when the separating axis of least overlap is the cross product of an edge of each box, the
+// contact is the midpoint of the closest points of those two edges. Returns 1 (contact in r[0..6]: dist, pos, normal),
+// 0 (separated by more than the margin) or -1 (a face axis separates best, or a vertex is involved: caller falls back to MPR).
+// Every lane computes the same thing (a few hundred flops, box-box pairs are rare: the humanoids' two feet).
+LS_DEV int box_box_edge(float margin, const float* p1, const float* m1, const float* s1, const float* p2, const float* m2,
+                        const float* s2, float* r) {
+  float A[3][3], B[3][3];
+  const float d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { A[i][k] = m1[3 * k + i]; B[i][k] = m2[3 * k + i]; }
+  float best = -3.0e38f, bn[3] = {0, 0, 0};
+  int bi = -1, bj = -1;
+  for (int f = 0; f < 6; f++) {
+    const float* ax = f < 3 ? A[f] : B[f - 3];
+    float ra = 0, rb = 0;
+    for (int i = 0; i < 3; i++) { ra += s1[i] * fabsf(dot3(A[i], ax)); rb += s2[i] * fabsf(dot3(B[i], ax)); }
+    const float sep = fabsf(dot3(d, ax)) - ra - rb;
+    if (sep > best) { best = sep; bi = -1; bj = f; }
+  }
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    float ax[3];
+    cross3(ax, A[i], B[j]);
+    const float l2 = dot3(ax, ax);
+    if (l2 < 1e-12f) continue;
+    const float il = rsqrtf(l2);
+    for (int k = 0; k < 3; k++) ax[k] *= il;
+    float ra = 0, rb = 0;
+    for (int k = 0; k < 3; k++) { ra += s1[k] * fabsf(dot3(A[k], ax)); rb += s2[k] * fabsf(dot3(B[k], ax)); }
+    const float sd = dot3(d, ax), sep = fabsf(sd) - ra - rb;
+    if (sep > best + 1e-7f) { best = sep; bi = i; bj = j; for (int k = 0; k < 3; k++) bn[k] = sd >= 0 ? ax[k] : -ax[k]; }
+  }
+  if (bi < 0) return -1;
+  if (best > margin) return 0;
+  float e1[3] = {p1[0], p1[1], p1[2]}, e2[3] = {p2[0], p2[1], p2[2]};
+  for (int i = 0; i < 3; i++) if (i != bi) { const float sg = dot3(A[i], bn) >= 0 ? s1[i] : -s1[i]; for (int k = 0; k < 3; k++) e1[k] += sg * A[i][k]; }
+  for (int j = 0; j < 3; j++) if (j != bj) { const float sg = dot3(B[j], bn) >= 0 ? -s2[j] : s2[j]; for (int k = 0; k < 3; k++) e2[k] += sg * B[j][k]; }
+  const float rr[3] = {e1[0] - e2[0], e1[1] - e2[1], e1[2] - e2[2]};
+  const float b = dot3(A[bi], B[bj]), cc = dot3(A[bi], rr), f = dot3(B[bj], rr), den = 1.0f - b * b;
+  const float t = (b * f - cc) / den, u = (f - b * cc) / den;
+  if (fabsf(t) > s1[bi] || fabsf(u) > s2[bj]) return -1;
+  r[0] = best;
+  for (int k = 0; k < 3; k++) { r[1 + k] = 0.5f * ((e1[k] + t * A[bi][k]) + (e2[k] + u * B[bj][k])); r[4 + k] = bn[k]; }
+  return 1;
+}
+
 // warp-cooperative narrow phase of one convex pair (mjc_Convex): at most one contact.
 // The pair belongs to env `o` (geom frames, separating-direction cache: read only); the executing warp's own env `e` only
 // lends its contact-Jacobian storage as scratch. On the GPU the warps of a block SHARE these jobs (collision()): a lone
@@ -1284,6 +1329,14 @@ LS_FN void convex_job(const int ms, const EnvS<C>& o, EnvS<C>& e, int p, float* 
     for (int k = 0; k < 9; k++) { a.mat[k] = m1[k]; b.mat[k] = m2[k]; }
   }
   SYNC();
+  if (t1 == LS_GEOM_BOX && t2 == LS_GEOM_BOX) {        // mjc_BoxBox: the edge-edge branch is exact, the rest falls through to MPR
+    float rb[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int nb = box_box_edge(margin, o.gxpos[g1], m1, m.geom_size + 3 * g1, o.gxpos[g2], m2, m.geom_size + 3 * g2, rb);
+    if (nb >= 0) {
+      LANE0 { for (int k = 0; k < 7; k++) res[k] = rb[k]; res[7] = nb > 0 ? 1.0f : 3.0f; }      // (3: nothing to record)
+      return;
+    }
+  }
   float depth, dir[3], pos[3], sep[3] = {0, 0, 0};
   // A direction that separated this pair in an earlier evaluation of the control step is tried first (ONE support pair,
   // straight from the model's vertex arrays: nothing is staged for it; strict separation of the inflated geoms along it

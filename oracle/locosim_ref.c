@@ -864,6 +864,58 @@ static int convex_pair(RawCon* c, const RefSim* s, int g1, int g2, double margin
   return 1;
 }
 
+/* mjc_BoxBox, edge-edge branch. MuJoCo's dedicated box-box routine (engine_collision_box.c, not under /root/reference) is a
+ * separating-axis test over the 15 axes of two boxes; when the axis of least overlap (largest separation) is the cross
+ * product of an edge of each box, the contact is ONE point: the midpoint of the closest points of the two edges, normal along
+ * the axis, dist = separation. That case is geometrically unique and restated here; it is pinned by the reference golden
+ * HumanoidTorque4Ages.run.all (row 9: the infant's foot boxes pass each other edge to edge, 0.17 mm apart inside the 1 mm
+ * margin; MPR gets dist and normal right to 1e-7 but its contact POSITION is off by up to 1.6 mm there).
+ * Face / vertex cases (several contact points in MuJoCo) return -1: the caller falls back to the MPR stand-in. */
+static int box_box_edge(RawCon* c, double margin, const double* p1, const double* m1, const double* s1, const double* p2,
+                        const double* m2, const double* s2) {
+  double A[3][3], B[3][3], d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { A[i][k] = m1[3 * k + i]; B[i][k] = m2[3 * k + i]; }   /* box axes = columns */
+  double best = -1e300; int bi = -1, bj = -1; double bn[3] = {0, 0, 0};
+  /* face axes */
+  for (int f = 0; f < 6; f++) {
+    const double* ax = f < 3 ? A[f] : B[f - 3];
+    double ra = 0, rb = 0;
+    for (int i = 0; i < 3; i++) { ra += s1[i] * fabs(dot3(A[i], ax)); rb += s2[i] * fabs(dot3(B[i], ax)); }
+    double sep = fabs(dot3(d, ax)) - ra - rb;
+    if (sep > best) { best = sep; bi = -1; bj = f; }
+  }
+  /* edge x edge axes */
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    double ax[3];
+    cross3(ax, A[i], B[j]);
+    double l = norm3(ax);
+    if (l < 1e-6) continue;                                   /* parallel edges: covered by the face axes */
+    for (int k = 0; k < 3; k++) ax[k] /= l;
+    double ra = 0, rb = 0;
+    for (int k = 0; k < 3; k++) { ra += s1[k] * fabs(dot3(A[k], ax)); rb += s2[k] * fabs(dot3(B[k], ax)); }
+    double sd = dot3(d, ax), sep = fabs(sd) - ra - rb;
+    if (sep > best + 1e-12) { best = sep; bi = i; bj = j; for (int k = 0; k < 3; k++) bn[k] = sd >= 0 ? ax[k] : -ax[k]; }
+  }
+  if (bi < 0) return -1;                                       /* a face axis separates best: not the edge-edge case */
+  if (best > margin) return 0;
+  /* the two edges: on box 1 the edge along A[bi] that is extreme along +n in the other two axes, on box 2 along B[bj], extreme along -n */
+  double e1[3], e2[3];
+  for (int k = 0; k < 3; k++) { e1[k] = p1[k]; e2[k] = p2[k]; }
+  for (int i = 0; i < 3; i++) if (i != bi) { double sg = dot3(A[i], bn) >= 0 ? 1.0 : -1.0; for (int k = 0; k < 3; k++) e1[k] += sg * s1[i] * A[i][k]; }
+  for (int j = 0; j < 3; j++) if (j != bj) { double sg = dot3(B[j], bn) >= 0 ? -1.0 : 1.0; for (int k = 0; k < 3; k++) e2[k] += sg * s2[j] * B[j][k]; }
+  /* closest points of the lines e1 + t A[bi], e2 + u B[bj] */
+  double r[3] = {e1[0] - e2[0], e1[1] - e2[1], e1[2] - e2[2]};
+  double b = dot3(A[bi], B[bj]), cc = dot3(A[bi], r), f = dot3(B[bj], r), den = 1.0 - b * b;
+  double t = (b * f - cc) / den, u = (f - b * cc) / den;
+  if (fabs(t) > s1[bi] || fabs(u) > s2[bj]) return -1;        /* closest points off the edges: a vertex is involved */
+  double c1[3], c2[3];
+  for (int k = 0; k < 3; k++) { c1[k] = e1[k] + t * A[bi][k]; c2[k] = e2[k] + u * B[bj][k]; }
+  c->dist = best;
+  memset(c->frame, 0, sizeof(c->frame));
+  for (int k = 0; k < 3; k++) { c->frame[k] = bn[k]; c->pos[k] = 0.5 * (c1[k] + c2[k]); }
+  return 1;
+}
+
 static void make_frame(double* f) {
   /* mju_makeFrame: normal given in f[0:3]; tangent f[3:6] optional */
   normalize3(f);
@@ -950,10 +1002,13 @@ static void collision(RefSim* s) {
     } else {
       /* every other pair: mjc_Convex (MPR), one contact -- MuJoCo 2.3.7's collision table routes sphere | capsule |
          cylinder | box | mesh against cylinder | mesh there (and ellipsoids, which no in-scope model has).
-         DEVIATION: capsule-box and box-box have dedicated multi-contact routines in MuJoCo (mjc_CapsuleBox, mjc_BoxBox,
-         not restated); they also go through MPR here: ONE contact at the deepest point instead of up to 2 / 8
+         DEVIATION: capsule-box and box-box have dedicated multi-contact routines in MuJoCo (mjc_CapsuleBox, mjc_BoxBox);
+         only the edge-edge branch of mjc_BoxBox is restated (box_box_edge, golden-pinned); everything else of these two
+         goes through MPR here: ONE contact at the deepest point instead of up to 2 / 8
          (mjcf.py counts them in Model.n_approx_pairs; A1 trunk vs legs, the humanoid's two foot boxes). */
-      n = convex_pair(raw, s, g1, g2, margin);
+      n = -1;
+      if (t1 == LS_GEOM_BOX && t2 == LS_GEOM_BOX) n = box_box_edge(raw, margin, pos1, mat1, size1, pos2, mat2, size2);
+      if (n < 0) n = convex_pair(raw, s, g1, g2, margin);
     }
     for (int k = 0; k < n && s->ncon < MAXCON; k++) {
       Contact* c = &s->con[s->ncon++];

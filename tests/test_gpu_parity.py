@@ -54,7 +54,7 @@ def test_dropin_4ages_all_reproduces_reference_golden(bundled_only, task):
     rows = np.array(rows)
     assert np.abs(rows[0] - g[0]).max() < 1e-6
     assert rows.shape == g.shape, "done-flag timing differs from the golden (len %d vs %d)" % (len(rows), len(g))
-    tol = 5e-3 if task == "walk" else 2e-2
+    tol = 5e-3
     assert np.allclose(rows, g, rtol=tol, atol=tol), "max abs err %.3e" % np.abs(rows - g).max()
 
 

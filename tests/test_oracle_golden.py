@@ -37,10 +37,10 @@ def test_oracle_reproduces_reference_golden(oracle, bundled_only, task):
 def test_oracle_reproduces_4ages_all_goldens(oracle, bundled_only, task):
     """HumanoidTorque4Ages mode "all" (four humanoids in one env): draws of the reference's reset - model (base.py:187-191),
     trajectory within the model's range (base_humanoid_4_ages.py:132-136), sample - then the drawn humanoid's oracle.
-    walk.all is reproduced to 1e-13 over the whole episode. run.all is THE golden that reaches `mjc_BoxBox`: in row 9 the
-    infant's two foot boxes touch in flight (dist 1.7e-4 inside the margin); MuJoCo's dedicated multi-contact box-box routine
-    is not restated (such pairs go through MPR, one contact), which shows as 5.8e-3 in that row's
-    velocities, decaying afterwards; rows 0-8 are exact and the episode length is the golden's."""
+    Both are reproduced to 1e-13 over the whole episode. run.all is THE golden that reaches `mjc_BoxBox`: in row 9 the infant's
+    two foot boxes pass each other edge to edge, 0.17 mm apart inside the 1 mm margin. That branch of MuJoCo's box-box routine
+    (one contact at the midpoint of the closest points of the two edges) is restated exactly (`box_box_edge`); with the general
+    convex routine alone (MPR: dist and normal right to 1e-7, contact POSITION up to 1.6 mm off) the row was 5.8e-3 off."""
     g = golden("HumanoidTorque4Ages.%s.all" % task)
     np.random.seed(0)
     model_no = np.random.randint(0, 4)
@@ -55,11 +55,7 @@ def test_oracle_reproduces_4ages_all_goldens(oracle, bundled_only, task):
         rows.append(obs)
     rows = np.array(rows)
     assert rows.shape == g.shape, "episode length (done-flag timing) differs from the golden"
-    if task == "walk":
-        assert np.allclose(rows, g), "max abs err %.3e" % np.abs(rows - g).max()
-    else:
-        assert np.allclose(rows[:9], g[:9]), "max abs err %.3e" % np.abs(rows[:9] - g[:9]).max()
-        assert np.abs(rows - g).max() < 1e-2          # measured 5.8e-3 (box-box stand-in)
+    assert np.allclose(rows, g), "max abs err %.3e" % np.abs(rows - g).max()
 
 
 def test_oracle_rollout_threads_deterministic(oracle, bundled_only):
