@@ -342,9 +342,17 @@ static bool has_convex_pairs(const HostModel& hm) {
     if (v.pair_packed[p] & (2 << 24)) return true;
   return false;
 }
+static bool has_boxbox_pairs(const HostModel& hm) {
+  DevModel v;
+  bind_model(v, hm, hm.ints.data(), hm.reals.data());
+  for (int p = 0; p < hm.np; p++)
+    if (v.geom_type[v.pair_geom[2 * p]] == LS_GEOM_BOX && v.geom_type[v.pair_geom[2 * p + 1]] == LS_GEOM_BOX) return true;
+  return false;
+}
 template <class C>
 static bool cfg_fits(const HostModel& hm, const HostTask& ht) {
   if (!C::CONVEX && has_convex_pairs(hm)) return false;
+  if (!C::BOXBOX && has_boxbox_pairs(hm)) return false;
   return hm.nv <= C::NV && hm.nb <= C::NB && hm.ng <= C::NG && ht.obs_dim <= C::MAXOBS && hm.cone == (int)C::CONE &&
          hm.integrator == (int)C::RK4;
 }

@@ -1329,7 +1329,7 @@ LS_FN void convex_job(const int ms, const EnvS<C>& o, EnvS<C>& e, int p, float* 
     for (int k = 0; k < 9; k++) { a.mat[k] = m1[k]; b.mat[k] = m2[k]; }
   }
   SYNC();
-  if (t1 == LS_GEOM_BOX && t2 == LS_GEOM_BOX) {        // mjc_BoxBox: the edge-edge branch is exact, the rest falls through to MPR
+  if (C::BOXBOX && t1 == LS_GEOM_BOX && t2 == LS_GEOM_BOX) {        // mjc_BoxBox: the edge-edge branch is exact, the rest falls through to MPR
     float rb[7] = {0, 0, 0, 0, 0, 0, 0};
     const int nb = box_box_edge(margin, o.gxpos[g1], m1, m.geom_size + 3 * g1, o.gxpos[g2], m2, m.geom_size + 3 * g2, rb);
     if (nb >= 0) {

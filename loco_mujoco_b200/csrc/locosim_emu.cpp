@@ -66,6 +66,14 @@ struct EmuT : EmuBase {
   void bind_prm() override { e.prm = hm.default_row.data(); e.pk_tab = m.pair_packed; c_models[0] = m; init_workspace(0, e); }
 };
 
+static bool emu_has_boxbox(const HostModel& hm) {
+  DevModel v;
+  bind_model(v, hm, hm.ints.data(), hm.reals.data());
+  for (int p = 0; p < hm.np; p++)
+    if (v.geom_type[v.pair_geom[2 * p]] == LS_GEOM_BOX && v.geom_type[v.pair_geom[2 * p + 1]] == LS_GEOM_BOX) return true;
+  return false;
+}
+
 extern "C" {
 EmuBase* emu_create(const int* ints, int n_ints, const double* reals, int n_reals) {
   HostModel hm;
@@ -73,7 +81,7 @@ EmuBase* emu_create(const int* ints, int n_ints, const double* reals, int n_real
   if (!err.empty()) { fprintf(stderr, "emu: %s\n", err.c_str()); return nullptr; }
   EmuBase* s;
   if (hm.cone == 1 && hm.integrator == 0) s = new EmuT<CfgEllEuler>();
-  else if (hm.cone == 0 && hm.integrator == 0 && hm.nv > 18) s = new EmuT<CfgPyrEuler29>();
+  else if (hm.cone == 0 && hm.integrator == 0 && (hm.nv > 18 || emu_has_boxbox(hm))) s = new EmuT<CfgPyrEuler29>();   // (as cfg_fits in locosim.cu)
   else if (hm.cone == 0 && hm.integrator == 0) s = new EmuT<CfgPyrEuler>();
   else if (hm.cone == 0 && hm.integrator == 1) s = new EmuT<CfgPyrRK4>();
   else { fprintf(stderr, "emu: no config\n"); return nullptr; }

@@ -5,11 +5,10 @@ cp loco_mujoco_b200/liblocosim_cuda.so /tmp/keep.so
 for rep in 1 2; do
 for V in scratch/variants/*.so; do
   cp $V loco_mujoco_b200/liblocosim_cuda.so
-  for T in HumanoidTorque.run Atlas.walk; do
+  for T in ${TASKS:-HumanoidTorque.run Atlas.walk UnitreeA1.simple}; do
     python bench.py --task $T --steps 40 --warmup 5 --no-configs --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('$V $T %.0f %.3f' % (d['value'], d['kernel_ms_per_step']))" | tee -a $O
   done
-  python tools/cfg4_probe.py 2>&1 | grep "flush" | head -2 | sed "s|^|$V cfg4 |" | tee -a $O
 done
 done
 cp /tmp/keep.so loco_mujoco_b200/liblocosim_cuda.so
