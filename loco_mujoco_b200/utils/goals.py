@@ -1,26 +1,31 @@
-"""Goal container for goal-conditioned envs (reference: utils/goals.py:4-28)."""
-from copy import deepcopy
+"""Goal container of the goal-conditioned envs (UnitreeA1: desired direction + speed).
+
+Same public surface as the reference's helper (/root/reference/loco_mujoco/utils/goals.py): `set_goal`, `get_goal`,
+`get_direction`, `get_velocity`, call = `get_goal`; values are handed out as copies."""
+import copy
 
 
 class GoalDirectionVelocity:
+    __slots__ = ("_goal",)
+
     def __init__(self):
-        self._direction = None
-        self._velocity = None
-
-    def __call__(self):
-        return self.get_goal()
-
-    def get_goal(self):
-        assert self._direction is not None and self._velocity is not None
-        return deepcopy(self._direction), deepcopy(self._velocity)
+        self._goal = {}
 
     def set_goal(self, direction, velocity):
-        self._direction, self._velocity = direction, velocity
+        self._goal = {"direction": direction, "velocity": velocity}
+
+    def _get(self, key):
+        if key not in self._goal or self._goal[key] is None:
+            raise AssertionError("goal %s has not been set" % key)
+        return copy.deepcopy(self._goal[key])
 
     def get_direction(self):
-        assert self._direction is not None
-        return deepcopy(self._direction)
+        return self._get("direction")
 
     def get_velocity(self):
-        assert self._velocity is not None
-        return deepcopy(self._velocity)
+        return self._get("velocity")
+
+    def get_goal(self):
+        return self.get_direction(), self.get_velocity()
+
+    __call__ = get_goal
