@@ -916,6 +916,21 @@ static int box_box_edge(RawCon* c, double margin, const double* p1, const double
   return 1;
 }
 
+/* test entry points of the pair routines (tests/test_collision_pairs.py): out = dist, pos[3], normal[3] */
+int ref_debug_box_box_edge(double margin, const double* p1, const double* m1, const double* s1, const double* p2, const double* m2,
+                           const double* s2, double* out) {
+  RawCon c;
+  int n = box_box_edge(&c, margin, p1, m1, s1, p2, m2, s2);
+  if (n > 0) { out[0] = c.dist; for (int k = 0; k < 3; k++) { out[1 + k] = c.pos[k]; out[4 + k] = c.frame[k]; } }
+  return n;
+}
+int ref_debug_sphere_box(double margin, const double* p1, double r, const double* p2, const double* m2, const double* s2, double* out) {
+  RawCon c;
+  int n = sphere_box(&c, margin, p1, r, p2, m2, s2);
+  if (n > 0) { out[0] = c.dist; for (int k = 0; k < 3; k++) { out[1 + k] = c.pos[k]; out[4 + k] = c.frame[k]; } }
+  return n;
+}
+
 static void make_frame(double* f) {
   /* mju_makeFrame: normal given in f[0:3]; tangent f[3:6] optional */
   normalize3(f);

@@ -149,3 +149,114 @@ def test_cuda_engine_follows_oracle_on_the_synthetic_pairs(oracle, gtype, tilt, 
         for j, i in enumerate(range(0, N, 4)):
             worst = max(worst, float(np.abs(o[i, :nv] - refs[j][k, :nv]).max()))
     assert worst < 3e-3, worst
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the restated pair routines against brute-force geometry (oracle entry points ref_debug_*; no simulation involved)
+# ----------------------------------------------------------------------------------------------------------------------
+def _rand_rot(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _box_edges(p, R, s):
+    import itertools
+    V = {sg: p + R @ (np.array(sg) * s) for sg in itertools.product([-1, 1], repeat=3)}
+    E = []
+    for sg in V:
+        for ax in range(3):
+            if sg[ax] == -1:
+                o = list(sg)
+                o[ax] = 1
+                E.append((V[sg], V[tuple(o)]))
+    return list(V.values()), E
+
+
+def _seg_seg(p1, q1, p2, q2):
+    d1, d2, r = q1 - p1, q2 - p2, p1 - p2
+    a, e, f, c, b = d1 @ d1, d2 @ d2, d2 @ r, d1 @ r, d1 @ d2
+    den = a * e - b * b
+    s = float(np.clip((b * f - c * e) / den, 0, 1)) if den > 1e-15 else 0.0
+    t = (b * s + f) / e
+    if t < 0:
+        t, s = 0.0, float(np.clip(-c / a, 0, 1))
+    elif t > 1:
+        t, s = 1.0, float(np.clip((b - c) / a, 0, 1))
+    c1, c2 = p1 + d1 * s, p2 + d2 * t
+    return np.linalg.norm(c1 - c2), c1, c2
+
+
+def _pt_box(x, p, R, s):
+    loc = R.T @ (x - p)
+    c = np.clip(loc, -s, s)
+    return np.linalg.norm(loc - c), p + R @ c
+
+
+def test_box_box_edge_branch_is_the_exact_closest_feature(oracle):
+    """Whenever `box_box_edge` claims a pair (separated boxes whose closest features are two edges), its dist / position /
+    normal are those of the brute-force closest points over all 144 edge pairs and 16 vertex-box pairs."""
+    lib = oracle.lib
+    lib.ref_debug_box_box_edge.restype = ctypes.c_int
+    lib.ref_debug_box_box_edge.argtypes = [ctypes.c_double] + [ctypes.c_void_p] * 7
+    rng = np.random.default_rng(0)
+    claimed = 0
+    for trial in range(4000):
+        s1, s2 = rng.uniform(0.02, 0.2, 3), rng.uniform(0.02, 0.2, 3)
+        R1, R2 = _rand_rot(rng), _rand_rot(rng)
+        p1 = np.zeros(3)
+        p2 = rng.normal(size=3)
+        p2 *= (np.linalg.norm(s1) + np.linalg.norm(s2)) * rng.uniform(0.5, 1.1) / np.linalg.norm(p2)
+        out = np.zeros(7)
+        n = lib.ref_debug_box_box_edge(0.02, _p(p1), _p(np.ascontiguousarray(R1)), _p(s1), _p(p2), _p(np.ascontiguousarray(R2)), _p(s2), _p(out))
+        VA, EA = _box_edges(p1, R1, s1)
+        VB, EB = _box_edges(p2, R2, s2)
+        best = (1e9, None, None, "")
+        for a0, a1 in EA:
+            for b0, b1 in EB:
+                d, c1, c2 = _seg_seg(a0, a1, b0, b1)
+                if d < best[0] - 1e-12:
+                    best = (d, c1, c2, "edge")
+        for v in VA:
+            d, c = _pt_box(v, p2, R2, s2)
+            if d < best[0] - 1e-9:
+                best = (d, v, c, "vertex")
+        for v in VB:
+            d, c = _pt_box(v, p1, R1, s1)
+            if d < best[0] - 1e-9:
+                best = (d, c, v, "vertex")
+        if n == 1 and out[0] > 1e-6:                      # claimed, separated: must be THE closest feature pair
+            claimed += 1
+            assert best[3] == "edge"
+            assert abs(out[0] - best[0]) < 1e-9, (trial, out[0], best[0])
+            assert np.abs(out[1:4] - 0.5 * (best[1] + best[2])).max() < 1e-8
+            assert np.abs(out[4:7] - (best[2] - best[1]) / best[0]).max() < 1e-6
+        if n == 0:                                        # "farther apart than the margin"
+            assert best[0] > 0.02 - 1e-9
+    assert claimed > 40
+
+
+def test_sphere_box_matches_point_to_box_geometry(oracle):
+    lib = oracle.lib
+    lib.ref_debug_sphere_box.restype = ctypes.c_int
+    lib.ref_debug_sphere_box.argtypes = [ctypes.c_double, ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 4
+    rng = np.random.default_rng(1)
+    hits = 0
+    for trial in range(2000):
+        s2, R2, p2, r = rng.uniform(0.02, 0.2, 3), _rand_rot(rng), rng.normal(size=3) * 0.05, rng.uniform(0.01, 0.1)
+        p1 = p2 + R2 @ (rng.uniform(-1.6, 1.6, 3) * s2)
+        out = np.zeros(7)
+        n = lib.ref_debug_sphere_box(0.01, _p(p1), r, _p(p2), _p(np.ascontiguousarray(R2)), _p(s2), _p(out))
+        d, c = _pt_box(p1, p2, R2, s2)
+        if d < 1e-9:
+            continue                                      # centre inside the box: convention case
+        assert (n == 1) == (d - r <= 0.01), (trial, d - r)
+        if n == 1:
+            hits += 1
+            nrm = (c - p1) / d                            # from the sphere (geom 1) to the box (geom 2)
+            assert abs(out[0] - (d - r)) < 1e-12 and np.abs(out[4:7] - nrm).max() < 1e-9
+            assert np.abs(out[1:4] - (c - nrm * 0.5 * (d - r))).max() < 1e-9      # midway between the two surfaces
+    assert hits > 300
