@@ -706,21 +706,23 @@ LS_FN int plane_mesh(RawCon* c, float margin, const float* pos1, const float* no
   float d[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
   float dist0 = dot3(d, norm);
   int cnt = 0;
-  int taken[4];
+  int taken[3];
   float mind2 = (0.3f * rbound) * (0.3f * rbound);
-  for (int pass = 0; pass < 4; pass++) {
+  // support vertex first, then the next-deepest vertices at least 0.3 rbound away from the FIRST contact only, 3 contacts at
+  // most (oracle/locosim_ref.c plane_mesh: the rule the UnitreeH1.walk / .carry goldens pin)
+  for (int pass = 0; pass < 3; pass++) {
     int best = -1; float bd = 1e30f;
     for (int i = 0; i < nvert; i++) {
       const float* v = verts + 3 * i;
       float dd = dist0 + dot3(nl, v);
       if (dd > margin || dd >= bd) continue;
-      bool ok = true;
-      for (int t = 0; t < cnt; t++) {
-        const float* w = verts + 3 * taken[t];
+      if (cnt > 0) {
+        if (i == taken[0] || (cnt > 1 && i == taken[1])) continue;
+        const float* w = verts + 3 * taken[0];
         float ex = v[0] - w[0], ey = v[1] - w[1], ez = v[2] - w[2];
-        if (ex * ex + ey * ey + ez * ez < mind2) { ok = false; break; }
+        if (ex * ex + ey * ey + ez * ez < mind2) continue;
       }
-      if (ok) { best = i; bd = dd; }
+      best = i; bd = dd;
     }
     if (best < 0) break;
     float vg[3];

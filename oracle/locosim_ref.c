@@ -494,8 +494,12 @@ static int plane_box(RawCon* c, double margin, const double* pos1, const double*
   }
   return cnt;
 }
-/* plane vs convex vertex cloud: deepest vertex first, then up to 3 more vertices within margin that are
- * well separated from the ones already taken (restates the multi-contact intent of mjc_PlaneConvex) */
+/* mjc_PlaneConvex, mesh branch: the support vertex (deepest) first, then the next-deepest vertices within the margin that are
+ * at least 0.3 * rbound away from the FIRST contact (not from each other: two neighbouring sole vertices may both be taken),
+ * 3 contacts at most. MuJoCo walks the hull graph of the mesh from the support vertex (engine_collision_convex.c, not under
+ * /root/reference); this rule was inferred from the reference goldens UnitreeH1.walk / .carry, whose stance rows are reproduced
+ * to 1e-6 by exactly the vertex triple it selects (brute-force search over all triples of the 155 sole vertices near the floor:
+ * that triple 1.2e-7, the next best 1.3e-3), and by no rule that also keeps the later contacts apart (round 1: 1e-2). */
 static int plane_mesh(RawCon* c, double margin, const double* pos1, const double* mat1, const double* pos2,
                       const double* mat2, const double* verts, int nvert, double rbound) {
   double norm[3] = {mat1[2], mat1[5], mat1[8]};
@@ -504,21 +508,21 @@ static int plane_mesh(RawCon* c, double margin, const double* pos1, const double
   double d[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
   double dist0 = dot3(d, norm);
   int cnt = 0;
-  int taken[4];
+  int taken[3];
   double mind2 = (0.3 * rbound) * (0.3 * rbound);
-  for (int pass = 0; pass < 4; pass++) {
+  for (int pass = 0; pass < 3; pass++) {
     int best = -1; double bd = 1e300;
     for (int i = 0; i < nvert; i++) {
       const double* v = verts + 3 * i;
       double dd = dist0 + dot3(nl, v);
       if (dd > margin || dd >= bd) continue;
-      int ok = 1;
-      for (int t = 0; t < cnt; t++) {
-        const double* w = verts + 3 * taken[t];
+      if (cnt > 0) {
+        if (i == taken[0] || (cnt > 1 && i == taken[1])) continue;
+        const double* w = verts + 3 * taken[0];
         double e[3] = {v[0] - w[0], v[1] - w[1], v[2] - w[2]};
-        if (dot3(e, e) < mind2) { ok = 0; break; }
+        if (dot3(e, e) < mind2) continue;
       }
-      if (ok) { best = i; bd = dd; }
+      best = i; bd = dd;
     }
     if (best < 0) break;
     double vg[3];

@@ -15,7 +15,7 @@ import pytest
 
 from helpers import ROOT, FP32_ROWS, golden, make_env
 
-TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "HumanoidTorque.walk", "Atlas.walk", "Talos.walk", "UnitreeG1.run", "UnitreeG1.walk", "HumanoidTorque4Ages.walk.3",
+TASKS = ["UnitreeA1.simple", "UnitreeA1.hard", "HumanoidTorque.run", "HumanoidTorque.walk", "Atlas.walk", "Talos.walk", "UnitreeG1.run", "UnitreeG1.walk", "UnitreeH1.walk", "HumanoidTorque4Ages.walk.3",
          "HumanoidTorque4Ages.run.1"]
 
 
